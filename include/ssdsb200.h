@@ -1,0 +1,143 @@
+/*
+ * ssdsb200.h — C ABI of libssdsb200.so, the B200 (sm_100a) single-shot-detector hot path.
+ *
+ * This is the drop-in boundary for the `ssds._C` extension module that the reference
+ * (ShuangXieIrene/ssds.pytorch @ b5ec682) names but never shipped:
+ *   ssds/modeling/layers/box.py:3-4      commented imports  `from ssds._C import decode, nms`
+ *   ssds/modeling/layers/box.py:419-421  call site  decode_cuda(cls_head, box_head, anchors, stride, threshold, top_n)
+ *   ssds/modeling/layers/box.py:483-485  call site  nms_cuda(scores, boxes, classes, nms, ndetections)
+ *   ssds/utils/export.py:134-139         `hasattr(ssds, "_C")` feature probe
+ * plus the operator surface the same path uses in pure python: generate_anchors (box.py:46-58),
+ * box2delta/delta2box (:61-87), extract_targets/snap_to_anchors_by_iou (:116-226, :362-405),
+ * MultiBoxLoss.forward (ssds/core/criterion.py:43-71) and the conv stack of
+ * ssds/modeling/ssds/ssd.py:42-74 over ssds/modeling/nets/resnet.py:41-56.
+ *
+ * Conventions
+ *  - Plain C: raw DEVICE pointers + sizes + a cudaStream_t (passed as void*); no torch types.
+ *  - The caller owns every buffer, including the workspace (`*_workspace_bytes` tells how much);
+ *    the library never allocates or frees device memory and keeps no mutable global state.
+ *  - Every output is fully written (zero padded exactly like the reference), so no memset is needed.
+ *  - No host synchronisation; all work is enqueued on `stream`; fixed launch shapes
+ *    (CUDA-graph capturable).
+ *  - Return value: 0 on success, negative ssdsb_status otherwise; never throws across the ABI.
+ *    `ssdsb_last_error_string()` gives the detail for the calling thread.
+ *  - All float tensors are contiguous fp32 unless a name says bf16; index outputs are int32.
+ */
+#ifndef SSDSB200_H_
+#define SSDSB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSDSB_API __attribute__((visibility("default")))
+
+typedef enum {
+  SSDSB_OK = 0,
+  SSDSB_ERR_INVALID_ARGUMENT = -1, /* maps to ValueError in the python shim            */
+  SSDSB_ERR_WORKSPACE = -2,        /* workspace too small / NULL                        */
+  SSDSB_ERR_CUDA = -3,             /* a CUDA runtime/driver call or a launch failed     */
+  SSDSB_ERR_UNSUPPORTED = -4       /* valid request outside what the kernels implement  */
+} ssdsb_status;
+
+#define SSDSB_MAX_LEVELS 8
+
+SSDSB_API int ssdsb_version(void);
+SSDSB_API const char* ssdsb_last_error_string(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Anchors ("PriorBox").  reference: box.py:46-58 generate_anchors, grid add box.py:151-159.
+ * ------------------------------------------------------------------------------------------- */
+/* Base anchors [A,4], A = n_ratios*n_scales, scale-major / ratio-minor, round-half-even. */
+SSDSB_API int ssdsb_generate_anchors(int stride, const float* h_ratios, int n_ratios,
+                                     const float* h_scales, int n_scales,
+                                     float* d_out /*[A,4]*/, void* stream);
+/* Materialised grid in the reference's order [A, W, H, 4] (x-major, box.py:151-159). */
+SSDSB_API int ssdsb_anchor_grid(const float* d_base /*[A,4]*/, int A, int stride, int W, int H,
+                                float* d_out /*[A,W,H,4]*/, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Box codec.  reference: box2delta box.py:61-71 ("encode"), delta2box box.py:74-87 ("decode").
+ * ------------------------------------------------------------------------------------------- */
+SSDSB_API int ssdsb_box2delta(const float* d_boxes, const float* d_anchors, int n,
+                              float* d_out /*[n,4]*/, void* stream);
+SSDSB_API int ssdsb_delta2box(const float* d_deltas, const float* d_anchors, int n, int size_w,
+                              int size_h, int stride, float* d_out /*[n,4]*/, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * decode: threshold + top-k + index->(a,c,y,x) + loc gather + delta2box + clamp + centerness
+ * rescore.  reference: box.py:408-477 (per level) and decoder.py:36-48 (all levels, concatenated
+ * along dim 1 in level order, each level padded to top_n).
+ * Ties between equal scores are broken by ascending flat index (the reference leaves it to
+ * torch.topk).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* conf;    /* [B, A*C, H, W] scores (already sigmoid-ed), channel = a*C + c */
+  const float* loc;     /* [B, A*4, H, W] deltas, channel = a*4 + k                      */
+  const float* anchors; /* [A, 4] base anchors (device)                                  */
+  int A, C, H, W, stride;
+} ssdsb_level;
+
+SSDSB_API size_t ssdsb_decode_workspace_bytes(const ssdsb_level* levels, int n_levels, int B,
+                                              int top_n);
+SSDSB_API int ssdsb_decode(const ssdsb_level* levels, int n_levels, int B, float threshold,
+                           int top_n, int rescore,
+                           float* d_scores /*[B, L*top_n]*/, float* d_boxes /*[B, L*top_n, 4]*/,
+                           float* d_classes /*[B, L*top_n]*/,
+                           int32_t* d_index /*[B, L*top_n] flat index in the level, -1 pad; may be NULL*/,
+                           void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * nms: batched, class-aware (D)IoU NMS with the reference's exact arithmetic
+ * (+1 pixel areas, 1e-7 eps, DIoU on top-left corners).  reference: box.py:480-546.
+ * ------------------------------------------------------------------------------------------- */
+SSDSB_API size_t ssdsb_nms_workspace_bytes(int B, int N, int ndetections);
+SSDSB_API int ssdsb_nms(const float* d_scores /*[B,N]*/, const float* d_boxes /*[B,N,4]*/,
+                        const float* d_classes /*[B,N]*/, int B, int N, float nms_threshold,
+                        int ndetections, int using_diou,
+                        float* d_out_scores /*[B,D]*/, float* d_out_boxes /*[B,D,4]*/,
+                        float* d_out_classes /*[B,D]*/,
+                        int32_t* d_out_index /*[B,D] position in the input row, -1 pad; may be NULL*/,
+                        void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * match: IoU arg-max matcher + encode + depth (+ one-hot class target).
+ * reference: extract_targets box.py:362-405 -> snap_to_anchors_by_iou box.py:116-226.
+ * targets [B,T,5] = (x, y, w, h, label), rows with label <= -1 are padding.
+ * d_cls_target may be NULL (fused consumers only need depth).
+ * ------------------------------------------------------------------------------------------- */
+SSDSB_API int ssdsb_match_iou(const float* d_targets /*[B,T,5]*/, int B, int T,
+                              const float* d_base_anchors /*[A,4]*/, int A, int C, int stride,
+                              int H, int W, float match_threshold, float unmatch_threshold,
+                              float center_sampling_radius,
+                              float* d_cls_target /*[B,A,C,H,W] or NULL*/,
+                              float* d_box_target /*[B,A,4,H,W]*/, float* d_depth /*[B,A,1,H,W]*/,
+                              void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * MultiBoxLoss: BCE-with-logits + per-image hard-negative mining.
+ * reference: ssds/core/criterion.py:43-71 (intended per-image semantics).
+ *  - ssdsb_multibox_loss      drop-in: unreduced loss [B,A,C,H,W] from logits + one-hot target.
+ *  - ssdsb_multibox_loss_sum  fused: no materialised target; the class comes from depth
+ *    (depth > 0 => class = depth-1); writes per image sum(loss * (depth >= 0)) and the number of
+ *    positives, i.e. what pipeline_anchor_basic.py:76-82 reduces to.
+ * ------------------------------------------------------------------------------------------- */
+SSDSB_API size_t ssdsb_multibox_loss_workspace_bytes(int B, int A, int C, int H, int W);
+SSDSB_API int ssdsb_multibox_loss(const float* d_logits /*[B,A,C,H,W]*/,
+                                  const float* d_target /*[B,A,C,H,W]*/,
+                                  const float* d_depth /*[B,A,1,H,W]*/, int B, int A, int C, int H,
+                                  int W, int negpos_ratio, float* d_out /*[B,A,C,H,W]*/,
+                                  void* d_workspace, size_t workspace_bytes, void* stream);
+SSDSB_API int ssdsb_multibox_loss_sum(const float* d_logits /*[B,A,C,H,W]*/,
+                                      const float* d_depth /*[B,A,1,H,W]*/, int B, int A, int C,
+                                      int H, int W, int negpos_ratio, float* d_loss_sum /*[B]*/,
+                                      float* d_num_pos /*[B]*/, void* d_workspace,
+                                      size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSDSB200_H_ */

@@ -1,0 +1,102 @@
+"""ctypes binding of libssdsb200.so (the C ABI declared in include/ssdsb200.h).
+
+There is NO fallback: if the shared library is missing or a call fails, this raises.
+PyTorch is used only as the owner of device memory and streams; the library itself has no
+torch dependency and takes raw device pointers.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libssdsb200.so")
+
+SSDSB_MAX_LEVELS = 8
+
+
+class Level(C.Structure):
+    """mirror of `ssdsb_level` (include/ssdsb200.h)."""
+    _fields_ = [("conf", C.c_void_p), ("loc", C.c_void_p), ("anchors", C.c_void_p),
+                ("A", C.c_int), ("C", C.c_int), ("H", C.c_int), ("W", C.c_int),
+                ("stride", C.c_int)]
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m ssds_pytorch_b200.build` "
+            "(or __graft_entry__.build()). There is no CPU/PyTorch fallback for the hot path.")
+    lib = C.CDLL(LIB_PATH)
+    vp, i, f, sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
+    fp = C.POINTER(C.c_float)
+    lp = C.POINTER(Level)
+    sig = {
+        "ssdsb_version": (i, []),
+        "ssdsb_last_error_string": (C.c_char_p, []),
+        "ssdsb_generate_anchors": (i, [i, fp, i, fp, i, vp, vp]),
+        "ssdsb_anchor_grid": (i, [vp, i, i, i, i, vp, vp]),
+        "ssdsb_box2delta": (i, [vp, vp, i, vp, vp]),
+        "ssdsb_delta2box": (i, [vp, vp, i, i, i, i, vp, vp]),
+        "ssdsb_decode_workspace_bytes": (sz, [lp, i, i, i]),
+        "ssdsb_decode": (i, [lp, i, i, f, i, i, vp, vp, vp, vp, vp, sz, vp]),
+        "ssdsb_nms_workspace_bytes": (sz, [i, i, i]),
+        "ssdsb_nms": (i, [vp, vp, vp, i, i, f, i, i, vp, vp, vp, vp, vp, sz, vp]),
+        "ssdsb_match_iou": (i, [vp, i, i, vp, i, i, i, i, i, f, f, f, vp, vp, vp, vp]),
+        "ssdsb_multibox_loss_workspace_bytes": (sz, [i, i, i, i, i]),
+        "ssdsb_multibox_loss": (i, [vp, vp, vp, i, i, i, i, i, i, vp, vp, sz, vp]),
+        "ssdsb_multibox_loss_sum": (i, [vp, vp, i, i, i, i, i, i, vp, vp, vp, sz, vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)          # AttributeError if the .so does not export it
+        fn.restype, fn.argtypes = res, args
+    return lib, sig
+
+
+lib, SIGNATURES = _load()
+
+SSDSB_OK, ERR_INVALID, ERR_WORKSPACE, ERR_CUDA, ERR_UNSUPPORTED = 0, -1, -2, -3, -4
+
+
+def check(rc, what):
+    """Map C status codes to the exception types the reference raises."""
+    if rc == SSDSB_OK:
+        return
+    msg = f"{what}: {lib.ssdsb_last_error_string().decode(errors='replace')}"
+    if rc == ERR_INVALID:
+        raise ValueError(msg)
+    if rc == ERR_UNSUPPORTED:
+        raise NotImplementedError(msg)
+    raise RuntimeError(f"{msg} (status {rc})")
+
+
+def stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def dev_f32(t, device=None):
+    """contiguous fp32 CUDA tensor (no copy if it already is one)."""
+    if not isinstance(t, torch.Tensor):
+        t = torch.as_tensor(t)
+    if device is None:
+        device = t.device if t.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    if not t.is_cuda and not torch.cuda.is_available():
+        raise RuntimeError("ssds_pytorch_b200 needs a CUDA device (B200); no CPU fallback exists")
+    return t.to(device=device, dtype=torch.float32).contiguous()
+
+
+_workspaces = {}
+
+
+def workspace(nbytes, device):
+    """Grow-only per-device scratch buffer owned by the caller side (torch), 256-byte aligned."""
+    key = (device.type, device.index)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws

@@ -1,0 +1,27 @@
+// Error plumbing + version for the C ABI (include/ssdsb200.h).
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace ssdsb {
+
+std::string& last_error() {
+  static thread_local std::string e;
+  return e;
+}
+
+int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  last_error() = buf;
+  return code;
+}
+
+}  // namespace ssdsb
+
+extern "C" int ssdsb_version(void) { return 100; }
+
+extern "C" const char* ssdsb_last_error_string(void) { return ssdsb::last_error().c_str(); }

@@ -1,0 +1,331 @@
+// decode: threshold + per-image/level top-k + index->(a,c,y,x) + loc gather + delta2box + clamp +
+// centerness rescore, for ALL levels of ALL images in two launches.
+//
+// reference: ssds/modeling/layers/box.py:408-477 (per level, python loop over the batch) and
+// ssds/modeling/layers/decoder.py:36-48 (loop over levels + torch.cat along dim 1).
+//
+// B200 design (HBM-bound: every score is read exactly once, 128-bit loads):
+//   kernel 1  decode_select   grid = (slices per image summed over levels, B).  A CTA streams one
+//             slice (<= 64 Ki scores) of one (image, level) score map, keeps a running top-K of
+//             64-bit keys (ordered score << 32 | ~flat_index) in shared memory (bitonic prune) and
+//             shares its K-th key with the other slices of the same map through a global
+//             atomicMax, so late slices reject almost everything with one compare.  Survivors are
+//             packed into a per-(image, level) candidate list.
+//   kernel 2  decode_finalize grid = (L, B).  Merges the candidate list to the exact top-K (same
+//             accumulator), then K threads turn keys into boxes: gather the 4 deltas, add the grid
+//             anchor, delta2box (box.py:74-87), clamp, centerness rescore (box.py:464-471), and
+//             write straight into the concatenated [B, L*K] outputs (zero padded).
+// Order: descending score, ascending flat index among equal scores (torch.topk leaves it open).
+#include "common.cuh"
+
+namespace ssdsb {
+namespace {
+
+constexpr int DEC_NT = 256;
+constexpr int DEC_EPT = 4;                 // one float4 per thread per tile
+constexpr int DEC_TILE = DEC_NT * DEC_EPT; // 1024 scores
+constexpr int DEC_SLICE = 64 * 1024;       // scores per CTA
+constexpr int DEC_MAX_K = 1024;
+
+struct DecodeParams {
+  ssdsb_level lv[SSDSB_MAX_LEVELS];
+  int slice_begin[SSDSB_MAX_LEVELS + 1];  // prefix sum of slices per image
+  int cand_off[SSDSB_MAX_LEVELS + 1];     // prefix sum of candidate capacity per image
+  int n_levels, B, K, cap;
+  float threshold;
+  int rescore;
+};
+
+// workspace layout: [gthr: B*L u64][gcnt: B*L i32 (padded)][cand: B*cand_total u64]
+__device__ __forceinline__ unsigned long long* ws_gthr(void* ws) {
+  return reinterpret_cast<unsigned long long*>(ws);
+}
+__device__ __forceinline__ int* ws_gcnt(void* ws, int B, int L) {
+  return reinterpret_cast<int*>(reinterpret_cast<unsigned long long*>(ws) + (size_t)B * L);
+}
+__device__ __forceinline__ unsigned long long* ws_cand(void* ws, int B, int L) {
+  size_t head = (size_t)B * L * 8 + (((size_t)B * L * 4 + 7) / 8) * 8;
+  return reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(ws) + head);
+}
+
+__global__ void __launch_bounds__(DEC_NT)
+decode_select(const __grid_constant__ DecodeParams p, void* __restrict__ ws) {
+  extern __shared__ __align__(16) unsigned long long buf[];  // [p.cap]
+  __shared__ int s_cnt;
+  __shared__ unsigned long long s_thr;
+
+  const int b = blockIdx.y;
+  int l = 0;
+  while (l + 1 < p.n_levels && (int)blockIdx.x >= p.slice_begin[l + 1]) ++l;
+  const int slice = blockIdx.x - p.slice_begin[l];
+  const ssdsb_level& lv = p.lv[l];
+  const int n = lv.A * lv.C * lv.H * lv.W;
+  const int begin = slice * DEC_SLICE;
+  const int end = min(n, begin + DEC_SLICE);
+  const float* src = lv.conf + (size_t)b * n;
+  const int tid = threadIdx.x;
+  const int L = p.n_levels;
+  unsigned long long* gthr = ws_gthr(ws) + (size_t)b * L + l;
+
+  if (tid == 0) {
+    s_cnt = 0;
+    s_thr = 0ull;
+  }
+  __syncthreads();
+
+  const bool vec_ok = ((n & 3) == 0) && ((reinterpret_cast<uintptr_t>(lv.conf) & 15) == 0);
+  const float thr = p.threshold;
+  const int limit = p.cap - DEC_TILE;
+  int since_sync = 0;
+
+  for (int base = begin; base < end; base += DEC_TILE) {
+    float v[DEC_EPT];
+    const int i0 = base + tid * DEC_EPT;
+    if (vec_ok && i0 + DEC_EPT <= end) {
+      float4 q = __ldcs(reinterpret_cast<const float4*>(src + i0));  // streamed once: evict-first
+      v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+    } else {
+#pragma unroll
+      for (int e = 0; e < DEC_EPT; ++e) v[e] = (i0 + e < end) ? __ldcs(src + i0 + e) : -1.0f;
+    }
+    unsigned long long k[DEC_EPT];
+    bool take[DEC_EPT];
+    const unsigned long long cur = s_thr;
+#pragma unroll
+    for (int e = 0; e < DEC_EPT; ++e) {
+      k[e] = make_key(v[e], (uint32_t)(i0 + e));
+      take[e] = (i0 + e < end) && (v[e] >= thr) && (k[e] > cur);
+    }
+    const int fill = topk_append<DEC_EPT>(buf, &s_cnt, k, take);
+    if (__syncthreads_or(fill > limit)) {
+      topk_prune<DEC_NT>(buf, &s_cnt, &s_thr, p.K);
+      if (tid == 0 && s_cnt >= p.K) {  // publish our K-th key, adopt the best one seen anywhere
+        unsigned long long old = atomicMax(gthr, s_thr);
+        if (old > s_thr) s_thr = old;
+      }
+      __syncthreads();
+      since_sync = 0;
+    } else if (++since_sync == 8) {  // cheap periodic refresh of the shared bound
+      if (tid == 0) {
+        unsigned long long g = *reinterpret_cast<volatile unsigned long long*>(gthr);
+        if (g > s_thr) s_thr = g;
+      }
+      __syncthreads();
+      since_sync = 0;
+    }
+  }
+  topk_prune<DEC_NT>(buf, &s_cnt, &s_thr, p.K);
+  if (tid == 0) {
+    if (s_cnt >= p.K) atomicMax(gthr, s_thr);
+    s_thr = *reinterpret_cast<volatile unsigned long long*>(gthr);
+  }
+  __syncthreads();
+  // emit keys >= the shared bound (the bound itself is somebody's K-th key and must survive)
+  const unsigned long long g = s_thr;
+  const int cnt = s_cnt;
+  __shared__ int s_emit, s_base;
+  if (tid == 0) s_emit = 0;
+  __syncthreads();
+  // buf is sorted descending: the survivors are a prefix
+  int mine = 0;
+  for (int i = tid; i < cnt; i += DEC_NT) mine += (buf[i] >= g) ? 1 : 0;
+  if (mine) atomicAdd(&s_emit, mine);
+  __syncthreads();
+  const int ne = s_emit;
+  if (tid == 0 && ne > 0) s_base = atomicAdd(ws_gcnt(ws, p.B, L) + (size_t)b * L + l, ne);
+  __syncthreads();
+  if (ne > 0) {
+    const int cand_total = p.cand_off[L];
+    unsigned long long* dst =
+        ws_cand(ws, p.B, L) + (size_t)b * cand_total + p.cand_off[l] + s_base;
+    for (int i = tid; i < ne; i += DEC_NT) dst[i] = buf[i];
+  }
+}
+
+__device__ __forceinline__ float clampf_nanprop(float t, float lo, float hi) {
+  // torch.max(m, torch.min(t, M)) — NaN propagates
+  return (t != t) ? t : fmaxf(lo, fminf(t, hi));
+}
+
+__global__ void __launch_bounds__(DEC_NT)
+decode_finalize(const __grid_constant__ DecodeParams p, void* __restrict__ ws,
+                float* __restrict__ out_scores, float* __restrict__ out_boxes,
+                float* __restrict__ out_classes, int32_t* __restrict__ out_index) {
+  extern __shared__ __align__(16) unsigned long long buf[];  // [p.cap]
+  __shared__ int s_cnt;
+  __shared__ unsigned long long s_thr;
+
+  const int l = blockIdx.x, b = blockIdx.y;
+  const int L = p.n_levels, K = p.K;
+  const int tid = threadIdx.x;
+  const ssdsb_level& lv = p.lv[l];
+  const int cand_total = p.cand_off[L];
+  const unsigned long long* cand =
+      ws_cand(ws, p.B, L) + (size_t)b * cand_total + p.cand_off[l];
+  const int ncand = ws_gcnt(ws, p.B, L)[(size_t)b * L + l];
+
+  if (tid == 0) {
+    s_cnt = 0;
+    s_thr = 0ull;
+  }
+  __syncthreads();
+  const int limit = p.cap - DEC_TILE;
+  for (int base = 0; base < ncand; base += DEC_TILE) {
+    unsigned long long k[DEC_EPT];
+    bool take[DEC_EPT];
+    const unsigned long long cur = s_thr;
+#pragma unroll
+    for (int e = 0; e < DEC_EPT; ++e) {
+      int i = base + e * DEC_NT + tid;
+      k[e] = (i < ncand) ? cand[i] : 0ull;
+      take[e] = (i < ncand) && (k[e] > cur);
+    }
+    const int fill = topk_append<DEC_EPT>(buf, &s_cnt, k, take);
+    if (__syncthreads_or(fill > limit)) topk_prune<DEC_NT>(buf, &s_cnt, &s_thr, K);
+  }
+  topk_prune<DEC_NT>(buf, &s_cnt, &s_thr, K);
+  const int nout = min(s_cnt, K);
+
+  const int W = lv.W, H = lv.H, C = lv.C;
+  const int HW = H * W;
+  const float stride_f = (float)lv.stride;
+  const float Mx = (float)W * stride_f - 1.0f;  // box.py:83  size=[W,H] * stride - 1
+  const float My = (float)H * stride_f - 1.0f;
+  const float* loc = lv.loc + (size_t)b * lv.A * 4 * HW;
+  const size_t row = (size_t)b * L * K + (size_t)l * K;
+
+  for (int t = tid; t < K; t += DEC_NT) {
+    float score = 0.f, cls = 0.f, x1 = 0.f, y1 = 0.f, x2 = 0.f, y2 = 0.f;
+    int32_t flat = -1;
+    if (t < nout) {
+      const unsigned long long key = buf[t];
+      score = key_score(key);
+      const uint32_t idx = key_index(key);
+      flat = (int32_t)idx;
+      const int x = idx % W;                       // box.py:452-454
+      const int y = (idx / W) % H;
+      const int c = (idx / W / H) % C;             // box.py:448
+      const int a = idx / C / H / W;
+      cls = (float)c;
+      const float d0 = __ldg(loc + (size_t)(a * 4 + 0) * HW + y * W + x);
+      const float d1 = __ldg(loc + (size_t)(a * 4 + 1) * HW + y * W + x);
+      const float d2 = __ldg(loc + (size_t)(a * 4 + 2) * HW + y * W + x);
+      const float d3 = __ldg(loc + (size_t)(a * 4 + 3) * HW + y * W + x);
+      const float4 an = __ldg(reinterpret_cast<const float4*>(lv.anchors) + a);
+      // grid anchor: (x,y,x,y)*stride + anchors[a]   box.py:459-462
+      const float gx1 = (float)x * stride_f + an.x, gy1 = (float)y * stride_f + an.y;
+      const float gx2 = (float)x * stride_f + an.z, gy2 = (float)y * stride_f + an.w;
+      // delta2box  box.py:74-87
+      const float aw = gx2 - gx1 + 1.0f, ah = gy2 - gy1 + 1.0f;
+      const float cx = gx1 + 0.5f * aw, cy = gy1 + 0.5f * ah;
+      const float pcx = d0 * aw + cx, pcy = d1 * ah + cy;
+      const float pw = (float)exp((double)d2) * aw, ph = (float)exp((double)d3) * ah;
+      x1 = clampf_nanprop(pcx - 0.5f * pw, 0.0f, Mx);
+      y1 = clampf_nanprop(pcy - 0.5f * ph, 0.0f, My);
+      x2 = clampf_nanprop(pcx + 0.5f * pw - 1.0f, 0.0f, Mx);
+      y2 = clampf_nanprop(pcy + 0.5f * ph - 1.0f, 0.0f, My);
+      if (p.rescore) {  // box.py:464-471
+        const float gcx = (gx1 + gx2) / 2.0f, gcy = (gy1 + gy2) / 2.0f;
+        const float ltx = fabsf(gcx - x1), lty = fabsf(gcy - y1);
+        const float rbx = fabsf(x2 - gcx), rby = fabsf(y2 - gcy);
+        const float qx = fminf(ltx, rbx) / fmaxf(ltx, rbx);
+        const float qy = fminf(lty, rby) / fmaxf(lty, rby);
+        score = score * sqrtf(qx * qy);
+      }
+    }
+    out_scores[row + t] = score;
+    out_classes[row + t] = cls;
+    reinterpret_cast<float4*>(out_boxes)[row + t] = make_float4(x1, y1, x2, y2);
+    if (out_index) out_index[row + t] = flat;
+  }
+}
+
+int fill_params(DecodeParams& p, const ssdsb_level* levels, int n_levels, int B, int top_n) {
+  p.n_levels = n_levels;
+  p.B = B;
+  p.K = top_n;
+  p.cap = next_pow2(2 * top_n + DEC_TILE);
+  if (p.cap < 2 * DEC_TILE) p.cap = 2 * DEC_TILE;
+  p.slice_begin[0] = 0;
+  p.cand_off[0] = 0;
+  for (int l = 0; l < n_levels; ++l) {
+    p.lv[l] = levels[l];
+    long long n = (long long)levels[l].A * levels[l].C * levels[l].H * levels[l].W;
+    int slices = (int)((n + DEC_SLICE - 1) / DEC_SLICE);
+    if (slices < 1) slices = 1;
+    p.slice_begin[l + 1] = p.slice_begin[l] + slices;
+    p.cand_off[l + 1] = p.cand_off[l] + slices * top_n;
+  }
+  return 0;
+}
+
+}  // namespace
+}  // namespace ssdsb
+
+using namespace ssdsb;
+
+static int validate_levels(const ssdsb_level* levels, int n_levels, int B, int top_n,
+                           bool need_ptrs) {
+  SSDSB_REQUIRE(levels != nullptr, "decode: levels is NULL");
+  SSDSB_REQUIRE(n_levels >= 1 && n_levels <= SSDSB_MAX_LEVELS, "decode: n_levels=%d outside [1,%d]",
+                n_levels, SSDSB_MAX_LEVELS);
+  SSDSB_REQUIRE(B >= 0, "decode: negative batch");
+  SSDSB_REQUIRE(top_n >= 1, "decode: top_n=%d must be >= 1", top_n);
+  if (top_n > DEC_MAX_K)
+    return fail(SSDSB_ERR_UNSUPPORTED, "decode: top_n=%d > %d not implemented", top_n, DEC_MAX_K);
+  for (int l = 0; l < n_levels; ++l) {
+    const ssdsb_level& v = levels[l];
+    SSDSB_REQUIRE(v.A >= 1 && v.C >= 1 && v.H >= 1 && v.W >= 1 && v.stride >= 1,
+                  "decode: level %d has a non-positive dimension", l);
+    SSDSB_REQUIRE((long long)v.A * v.C * v.H * v.W < (1ll << 31),
+                  "decode: level %d has too many scores per image", l);
+    if (need_ptrs) {
+      SSDSB_REQUIRE(v.conf && v.loc && v.anchors, "decode: level %d has a NULL pointer", l);
+      SSDSB_REQUIRE(((uintptr_t)v.anchors & 15) == 0, "decode: anchors must be 16-byte aligned");
+    }
+  }
+  return SSDSB_OK;
+}
+
+extern "C" size_t ssdsb_decode_workspace_bytes(const ssdsb_level* levels, int n_levels, int B,
+                                               int top_n) {
+  if (validate_levels(levels, n_levels, B, top_n, false) != SSDSB_OK) return 0;
+  DecodeParams p;
+  fill_params(p, levels, n_levels, B, top_n);
+  size_t head = (size_t)B * n_levels * 8 + (((size_t)B * n_levels * 4 + 7) / 8) * 8;
+  return head + (size_t)B * p.cand_off[n_levels] * 8 + 16;
+}
+
+extern "C" int ssdsb_decode(const ssdsb_level* levels, int n_levels, int B, float threshold,
+                            int top_n, int rescore, float* d_scores, float* d_boxes,
+                            float* d_classes, int32_t* d_index, void* d_workspace,
+                            size_t workspace_bytes, void* stream) {
+  int rc = validate_levels(levels, n_levels, B, top_n, true);
+  if (rc != SSDSB_OK) return rc;
+  if (B == 0) return SSDSB_OK;
+  SSDSB_REQUIRE(d_scores && d_boxes && d_classes, "decode: NULL output");
+  SSDSB_REQUIRE(((uintptr_t)d_boxes & 15) == 0, "decode: boxes output must be 16-byte aligned");
+  const size_t need = ssdsb_decode_workspace_bytes(levels, n_levels, B, top_n);
+  if (!d_workspace || workspace_bytes < need || ((uintptr_t)d_workspace & 15) != 0)
+    return fail(SSDSB_ERR_WORKSPACE, "decode: workspace %zu B given, %zu B (16-byte aligned) needed",
+                workspace_bytes, need);
+  DecodeParams p;
+  fill_params(p, levels, n_levels, B, top_n);
+  p.threshold = threshold;
+  p.rescore = rescore;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t head = (size_t)B * n_levels * 8 + (((size_t)B * n_levels * 4 + 7) / 8) * 8;
+  SSDSB_CUDA(cudaMemsetAsync(d_workspace, 0, head, st));
+  const size_t smem = (size_t)p.cap * sizeof(unsigned long long);
+  SSDSB_CUDA(cudaFuncSetAttribute(decode_select, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
+  SSDSB_CUDA(cudaFuncSetAttribute(decode_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
+  dim3 g1(p.slice_begin[n_levels], B);
+  decode_select<<<g1, DEC_NT, smem, st>>>(p, d_workspace);
+  SSDSB_LAUNCH_CHECK("decode_select");
+  dim3 g2(n_levels, B);
+  decode_finalize<<<g2, DEC_NT, smem, st>>>(p, d_workspace, d_scores, d_boxes, d_classes, d_index);
+  SSDSB_LAUNCH_CHECK("decode_finalize");
+  return SSDSB_OK;
+}

@@ -1,0 +1,290 @@
+// MultiBoxLoss: BCE-with-logits + per-image hard-negative mining.
+//
+// reference: ssds/core/criterion.py:43-71
+//   ce      = BCEWithLogits(logits, target)                      [B,A,C,H,W]   (:54)
+//   max_ce  = max over C, zeroed where depth != 0                [B, A*H*W]    (:57-59)
+//   rank    = position in a descending sort of max_ce             (:60-61; ties: lower index first)
+//   num_neg = min(negpos_ratio * #(depth > 0), N - 1)             (:64-65) — per image (the
+//             reference's expand_as at :66 only runs for B == 1)
+//   out     = ce * ((depth > 0) | (rank < num_neg))               (:67-71), unreduced.
+// The caller (pipeline_anchor_basic.py:79-82) multiplies by (depth >= 0) and sums.
+//
+// B200 design (HBM-bound):
+//   mbl_ce      one thread per anchor (x fastest => coalesced plane reads), C logits each:
+//               writes the per-anchor max (as an order-preserving u32) and either the unreduced
+//               ce (drop-in) or the per-anchor sum (fused), counts positives per image.
+//   mbl_select  one CTA per image: 4-pass 8-bit radix select of the num_neg-th largest max_ce
+//               straight from L2 (N <= 76 800 values), then the index cut among equal values so
+//               the selection equals a stable descending sort's.
+//   mbl_mask    drop-in: zero the C planes of every unselected anchor.
+//   mbl_sum     fused: per image deterministic reduction of sum_ce over selected anchors.
+// The full double sort of the reference is never done; the one-hot target is never materialised in
+// the fused path.
+#include "common.cuh"
+
+namespace ssdsb {
+namespace {
+
+constexpr int MBL_NT = 256;
+constexpr int SEL_NT = 1024;
+
+__device__ __forceinline__ float bce_logits(float x, float t) {
+  // torch: (1 - t) * x - log_sigmoid(x);  log_sigmoid(x) = min(x,0) - log1p(exp(-|x|))
+  const float ls = fminf(x, 0.0f) - log1pf(expf(-fabsf(x)));
+  return (1.0f - t) * x - ls;
+}
+
+// MODE 0: drop-in (reads target, writes unreduced ce to out); MODE 1: fused (class from depth,
+// writes per-anchor sum to sce).
+template <int MODE>
+__global__ void __launch_bounds__(MBL_NT)
+mbl_ce(const float* __restrict__ logits, const float* __restrict__ target,
+       const float* __restrict__ depth, int A, int C, int HW, float* __restrict__ out,
+       uint32_t* __restrict__ mce, float* __restrict__ sce, int* __restrict__ npos) {
+  const int b = blockIdx.y;
+  const int N = A * HW;
+  const int i = blockIdx.x * MBL_NT + threadIdx.x;
+  int pos = 0;
+  if (i < N) {
+    const int a = i / HW, yx = i % HW;
+    const float d = __ldg(depth + (size_t)b * N + i);
+    const size_t off = ((size_t)b * A + a) * C * HW + yx;
+    const float* lg = logits + off;
+    const int cpos = (d > 0.0f) ? (int)d - 1 : -1;
+    float mx = -INFINITY, sum = 0.0f;
+#pragma unroll 4
+    for (int c = 0; c < C; ++c) {
+      const float x = __ldcs(lg + (size_t)c * HW);
+      float t;
+      if (MODE == 0) t = __ldcs(target + off + (size_t)c * HW);
+      else t = (c == cpos) ? 1.0f : 0.0f;
+      const float ce = bce_logits(x, t);
+      mx = fmaxf(mx, ce);
+      if (MODE == 0) out[off + (size_t)c * HW] = ce;
+      else sum += ce;
+    }
+    if (d != 0.0f) mx = 0.0f;                      // criterion.py:59
+    mce[(size_t)b * N + i] = float_to_ordered(mx);
+    if (MODE == 1) sce[(size_t)b * N + i] = sum;
+    pos = (d > 0.0f) ? 1 : 0;
+  }
+  const int total = __syncthreads_count(pos);
+  if (threadIdx.x == 0 && total) atomicAdd(npos + b, total);
+}
+
+// per image: sel[b] = (value cut as ordered u32, index cut).  neg(i) = u_i > v || (u_i == v && i <= cut)
+__global__ void __launch_bounds__(SEL_NT)
+mbl_select(const uint32_t* __restrict__ mce, int N, const int* __restrict__ npos, int negpos_ratio,
+           uint2* __restrict__ sel) {
+  __shared__ int hist[256];
+  __shared__ uint32_t s_prefix;
+  __shared__ int s_remaining;
+  __shared__ int s_warp[SEL_NT / 32];
+  __shared__ int s_running, s_cut;
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x;
+  const uint32_t* u = mce + (size_t)b * N;
+  long long want = (long long)negpos_ratio * npos[b];
+  if (want > N - 1) want = N - 1;                   // criterion.py:65
+  if (want <= 0) {
+    if (tid == 0) sel[b] = make_uint2(0xffffffffu, 0xffffffffu);  // nothing is a hard negative
+    return;
+  }
+  if (tid == 0) {
+    s_prefix = 0u;
+    s_remaining = (int)want;
+  }
+  uint32_t mask = 0u;
+  for (int pass = 3; pass >= 0; --pass) {
+    for (int k = tid; k < 256; k += SEL_NT) hist[k] = 0;
+    __syncthreads();
+    const uint32_t prefix = s_prefix;
+    const int shift = pass * 8;
+    for (int i = tid; i < N; i += SEL_NT) {
+      const uint32_t v = __ldg(u + i);
+      if ((v & mask) == prefix) atomicAdd(&hist[(v >> shift) & 255u], 1);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int rem = s_remaining, d = 255;
+      for (; d > 0; --d) {
+        if (hist[d] >= rem) break;
+        rem -= hist[d];
+      }
+      s_remaining = rem;
+      s_prefix = prefix | ((uint32_t)d << shift);
+    }
+    mask |= 255u << shift;
+    __syncthreads();
+  }
+  const uint32_t vstar = s_prefix;
+  const int r = s_remaining;  // take the first r (in index order) of the elements equal to vstar
+  if (tid == 0) {
+    s_running = 0;
+    s_cut = -1;
+  }
+  __syncthreads();
+  for (int base = 0; base < N; base += SEL_NT) {
+    const int i = base + tid;
+    const bool eq = (i < N) && (__ldg(u + i) == vstar);
+    const unsigned m = __ballot_sync(0xffffffffu, eq);
+    const int lane = tid & 31, wid = tid >> 5;
+    if (lane == 0) s_warp[wid] = __popc(m);
+    __syncthreads();
+    int before = s_running;
+    for (int w = 0; w < wid; ++w) before += s_warp[w];
+    const int rank = before + __popc(m & ((1u << lane) - 1u)) + 1;  // 1-based among equals
+    if (eq && rank == r) s_cut = i;
+    __syncthreads();
+    if (tid == 0) {
+      int t = 0;
+      for (int w = 0; w < SEL_NT / 32; ++w) t += s_warp[w];
+      s_running += t;
+    }
+    __syncthreads();
+    if (s_running >= r) break;
+  }
+  if (tid == 0) sel[b] = make_uint2(vstar, (uint32_t)s_cut);
+}
+
+__device__ __forceinline__ bool is_neg(uint32_t u, int i, uint2 s) {
+  return (u > s.x) || (u == s.x && s.x != 0xffffffffu && (uint32_t)i <= s.y);
+}
+
+__global__ void __launch_bounds__(MBL_NT)
+mbl_mask(const float* __restrict__ depth, const uint32_t* __restrict__ mce,
+         const uint2* __restrict__ sel, int A, int C, int HW, float* __restrict__ out) {
+  const int b = blockIdx.y;
+  const int N = A * HW;
+  const int i = blockIdx.x * MBL_NT + threadIdx.x;
+  if (i >= N) return;
+  const float d = __ldg(depth + (size_t)b * N + i);
+  const bool keep = (d > 0.0f) || is_neg(__ldg(mce + (size_t)b * N + i), i, sel[b]);
+  if (keep) return;
+  const int a = i / HW, yx = i % HW;
+  float* o = out + ((size_t)b * A + a) * C * HW + yx;
+  // reference: ce * 0 (criterion.py:71) — identical to 0 for finite ce
+  for (int c = 0; c < C; ++c) o[(size_t)c * HW] = 0.0f;
+}
+
+__global__ void __launch_bounds__(SEL_NT)
+mbl_sum(const float* __restrict__ depth, const uint32_t* __restrict__ mce,
+        const float* __restrict__ sce, const uint2* __restrict__ sel, const int* __restrict__ npos,
+        int N, float* __restrict__ loss_sum, float* __restrict__ num_pos) {
+  __shared__ double s_part[SEL_NT / 32];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const uint2 s = sel[b];
+  double acc = 0.0;
+  for (int i = tid; i < N; i += SEL_NT) {
+    const float d = __ldg(depth + (size_t)b * N + i);
+    if (d >= 0.0f) {                                   // pipeline_anchor_basic.py:79-82
+      const bool keep = (d > 0.0f) || is_neg(__ldg(mce + (size_t)b * N + i), i, s);
+      if (keep) acc += (double)__ldg(sce + (size_t)b * N + i);
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+  if ((tid & 31) == 0) s_part[tid >> 5] = acc;
+  __syncthreads();
+  if (tid == 0) {
+    double t = 0.0;
+    for (int w = 0; w < SEL_NT / 32; ++w) t += s_part[w];
+    loss_sum[b] = (float)t;
+    num_pos[b] = (float)npos[b];
+  }
+}
+
+struct MblWs {
+  uint32_t* mce;
+  float* sce;
+  uint2* sel;
+  int* npos;
+  size_t head;  // bytes of (sel + npos), zeroed per call
+};
+
+size_t mbl_ws_bytes(int B, long long N) {
+  return align_up((size_t)B * 8, 16) + align_up((size_t)B * 4, 16) + align_up((size_t)B * N * 4, 16) * 2;
+}
+
+MblWs mbl_carve(void* ws, int B, long long N) {
+  MblWs w;
+  unsigned char* p = reinterpret_cast<unsigned char*>(ws);
+  w.sel = reinterpret_cast<uint2*>(p);
+  p += align_up((size_t)B * 8, 16);
+  w.npos = reinterpret_cast<int*>(p);
+  p += align_up((size_t)B * 4, 16);
+  w.head = (size_t)(p - reinterpret_cast<unsigned char*>(ws));
+  w.mce = reinterpret_cast<uint32_t*>(p);
+  p += align_up((size_t)B * N * 4, 16);
+  w.sce = reinterpret_cast<float*>(p);
+  return w;
+}
+
+int mbl_check(int B, int A, int C, int H, int W, int negpos_ratio, const void* ws, size_t ws_bytes) {
+  SSDSB_REQUIRE(B >= 0 && A >= 1 && C >= 1 && H >= 1 && W >= 1,
+                "multibox_loss: bad shape B=%d A=%d C=%d H=%d W=%d", B, A, C, H, W);
+  SSDSB_REQUIRE(negpos_ratio >= 0, "multibox_loss: negpos_ratio=%d", negpos_ratio);
+  SSDSB_REQUIRE((long long)A * H * W < (1ll << 31), "multibox_loss: too many anchors");
+  SSDSB_REQUIRE(B <= 65535, "multibox_loss: B=%d > 65535", B);
+  const size_t need = mbl_ws_bytes(B, (long long)A * H * W);
+  if (B > 0 && (!ws || ws_bytes < need || ((uintptr_t)ws & 15) != 0))
+    return fail(SSDSB_ERR_WORKSPACE, "multibox_loss: workspace %zu B given, %zu B needed", ws_bytes,
+                need);
+  return SSDSB_OK;
+}
+
+}  // namespace
+}  // namespace ssdsb
+
+using namespace ssdsb;
+
+extern "C" size_t ssdsb_multibox_loss_workspace_bytes(int B, int A, int C, int H, int W) {
+  (void)C;
+  if (B < 0 || A < 1 || H < 1 || W < 1) return 0;
+  return mbl_ws_bytes(B, (long long)A * H * W);
+}
+
+extern "C" int ssdsb_multibox_loss(const float* d_logits, const float* d_target,
+                                   const float* d_depth, int B, int A, int C, int H, int W,
+                                   int negpos_ratio, float* d_out, void* d_workspace,
+                                   size_t workspace_bytes, void* stream) {
+  int rc = mbl_check(B, A, C, H, W, negpos_ratio, d_workspace, workspace_bytes);
+  if (rc != SSDSB_OK) return rc;
+  if (B == 0) return SSDSB_OK;
+  SSDSB_REQUIRE(d_logits && d_target && d_depth && d_out, "multibox_loss: NULL argument");
+  const int HW = H * W, N = A * HW;
+  MblWs w = mbl_carve(d_workspace, B, N);
+  cudaStream_t st = (cudaStream_t)stream;
+  SSDSB_CUDA(cudaMemsetAsync(d_workspace, 0, w.head, st));
+  dim3 grid((N + MBL_NT - 1) / MBL_NT, B);
+  mbl_ce<0><<<grid, MBL_NT, 0, st>>>(d_logits, d_target, d_depth, A, C, HW, d_out, w.mce, nullptr,
+                                     w.npos);
+  SSDSB_LAUNCH_CHECK("mbl_ce<0>");
+  mbl_select<<<B, SEL_NT, 0, st>>>(w.mce, N, w.npos, negpos_ratio, w.sel);
+  SSDSB_LAUNCH_CHECK("mbl_select");
+  mbl_mask<<<grid, MBL_NT, 0, st>>>(d_depth, w.mce, w.sel, A, C, HW, d_out);
+  SSDSB_LAUNCH_CHECK("mbl_mask");
+  return SSDSB_OK;
+}
+
+extern "C" int ssdsb_multibox_loss_sum(const float* d_logits, const float* d_depth, int B, int A,
+                                       int C, int H, int W, int negpos_ratio, float* d_loss_sum,
+                                       float* d_num_pos, void* d_workspace, size_t workspace_bytes,
+                                       void* stream) {
+  int rc = mbl_check(B, A, C, H, W, negpos_ratio, d_workspace, workspace_bytes);
+  if (rc != SSDSB_OK) return rc;
+  if (B == 0) return SSDSB_OK;
+  SSDSB_REQUIRE(d_logits && d_depth && d_loss_sum && d_num_pos, "multibox_loss_sum: NULL argument");
+  const int HW = H * W, N = A * HW;
+  MblWs w = mbl_carve(d_workspace, B, N);
+  cudaStream_t st = (cudaStream_t)stream;
+  SSDSB_CUDA(cudaMemsetAsync(d_workspace, 0, w.head, st));
+  dim3 grid((N + MBL_NT - 1) / MBL_NT, B);
+  mbl_ce<1><<<grid, MBL_NT, 0, st>>>(d_logits, nullptr, d_depth, A, C, HW, nullptr, w.mce, w.sce,
+                                     w.npos);
+  SSDSB_LAUNCH_CHECK("mbl_ce<1>");
+  mbl_select<<<B, SEL_NT, 0, st>>>(w.mce, N, w.npos, negpos_ratio, w.sel);
+  SSDSB_LAUNCH_CHECK("mbl_select");
+  mbl_sum<<<B, SEL_NT, 0, st>>>(d_depth, w.mce, w.sce, w.sel, w.npos, N, d_loss_sum, d_num_pos);
+  SSDSB_LAUNCH_CHECK("mbl_sum");
+  return SSDSB_OK;
+}
