@@ -137,6 +137,53 @@ SSDSB_API int ssdsb_multibox_loss_sum(const float* d_logits /*[B,A,C,H,W]*/,
                                       float* d_num_pos /*[B]*/, void* d_workspace,
                                       size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Conv stack (tcgen05 / TMA implicit GEMM), bf16 x bf16 -> fp32 accumulate.
+ * One call replaces nn.Conv2d -> BatchNorm2d(eval, folded) -> [+ residual] -> [ReLU] of the
+ * reference model graph (ssds/modeling/ssds/ssd.py:42-74, nets/resnet.py:41-56, torchvision
+ * Bottleneck, layers/basic_layers.py:41-57), or a multibox head pair (ssd.py:100-103) + the eval
+ * sigmoid (ssd.py:72-73).
+ *   x : NHWC bf16, channel stride x_cstride (0 => Cin); Cin % 64 == 0, or Cin == 16 (the
+ *       space-to-depth packed image of the 7x7/s2 stem, see ssdsb_pack_image_s2d).
+ *   w : bf16 [w_rows >= Cout][KH*KW][Cin], BN scale folded in; bias fp32 [Cout] (folded BN shift
+ *       or the conv bias).
+ *   out_mode 0 : y = NHWC bf16 [N,Ho,Wo,out_cstride], optional residual (same layout, res_cstride)
+ *                and ReLU.  Cout % 32 == 0.
+ *   out_mode 1 : multibox head: output channels [0,n_loc) -> y  = fp32 NCHW [N,n_loc,Ho,Wo] (loc),
+ *                [n_loc,Cout) -> y2 = fp32 NCHW [N,Cout-n_loc,Ho,Wo] (conf), sigmoid-ed if `sigmoid`.
+ *   Ho/Wo: 0 => (H + 2*pad - KH)/stride + 1; pad is the top/left padding, the bottom/right halo is
+ *   whatever Ho/Wo imply (TMA zero-fills out-of-bounds reads).
+ * ------------------------------------------------------------------------------------------- */
+enum { SSDSB_CONV_OUT_NHWC_BF16 = 0, SSDSB_CONV_OUT_HEAD_NCHW_F32 = 1 };
+
+typedef struct {
+  int N, H, W, Cin;
+  int Cout, KH, KW, stride, pad;
+  int Ho, Wo;
+  int x_cstride, out_cstride, res_cstride;
+  int w_rows;
+  int relu;
+  int out_mode;
+  int n_loc;
+  int sigmoid;
+} ssdsb_conv_desc;
+
+SSDSB_API int ssdsb_conv2d_bf16(const ssdsb_conv_desc* desc, const void* d_x, const void* d_w,
+                                const float* d_bias, const void* d_residual, void* d_y, void* d_y2,
+                                void* stream);
+
+/* Image pre-processing fused with the layout change the stem needs (SSDDetector.__call__,
+ * ssds/ssds.py:48-57: HWC->CHW, (x - mean)/std): packs an image batch into the 2x2
+ * space-to-depth NHWC16 bf16 tensor [N, H/2, W/2, 16] (channel (a*2+b)*3+c = pixel (2i+a, 2j+b),
+ * channels 12..15 zero) on which the 7x7/s2 stem is a 4x4/s1 convolution.
+ * src_format 0: fp32 NCHW [N,3,H,W]; 1: uint8 NHWC [N,H,W,3].  H and W must be even. */
+SSDSB_API int ssdsb_pack_image_s2d(const void* d_src, int src_format, int N, int H, int W,
+                                   float mean, float std, void* d_out, void* stream);
+
+/* 3x3 / stride 2 / pad 1 max pooling on NHWC bf16 (resnet.py:45 `self.maxpool`). C % 8 == 0. */
+SSDSB_API int ssdsb_maxpool3x3s2_nhwc_bf16(const void* d_x, int N, int H, int W, int C, void* d_y,
+                                           void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -68,7 +68,7 @@ def build(force=False, verbose=False):
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    link = [nvcc()] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcuda"]
+    link = [nvcc()] + ARCH + ["-shared", "-o", LIB] + objs 
     subprocess.check_call(link)
     open(STAMP, "w").write(d)
     return LIB

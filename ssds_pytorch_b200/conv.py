@@ -1,0 +1,123 @@
+"""Host side of the tcgen05 conv stack: weight packing (BN folding, one-time) and thin launchers.
+
+Layout contract (see csrc/conv_igemm.cu): activations NHWC bf16; weights bf16 [Cout, KH*KW, Cin]
+with the eval-mode BatchNorm scale folded in; bias fp32 [Cout] = folded BN shift or conv bias.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import lib, check, ptr, stream_ptr
+
+
+def fold_bn(weight, bn=None, bias=None):
+    """weight [Cout,Cin,KH,KW] fp32 (+ BatchNorm2d eval statistics) -> (folded weight, bias) fp32.
+    y = gamma * (conv(x) - mean) / sqrt(var + eps) + beta  (torch BatchNorm2d, eval)."""
+    w = weight.detach().float()
+    cout = w.shape[0]
+    b = bias.detach().float() if bias is not None else torch.zeros(cout)
+    if bn is not None:
+        gamma, beta, mean, var, eps = bn
+        scale = gamma.detach().float() / torch.sqrt(var.detach().float() + eps)
+        w = w * scale.view(-1, 1, 1, 1)
+        b = (b - mean.detach().float()) * scale + beta.detach().float()
+    return w, b
+
+
+def pack_weight(w_folded, cin_pad=None):
+    """[Cout,Cin,KH,KW] fp32 -> bf16 [Cout, KH*KW, Cin_pad] (K-major: tap-major, channel-minor)."""
+    cout, cin, kh, kw = w_folded.shape
+    cin_pad = cin_pad or cin
+    out = torch.zeros((cout, kh * kw, cin_pad), dtype=torch.float32)
+    out[:, :, :cin] = w_folded.permute(0, 2, 3, 1).reshape(cout, kh * kw, cin)
+    return out.to(torch.bfloat16).contiguous()
+
+
+def pack_stem_weight_s2d(w_folded):
+    """7x7/s2/p3 stem [Cout,3,7,7] -> the equivalent 4x4/s1 kernel on the 2x2 space-to-depth image:
+    bf16 [Cout, 16 taps, 16 ch], channel (a*2+b)*3+c, W'[kh',kw',a,b,c] = W[c, 2kh'+a-1, 2kw'+b-1]
+    (zero where the index is -1); s2d row = ho - 2 + kh'."""
+    cout = w_folded.shape[0]
+    assert tuple(w_folded.shape[1:]) == (3, 7, 7)
+    out = torch.zeros((cout, 4, 4, 16), dtype=torch.float32)
+    for khp in range(4):
+        for a in range(2):
+            r = 2 * khp + a - 1
+            if r < 0:
+                continue
+            for kwp in range(4):
+                for b in range(2):
+                    s = 2 * kwp + b - 1
+                    if s < 0:
+                        continue
+                    for c in range(3):
+                        out[:, khp, kwp, (a * 2 + b) * 3 + c] = w_folded[:, c, r, s]
+    return out.reshape(cout, 16, 16).to(torch.bfloat16).contiguous()
+
+
+def conv2d(x, w, bias, KH, KW, stride, pad, relu=False, residual=None, out=None, Ho=0, Wo=0):
+    """x NHWC bf16 [N,H,W,Cin] -> NHWC bf16 [N,Ho,Wo,Cout]; w bf16 [Cout, KH*KW, Cin]."""
+    N, H, W, Cin = x.shape
+    Cout = w.shape[0]
+    ho = Ho or (H + 2 * pad - KH) // stride + 1
+    wo = Wo or (W + 2 * pad - KW) // stride + 1
+    if out is None:
+        out = torch.empty((N, ho, wo, Cout), dtype=torch.bfloat16, device=x.device)
+    d = _lib.ConvDesc(N=N, H=H, W=W, Cin=Cin, Cout=Cout, KH=KH, KW=KW, stride=stride, pad=pad,
+                      Ho=ho, Wo=wo, x_cstride=x.stride(2), out_cstride=out.stride(2),
+                      res_cstride=residual.stride(2) if residual is not None else 0,
+                      w_rows=w.shape[0], relu=int(relu), out_mode=0, n_loc=0, sigmoid=0)
+    with torch.cuda.device(x.device):
+        check(lib.ssdsb_conv2d_bf16(C.byref(d), ptr(x), ptr(w), ptr(bias), ptr(residual), ptr(out),
+                                    None, stream_ptr()), "conv2d")
+    return out
+
+
+def conv2d_head(x, w, bias, n_loc, sigmoid, KH=3, KW=3, stride=1, pad=1, loc=None, conf=None):
+    """Fused multibox head: x NHWC bf16 -> (loc fp32 NCHW [N,n_loc,H,W], conf fp32 NCHW [N,Cout-n_loc,H,W]).
+    w rows [0,n_loc) are the loc conv, [n_loc,Cout) the conf conv (ssd.py:100-103)."""
+    N, H, W, Cin = x.shape
+    Cout = w.shape[0]
+    ho = (H + 2 * pad - KH) // stride + 1
+    wo = (W + 2 * pad - KW) // stride + 1
+    if loc is None:
+        loc = torch.empty((N, n_loc, ho, wo), dtype=torch.float32, device=x.device)
+    if conf is None:
+        conf = torch.empty((N, Cout - n_loc, ho, wo), dtype=torch.float32, device=x.device)
+    d = _lib.ConvDesc(N=N, H=H, W=W, Cin=Cin, Cout=Cout, KH=KH, KW=KW, stride=stride, pad=pad,
+                      Ho=ho, Wo=wo, x_cstride=x.stride(2), out_cstride=0, res_cstride=0,
+                      w_rows=w.shape[0], relu=0, out_mode=1, n_loc=n_loc, sigmoid=int(sigmoid))
+    with torch.cuda.device(x.device):
+        check(lib.ssdsb_conv2d_bf16(C.byref(d), ptr(x), ptr(w), ptr(bias), None, ptr(loc), ptr(conf),
+                                    stream_ptr()), "conv2d_head")
+    return loc, conf
+
+
+def pack_image_s2d(images, mean=0.0, std=1.0, out=None):
+    """images: fp32 NCHW [N,3,H,W] or uint8 NHWC [N,H,W,3] (CUDA) -> bf16 [N,H/2,W/2,16]."""
+    if images.dtype == torch.uint8:
+        N, H, W, _ = images.shape
+        fmt = 1
+    else:
+        images = images.float()
+        N, _, H, W = images.shape
+        fmt = 0
+    images = images.contiguous()
+    if out is None:
+        out = torch.empty((N, H // 2, W // 2, 16), dtype=torch.bfloat16, device=images.device)
+    with torch.cuda.device(images.device):
+        check(lib.ssdsb_pack_image_s2d(ptr(images), fmt, N, H, W, float(mean), float(std), ptr(out),
+                                       stream_ptr()), "pack_image_s2d")
+    return out
+
+
+def maxpool3x3s2(x, out=None):
+    """NHWC bf16 max pooling 3x3 / stride 2 / pad 1 (resnet.py:45)."""
+    N, H, W, Cc = x.shape
+    ho, wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    if out is None:
+        out = torch.empty((N, ho, wo, Cc), dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib.ssdsb_maxpool3x3s2_nhwc_bf16(ptr(x), N, H, W, Cc, ptr(out), stream_ptr()), "maxpool")
+    return out

@@ -1,0 +1,566 @@
+// Implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05 + TMEM + TMA), sm_100a only.
+//
+// Replaces, for the SSD conv stack (reference ssds/modeling/ssds/ssd.py:42-74 over
+// ssds/modeling/nets/resnet.py:41-56 and layers/basic_layers.py:27-57), every
+// nn.Conv2d -> BatchNorm2d(eval) -> [+ residual] -> ReLU chain and the 3x3 multibox heads
+// (ssd.py:100-103, + sigmoid in eval, ssd.py:72-73) by ONE kernel launch per convolution.
+//
+//   D[pixel, cout] = sum_{tap, cin} X[pixel shifted by tap, cin] * Wt[cout, tap, cin]
+//
+//   * activations: NHWC bf16.  An M-tile is a (BW x BH x BN) patch of 128 output pixels; the A
+//     operand of one (tap, 64-channel) K-block is ONE 4-D TMA box load at the shifted coordinate
+//     (c, w*s+kw-p, h*s+kh-p, n): TMA zero-fills the halo (conv padding) and the ragged edge, and
+//     its traversal stride implements stride-2 convolutions.  No im2col buffer exists anywhere.
+//   * weights: BN-folded bf16 [Cout_pad][tap][Cin] (K-major) -> 2-D TMA box (64, BLOCK_N).
+//   * both land in 128B-swizzled shared memory, STAGES deep; one elected thread issues
+//     tcgen05.mma (M=128, N=BLOCK_N, K=16) with fp32 accumulators in TMEM, double buffered so
+//     the epilogue of tile i overlaps the MMAs of tile i+1 (persistent CTAs, 1 per SM).
+//   * epilogue warps: tcgen05.ld -> +bias (folded BN / conv bias) -> +residual -> ReLU -> bf16
+//     NHWC, or for the multibox head -> fp32 NCHW split into loc / sigmoid(conf), the exact
+//     tensors `model(x)` returns in the reference.
+//   * 7x7/s2 stem (Cin=3): the image is pre-packed 2x2 space-to-depth into NHWC16 (layout.cu), on
+//     which the stem is a 4x4/s1 convolution; its K-block is one tap x 16 channels (32-byte rows,
+//     SWIZZLE_32B, one K=16 MMA per block) — same kernel, BLOCK_K = 16.
+//
+// Warp roles (256 threads): w0 TMA producer, w1 MMA issuer, w2 TMEM allocator, w4-7 epilogue.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "conv_params.h"
+
+namespace ssdsb {
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int UMMA_K = 16;
+constexpr int CONV_NT = 256;
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0,
+                                            int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0,
+                                            int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   smem_u32(bar))
+               : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], bf16 x bf16 -> fp32
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+        "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major swizzled operand tile: rows of ROW_BYTES (= swizzle span: 128 or 32), 8-row groups
+// 8*ROW_BYTES apart; one swizzle atom along K, so the leading-dimension offset is unused.
+template <int ROW_BYTES>
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  static_assert(ROW_BYTES == 128 || ROW_BYTES == 32, "unsupported swizzle span");
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3ffffu) >> 4);          // start address        bits [0,14)
+  d |= (uint64_t)((8u * ROW_BYTES) >> 4) << 32;          // stride byte offset   bits [32,46)
+  d |= (uint64_t)1 << 46;                                // descriptor version (Blackwell)
+  d |= (uint64_t)(ROW_BYTES == 128 ? 2 : 6) << 61;       // SWIZZLE_128B / SWIZZLE_32B
+  return d;
+}
+// kind::f16 instruction descriptor: bf16 x bf16 -> f32, both operands K-major
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel
+// ---------------------------------------------------------------------------------------------
+template <int BLOCK_N, int BLOCK_K>
+struct ConvSmem {
+  static constexpr int ROW_BYTES = BLOCK_K * 2;
+  static constexpr int A_STAGE_BYTES = BLOCK_M * ROW_BYTES;
+  static constexpr int B_STAGE_BYTES = BLOCK_N * ROW_BYTES;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int STAGES = (BLOCK_K == 16) ? 16 : ((BLOCK_N >= 256) ? 4 : (BLOCK_N >= 128 ? 6 : 8));
+  static constexpr int TMEM_COLS = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;
+  static constexpr int BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
+  static_assert(STAGE_BYTES % 1024 == 0, "stage bases must stay 1024-byte aligned");
+};
+
+template <int BLOCK_N, int BLOCK_K>
+__global__ void __launch_bounds__(CONV_NT, 1)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ ConvKernelParams p) {
+  using S = ConvSmem<BLOCK_N, BLOCK_K>;
+  constexpr int A_STAGE_BYTES = S::A_STAGE_BYTES;
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>(
+      (reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::STAGES * S::STAGE_BYTES);
+  uint64_t* full_bar = bars;                      // [STAGES]
+  uint64_t* empty_bar = bars + S::STAGES;         // [STAGES]
+  uint64_t* tmem_full = bars + 2 * S::STAGES;     // [2]
+  uint64_t* tmem_empty = bars + 2 * S::STAGES + 2;// [2]
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * S::STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < S::STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(tmem_holder)),
+                 "r"((uint32_t)S::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int num_tiles = m_tiles * p.n_tiles;
+  const int rows = p.BW * p.BH * p.BN;
+  const uint32_t tx_bytes = (uint32_t)rows * (BLOCK_K * 2) + (uint32_t)S::B_STAGE_BYTES;
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.n_tiles;
+        const int m = tile / p.n_tiles;
+        const int tw = m % p.tiles_w;
+        const int th = (m / p.tiles_w) % p.tiles_h;
+        const int tn = m / (p.tiles_w * p.tiles_h);
+        const int w0 = tw * p.BW, h0 = th * p.BH, n0 = tn * p.BN;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          unsigned char* sa = smem + stage * S::STAGE_BYTES;
+          unsigned char* sb = sa + A_STAGE_BYTES;
+          mbar_expect_tx(&full_bar[stage], tx_bytes);
+          const int tap = kb / p.kc_per_tap;
+          const int kc = kb - tap * p.kc_per_tap;
+          const int kh = tap / p.KW, kw = tap - kh * p.KW;
+          tma_load_4d(sa, &tmA, &full_bar[stage], kc * BLOCK_K, w0 * p.stride + kw - p.pad,
+                      h0 * p.stride + kh - p.pad, n0);
+          tma_load_2d(sb, &tmB, &full_bar[stage], kb * BLOCK_K, n_tile * BLOCK_N);
+          if (++stage == S::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * S::STAGE_BYTES);
+          const uint64_t a_desc = make_smem_desc<S::ROW_BYTES>(a_addr);
+          const uint64_t b_desc = make_smem_desc<S::ROW_BYTES>(a_addr + A_STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            // advance 16 bf16 = 32 bytes inside the swizzle row: +2 in the (>>4) address field
+            umma_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
+                      (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          tcgen05_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          if (++stage == S::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        tcgen05_commit(&tmem_full[acc]);      // accumulator ready for the epilogue
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // =============================== epilogue ===============================
+    const int q = warp - 4;                   // TMEM lane quarter this warp may read
+    const int r = q * 32 + lane;              // row of the tile == TMEM lane
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int n_tile = tile % p.n_tiles;
+      const int m = tile / p.n_tiles;
+      const int tw = m % p.tiles_w;
+      const int th = (m / p.tiles_w) % p.tiles_h;
+      const int tn = m / (p.tiles_w * p.tiles_h);
+      // row r -> (bn, bh, bw) in TMA box order (w fastest)
+      const int bw = r % p.BW;
+      const int bh = (r / p.BW) % p.BH;
+      const int bn = r / (p.BW * p.BH);
+      const int w = tw * p.BW + bw, h = th * p.BH + bh, n = tn * p.BN + bn;
+      const bool row_ok = (r < rows) && (w < p.Wo) && (h < p.Ho) && (n < p.N);
+
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tcgen05_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+      const size_t pix = ((size_t)n * p.Ho + h) * p.Wo + w;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        const int col0 = n_tile * BLOCK_N + c0;
+        if (col0 >= p.Cout) break;            // warp-uniform
+        uint32_t v[32];
+        tmem_ld32(t_row + (uint32_t)c0, v);
+        tmem_ld_wait();
+        if (p.mode == CONV_OUT_NHWC_BF16) {
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + __ldg(p.bias + col0 + j);
+          if (row_ok) {
+            if (p.residual) {
+              const uint4* rp = reinterpret_cast<const uint4*>(
+                  reinterpret_cast<const __nv_bfloat16*>(p.residual) + pix * p.res_cstride + col0);
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                const uint4 rv = __ldg(rp + g);
+                const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&rw[e]);
+                  f[g * 8 + e * 2 + 0] += __bfloat162float(h2.x);
+                  f[g * 8 + e * 2 + 1] += __bfloat162float(h2.y);
+                }
+              }
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+            }
+            uint4* yp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.y) +
+                                                 pix * p.out_cstride + col0);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint4 o;
+              o.x = pack_bf16(f[g * 8 + 0], f[g * 8 + 1]);
+              o.y = pack_bf16(f[g * 8 + 2], f[g * 8 + 3]);
+              o.z = pack_bf16(f[g * 8 + 4], f[g * 8 + 5]);
+              o.w = pack_bf16(f[g * 8 + 6], f[g * 8 + 7]);
+              yp[g] = o;
+            }
+          }
+        } else {
+          // multibox head: channels [0, n_loc) -> loc fp32 NCHW; [n_loc, Cout) -> sigmoid -> conf
+          const size_t hw = (size_t)p.Ho * p.Wo;
+          const size_t sp = (size_t)h * p.Wo + w;
+          float* loc = reinterpret_cast<float*>(p.y) + (size_t)n * p.n_loc * hw + sp;
+          float* conf = reinterpret_cast<float*>(p.y2) + (size_t)n * (p.Cout - p.n_loc) * hw + sp;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int col = col0 + j;
+            if (col < p.Cout && row_ok) {
+              const float x = __uint_as_float(v[j]) + __ldg(p.bias + col);
+              if (col < p.n_loc) {
+                loc[(size_t)col * hw] = x;
+              } else {
+                const float s = p.sigmoid ? 1.0f / (1.0f + __expf(-x)) : x;
+                __stcs(conf + (size_t)(col - p.n_loc) * hw, s);
+              }
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)S::TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side: tensor maps + launch
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+int pick_block_n(int cout) {
+  if (cout <= 64) return 64;
+  if (cout <= 128) return 128;
+  return 256;
+}
+
+template <int BLOCK_N, int BLOCK_K>
+int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvKernelParams& kp, int sms,
+           cudaStream_t st) {
+  using S = ConvSmem<BLOCK_N, BLOCK_K>;
+  static bool configured = false;
+  if (!configured) {
+    SSDSB_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BLOCK_N, BLOCK_K>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, S::BYTES));
+    configured = true;
+  }
+  const int tiles = kp.tiles_w * kp.tiles_h * kp.tiles_n * kp.n_tiles;
+  const int grid = tiles < sms ? tiles : sms;
+  conv_igemm_kernel<BLOCK_N, BLOCK_K><<<grid, CONV_NT, S::BYTES, st>>>(tmA, tmB, kp);
+  SSDSB_LAUNCH_CHECK("conv_igemm_kernel");
+  return SSDSB_OK;
+}
+
+}  // namespace
+}  // namespace ssdsb
+
+using namespace ssdsb;
+
+extern "C" int ssdsb_conv2d_bf16(const ssdsb_conv_desc* d, const void* x, const void* w,
+                                 const float* bias, const void* residual, void* y, void* y2,
+                                 void* stream) {
+  SSDSB_REQUIRE(d && x && w && bias && y, "conv2d: NULL argument");
+  SSDSB_REQUIRE(d->N >= 1 && d->H >= 1 && d->W >= 1 && d->Cin >= 1 && d->Cout >= 1,
+                "conv2d: non-positive dimension");
+  SSDSB_REQUIRE(d->KH >= 1 && d->KW >= 1 && d->stride >= 1 && d->stride <= 2 && d->pad >= 0,
+                "conv2d: unsupported kernel geometry (KH=%d KW=%d stride=%d pad=%d)", d->KH, d->KW,
+                d->stride, d->pad);
+  const int Ho = d->Ho > 0 ? d->Ho : (d->H + 2 * d->pad - d->KH) / d->stride + 1;
+  const int Wo = d->Wo > 0 ? d->Wo : (d->W + 2 * d->pad - d->KW) / d->stride + 1;
+  SSDSB_REQUIRE(Ho >= 1 && Wo >= 1, "conv2d: empty output");
+  const int block_k = (d->Cin == 16) ? 16 : 64;
+  SSDSB_REQUIRE(d->Cin % block_k == 0, "conv2d: Cin=%d must be 16 or a multiple of 64", d->Cin);
+  const int cs = d->x_cstride ? d->x_cstride : d->Cin;
+  SSDSB_REQUIRE(cs >= d->Cin && cs % 8 == 0, "conv2d: bad input channel stride %d", cs);
+  SSDSB_REQUIRE(d->out_mode == CONV_OUT_NHWC_BF16 || d->out_mode == CONV_OUT_HEAD_NCHW_F32,
+                "conv2d: bad out_mode");
+  if (d->out_mode == CONV_OUT_NHWC_BF16) {
+    SSDSB_REQUIRE(d->out_cstride >= d->Cout && d->out_cstride % 8 == 0 && d->Cout % 32 == 0,
+                  "conv2d: NHWC output needs Cout %% 32 == 0 and a channel stride %% 8 == 0");
+    SSDSB_REQUIRE(!residual || (d->res_cstride >= d->Cout && d->res_cstride % 8 == 0 &&
+                                ((uintptr_t)residual & 15) == 0),
+                  "conv2d: bad residual stride/alignment");
+  } else {
+    SSDSB_REQUIRE(y2 && d->n_loc >= 0 && d->n_loc <= d->Cout, "conv2d: head needs y2 and n_loc");
+    SSDSB_REQUIRE(!residual, "conv2d: the head epilogue takes no residual");
+  }
+  SSDSB_REQUIRE(d->w_rows >= d->Cout, "conv2d: w_rows=%d < Cout=%d", d->w_rows, d->Cout);
+  SSDSB_REQUIRE((((uintptr_t)x | (uintptr_t)w | (uintptr_t)y) & 15) == 0,
+                "conv2d: pointers must be 16-byte aligned");
+  EncodeTiledFn encode = get_encode();
+  if (!encode) return fail(SSDSB_ERR_CUDA, "conv2d: cuTensorMapEncodeTiled entry point not found");
+
+  // ---- M tile: (BW, BH, BN) output pixels, product <= 128 --------------------------------------
+  int BW = Wo < 16 ? Wo : 16;
+  if (Wo > 16 && Wo < 32) BW = Wo;                              // e.g. 19 -> 19x6 = 114 rows
+  int BH = BLOCK_M / BW;
+  if (BH > Ho) BH = Ho;
+  int BN = BLOCK_M / (BW * BH);
+  if (BN > d->N) BN = d->N;
+  if (BN < 1) BN = 1;
+  // TMA box limit: 256 per dimension (box = outputs * stride)
+  SSDSB_REQUIRE(BW * d->stride <= 256 && BH * d->stride <= 256 && BN <= 256,
+                "conv2d: tile too large for a TMA box");
+
+  ConvKernelParams kp;
+  kp.BW = BW; kp.BH = BH; kp.BN = BN;
+  kp.tiles_w = (Wo + BW - 1) / BW;
+  kp.tiles_h = (Ho + BH - 1) / BH;
+  kp.tiles_n = (d->N + BN - 1) / BN;
+  const int block_n = pick_block_n(d->Cout);
+  kp.n_tiles = (d->Cout + block_n - 1) / block_n;
+  kp.taps = d->KH * d->KW;
+  kp.KW = d->KW;
+  kp.kc_per_tap = d->Cin / block_k;
+  kp.num_k_blocks = kp.taps * kp.kc_per_tap;
+  kp.stride = d->stride; kp.pad = d->pad;
+  kp.Ho = Ho; kp.Wo = Wo; kp.N = d->N;
+  kp.Cout = d->Cout;
+  kp.out_cstride = d->out_cstride;
+  kp.res_cstride = d->res_cstride;
+  kp.relu = d->relu;
+  kp.mode = d->out_mode;
+  kp.n_loc = d->n_loc;
+  kp.sigmoid = d->sigmoid;
+  kp.bias = bias;
+  kp.residual = residual;
+  kp.y = y; kp.y2 = y2;
+
+  // ---- tensor maps ------------------------------------------------------------------------------
+  const CUtensorMapSwizzle swz = block_k == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B;
+  alignas(64) CUtensorMap tmA;
+  alignas(64) CUtensorMap tmB;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
+    cuuint64_t strides[3] = {(cuuint64_t)cs * 2, (cuuint64_t)d->W * cs * 2,
+                             (cuuint64_t)d->H * d->W * cs * 2};
+    cuuint32_t box[4] = {(cuuint32_t)block_k, (cuuint32_t)(BW * d->stride),
+                         (cuuint32_t)(BH * d->stride), (cuuint32_t)BN};
+    cuuint32_t estr[4] = {1, (cuuint32_t)d->stride, (cuuint32_t)d->stride, 1};
+    CUresult r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims,
+                        strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+      return fail(SSDSB_ERR_CUDA, "conv2d: activation tensor map failed (CUresult %d)", (int)r);
+  }
+  {
+    const cuuint64_t ktot = (cuuint64_t)kp.num_k_blocks * block_k;
+    cuuint64_t dims[2] = {ktot, (cuuint64_t)d->w_rows};
+    cuuint64_t strides[1] = {ktot * 2};
+    cuuint32_t box[2] = {(cuuint32_t)block_k, (cuuint32_t)block_n};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims,
+                        strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+      return fail(SSDSB_ERR_CUDA, "conv2d: weight tensor map failed (CUresult %d)", (int)r);
+  }
+
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    SSDSB_CUDA(cudaGetDevice(&dev));
+    SSDSB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (block_k == 16) {
+    switch (block_n) {
+      case 64: return launch<64, 16>(tmA, tmB, kp, sms, st);
+      case 128: return launch<128, 16>(tmA, tmB, kp, sms, st);
+      default: return launch<256, 16>(tmA, tmB, kp, sms, st);
+    }
+  }
+  switch (block_n) {
+    case 64: return launch<64, 64>(tmA, tmB, kp, sms, st);
+    case 128: return launch<128, 64>(tmA, tmB, kp, sms, st);
+    default: return launch<256, 64>(tmA, tmB, kp, sms, st);
+  }
+}

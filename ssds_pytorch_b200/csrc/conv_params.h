@@ -1,0 +1,26 @@
+// Kernel-side parameter block of the implicit-GEMM convolution (internal).
+#pragma once
+#include <stdint.h>
+
+namespace ssdsb {
+
+enum { CONV_OUT_NHWC_BF16 = 0, CONV_OUT_HEAD_NCHW_F32 = 1 };
+
+struct ConvKernelParams {
+  int num_k_blocks;  // taps * kc_per_tap
+  int kc_per_tap;    // Cin / BLOCK_K
+  int KW, taps;
+  int stride, pad;
+  int BW, BH, BN;    // output-pixel patch of one M tile (product <= 128)
+  int tiles_w, tiles_h, tiles_n, n_tiles;
+  int Ho, Wo, N;
+  int Cout;
+  int out_cstride, res_cstride;
+  int relu, mode, n_loc, sigmoid;
+  const float* bias;
+  const void* residual;
+  void* y;
+  void* y2;
+};
+
+}  // namespace ssdsb

@@ -1,0 +1,135 @@
+// HBM-bound layout/pooling kernels around the conv stack (128-bit vectorised, streaming hints).
+//
+//   pack_image_s2d   reference ssds/ssds.py:48-57 (HWC->CHW, (x-mean)/std) fused with the 2x2
+//                    space-to-depth packing the tcgen05 stem consumes: out[n,i,j,(a*2+b)*3+c] =
+//                    (x[n,c,2i+a,2j+b] - mean)/std as bf16, channels 12..15 = 0.
+//   maxpool3x3s2     resnet.py:45 nn.MaxPool2d(3, 2, 1) on NHWC bf16, 8 channels per thread.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace ssdsb {
+namespace {
+
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+template <int FMT>  // 0: fp32 NCHW, 1: uint8 NHWC
+__global__ void __launch_bounds__(256)
+pack_image_s2d_kernel(const void* __restrict__ src, int N, int H, int W, float mean, float stdv,
+                      uint4* __restrict__ out) {
+  const int Ho = H >> 1, Wo = W >> 1;
+  const size_t total = (size_t)N * Ho * Wo;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const int j = (int)(i % Wo);
+    const int ii = (int)((i / Wo) % Ho);
+    const int n = (int)(i / ((size_t)Wo * Ho));
+    float v[12];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const int y = 2 * ii + a, x = 2 * j + b;
+          float f;
+          if (FMT == 0)
+            f = __ldg(reinterpret_cast<const float*>(src) + (((size_t)n * 3 + c) * H + y) * W + x);
+          else
+            f = (float)__ldg(reinterpret_cast<const unsigned char*>(src) +
+                             (((size_t)n * H + y) * W + x) * 3 + c);
+          v[(a * 2 + b) * 3 + c] = (f - mean) / stdv;   // ssds.py:57
+        }
+    uint4 lo, hi;
+    lo.x = pack2(v[0], v[1]); lo.y = pack2(v[2], v[3]); lo.z = pack2(v[4], v[5]); lo.w = pack2(v[6], v[7]);
+    hi.x = pack2(v[8], v[9]); hi.y = pack2(v[10], v[11]); hi.z = 0u; hi.w = 0u;
+    out[i * 2 + 0] = lo;
+    out[i * 2 + 1] = hi;
+  }
+}
+
+__device__ __forceinline__ uint32_t max_bf162(uint32_t a, uint32_t b) {
+  __nv_bfloat162 x = *reinterpret_cast<__nv_bfloat162*>(&a);
+  __nv_bfloat162 y = *reinterpret_cast<__nv_bfloat162*>(&b);
+  __nv_bfloat162 m = __hmax2(x, y);
+  return *reinterpret_cast<uint32_t*>(&m);
+}
+
+__global__ void __launch_bounds__(256)
+maxpool3x3s2_kernel(const uint4* __restrict__ x, int N, int H, int W, int C8, int Ho, int Wo,
+                    uint4* __restrict__ y) {
+  const size_t total = (size_t)N * Ho * Wo * C8;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C8);
+    const int wo = (int)((i / C8) % Wo);
+    const int ho = (int)((i / ((size_t)C8 * Wo)) % Ho);
+    const int n = (int)(i / ((size_t)C8 * Wo * Ho));
+    uint4 m;
+    bool first = true;
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      const int h = 2 * ho - 1 + dy;
+      if (h < 0 || h >= H) continue;
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const int w = 2 * wo - 1 + dx;
+        if (w < 0 || w >= W) continue;
+        const uint4 v = __ldg(x + (((size_t)n * H + h) * W + w) * C8 + c);
+        if (first) {
+          m = v;
+          first = false;
+        } else {
+          m.x = max_bf162(m.x, v.x); m.y = max_bf162(m.y, v.y);
+          m.z = max_bf162(m.z, v.z); m.w = max_bf162(m.w, v.w);
+        }
+      }
+    }
+    y[i] = m;
+  }
+}
+
+}  // namespace
+}  // namespace ssdsb
+
+using namespace ssdsb;
+
+extern "C" int ssdsb_pack_image_s2d(const void* d_src, int src_format, int N, int H, int W,
+                                    float mean, float stdv, void* d_out, void* stream) {
+  SSDSB_REQUIRE(d_src && d_out, "pack_image_s2d: NULL argument");
+  SSDSB_REQUIRE(N >= 1 && H >= 2 && W >= 2 && (H % 2) == 0 && (W % 2) == 0,
+                "pack_image_s2d: H and W must be even (N=%d H=%d W=%d)", N, H, W);
+  SSDSB_REQUIRE(src_format == 0 || src_format == 1, "pack_image_s2d: src_format=%d", src_format);
+  SSDSB_REQUIRE(stdv != 0.0f, "pack_image_s2d: std must be non-zero");
+  SSDSB_REQUIRE(((uintptr_t)d_out & 15) == 0, "pack_image_s2d: output must be 16-byte aligned");
+  const size_t total = (size_t)N * (H / 2) * (W / 2);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (src_format == 0)
+    pack_image_s2d_kernel<0><<<blocks, 256, 0, st>>>(d_src, N, H, W, mean, stdv,
+                                                     reinterpret_cast<uint4*>(d_out));
+  else
+    pack_image_s2d_kernel<1><<<blocks, 256, 0, st>>>(d_src, N, H, W, mean, stdv,
+                                                     reinterpret_cast<uint4*>(d_out));
+  SSDSB_LAUNCH_CHECK("pack_image_s2d_kernel");
+  return SSDSB_OK;
+}
+
+extern "C" int ssdsb_maxpool3x3s2_nhwc_bf16(const void* d_x, int N, int H, int W, int C, void* d_y,
+                                            void* stream) {
+  SSDSB_REQUIRE(d_x && d_y, "maxpool: NULL argument");
+  SSDSB_REQUIRE(N >= 1 && H >= 1 && W >= 1 && C >= 8 && C % 8 == 0, "maxpool: bad shape");
+  SSDSB_REQUIRE((((uintptr_t)d_x | (uintptr_t)d_y) & 15) == 0, "maxpool: pointers must be 16-byte aligned");
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  const size_t total = (size_t)N * Ho * Wo * (C / 8);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  maxpool3x3s2_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const uint4*>(d_x), N, H, W, C / 8, Ho, Wo, reinterpret_cast<uint4*>(d_y));
+  SSDSB_LAUNCH_CHECK("maxpool3x3s2_kernel");
+  return SSDSB_OK;
+}

@@ -1,0 +1,117 @@
+"""tcgen05 implicit-GEMM convolution vs a torch fp32 reference of the same op on bf16-rounded
+operands (the kernel multiplies bf16 x bf16 exactly and accumulates in fp32, so the only
+differences are fp32 summation order and the final bf16 rounding of the output).
+Tolerance (written here, as the task requires): |err| <= 2e-2 * max(1, |ref|) for bf16 outputs
+(1 bf16 ulp = 0.4-0.8 %), 1e-3 for fp32 head outputs."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def K():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    from ssds_pytorch_b200 import conv
+    return conv
+
+
+def ref_conv(x_nhwc, w, b, stride, pad, relu, residual=None):
+    x = x_nhwc.float().permute(0, 3, 1, 2)
+    y = F.conv2d(x, w.to(torch.bfloat16).float(), b, stride=stride, padding=pad)
+    if residual is not None:
+        y = y + residual.float().permute(0, 3, 1, 2)
+    if relu:
+        y = y.relu()
+    return y.permute(0, 2, 3, 1)
+
+
+CASES = [
+    # N, H, W, Cin, Cout, k, stride, pad, relu, residual
+    (2, 16, 16, 64, 64, 1, 1, 0, True, False),      # 1x1, BLOCK_N=64
+    (2, 16, 16, 64, 256, 1, 1, 0, False, True),     # 1x1 + residual, BLOCK_N=256
+    (2, 32, 32, 64, 64, 3, 1, 1, True, False),      # 3x3 halo, 2 x 4 tiles
+    (3, 16, 16, 128, 128, 3, 2, 1, True, False),    # 3x3 stride 2, BLOCK_N=128
+    (2, 16, 16, 256, 512, 1, 2, 0, False, False),   # 1x1 stride 2 (downsample)
+    (4, 8, 8, 128, 256, 3, 1, 1, True, False),      # 8x8 map: BN=2 images per tile
+    (8, 4, 4, 64, 128, 3, 2, 1, True, False),       # 4x4 -> 2x2: many images per tile
+    (5, 2, 2, 64, 64, 3, 1, 1, True, False),        # tiny map, ragged batch (5 of 32)
+    (3, 1, 1, 64, 64, 1, 1, 0, True, False),        # 1x1 map
+    (2, 19, 19, 64, 96, 3, 1, 1, True, False),      # 19x19 (MobileNet-SSD level): ragged tile rows
+    (1, 40, 24, 192, 320, 3, 1, 1, True, True),     # non-pow2 channels, several K blocks, edges
+    (2, 64, 64, 512, 64, 1, 1, 0, True, False),     # long K
+]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_conv_nhwc(K, case):
+    N, H, W, Cin, Cout, k, stride, pad, relu, use_res = case
+    g = torch.Generator().manual_seed(hash(case) % (2 ** 31))
+    x = torch.randn((N, H, W, Cin), generator=g).to(torch.bfloat16).cuda()
+    w = torch.randn((Cout, Cin, k, k), generator=g) * (1.0 / np.sqrt(Cin * k * k))
+    b = torch.randn((Cout,), generator=g)
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    res = torch.randn((N, Ho, Wo, Cout), generator=g).to(torch.bfloat16).cuda() if use_res else None
+    y = K.conv2d(x, K.pack_weight(w).cuda(), b.cuda(), k, k, stride, pad, relu, res)
+    torch.cuda.synchronize()
+    ref = ref_conv(x, w.cuda(), b.cuda(), stride, pad, relu, res)
+    err = (y.float() - ref).abs() / ref.abs().clamp(min=1.0)
+    assert err.max().item() <= 2e-2, f"max rel err {err.max().item()}"
+    assert torch.isfinite(y.float()).all()
+
+
+def test_conv_head_split_sigmoid(K):
+    """multibox head (ssd.py:100-103): loc 24 + conf 480 channels fused, fp32 NCHW, sigmoid on conf."""
+    g = torch.Generator().manual_seed(3)
+    N, H, W, Cin, A, Cc = 3, 16, 16, 128, 6, 80
+    x = torch.randn((N, H, W, Cin), generator=g).to(torch.bfloat16).cuda()
+    w = torch.randn((A * 4 + A * Cc, Cin, 3, 3), generator=g) * 0.02
+    b = torch.cat([torch.zeros(A * 4), torch.full((A * Cc,), -4.595)])
+    for sig in (True, False):
+        loc, conf = K.conv2d_head(x, K.pack_weight(w).cuda(), b.cuda(), A * 4, sig)
+        torch.cuda.synchronize()
+        ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.to(torch.bfloat16).float().cuda(), b.cuda(), padding=1)
+        rl, rc = ref[:, :A * 4], ref[:, A * 4:]
+        if sig:
+            rc = rc.sigmoid()
+        assert loc.shape == rl.shape and conf.shape == rc.shape
+        assert (loc - rl).abs().max().item() <= 1e-3
+        assert (conf - rc).abs().max().item() <= (1e-4 if sig else 1e-3)
+
+
+def test_stem_s2d_equals_7x7s2(K):
+    """resnet.py:42-44 conv1 7x7/s2/p3 on a 3-channel image == 4x4/s1 conv on the space-to-depth
+    packing, through pack_image_s2d for both fp32 NCHW and uint8 NHWC inputs."""
+    g = torch.Generator().manual_seed(5)
+    N, H, W = 2, 64, 96
+    w = torch.randn((64, 3, 7, 7), generator=g) * 0.1
+    b = torch.randn((64,), generator=g) * 0.1
+    img_u8 = torch.randint(0, 256, (N, H, W, 3), generator=g, dtype=torch.uint8)
+    for fmt in ("f32", "u8"):
+        if fmt == "f32":
+            src = (img_u8.float() / 255.0).permute(0, 3, 1, 2).contiguous().cuda()
+            packed = K.pack_image_s2d(src, 0.0, 1.0)
+        else:
+            packed = K.pack_image_s2d(img_u8.cuda(), 0.0, 255.0)
+        y = K.conv2d(packed, K.pack_stem_weight_s2d(w).cuda(), b.cuda(), 4, 4, 1, 2, True,
+                     Ho=H // 2, Wo=W // 2)
+        torch.cuda.synchronize()
+        xr = (img_u8.float() / 255.0).to(torch.bfloat16).float().permute(0, 3, 1, 2).cuda()
+        ref = F.conv2d(xr, w.to(torch.bfloat16).float().cuda(), b.cuda(), stride=2, padding=3).relu()
+        ref = ref.permute(0, 2, 3, 1)
+        err = (y.float() - ref).abs() / ref.abs().clamp(min=1.0)
+        assert err.max().item() <= 2e-2, (fmt, err.max().item())
+
+
+def test_maxpool(K):
+    g = torch.Generator().manual_seed(9)
+    for (N, H, W, Cc) in [(2, 32, 32, 64), (1, 15, 17, 8)]:
+        x = torch.randn((N, H, W, Cc), generator=g).to(torch.bfloat16).cuda()
+        y = K.maxpool3x3s2(x)
+        ref = F.max_pool2d(x.float().permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1)
+        assert torch.equal(y.float(), ref)
