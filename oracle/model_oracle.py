@@ -1,0 +1,94 @@
+"""CPU oracle for the conv-stack half of the hot path (torch functional ops, fp32).
+
+TEST INFRASTRUCTURE ONLY (same rule as oracle/box_oracle.py): not importable from the product.
+
+Restates the reference graph with plain `torch.nn.functional` calls on a `state_dict`:
+    ssds/modeling/ssds/ssd.py:42-74       SSD.forward
+    ssds/modeling/nets/resnet.py:41-56    ResNet.forward
+    torchvision.models.resnet Bottleneck/BasicBlock forward (v1.5, stride on the 3x3)
+    ssds/modeling/layers/basic_layers.py:41-57  ConvBNReLUx2
+The convolution/BN arithmetic itself lives in PyTorch (third party, unpinned by the reference —
+SURVEY 8c); the oracle calls the same library (torch 2.11 CPU) the reference would.
+Pinned against the reference's own nn.Module forward by tests/golden/model_small.npz
+(tests/golden/make_golden_model.py).
+
+policy="fp32": the reference's arithmetic.  policy="bf16": the rounding policy of the B200 path —
+BN folded into the weights, weights and every stored activation rounded to bf16, fp32 accumulation,
+fp32 head outputs — so that the CUDA path can be compared within accumulation-order noise.
+"""
+import torch
+import torch.nn.functional as F
+
+EPS = 1e-5
+
+
+def _r(t, policy):
+    return t.to(torch.bfloat16).float() if policy == "bf16" else t
+
+
+def _conv_bn(x, sd, wkey, bnkey, stride, pad, relu, policy, residual=None, bias=None):
+    w = sd[wkey].float()
+    if policy == "bf16":
+        b = bias.float() if bias is not None else torch.zeros(w.shape[0])
+        if bnkey is not None:
+            scale = sd[bnkey + ".weight"].float() / torch.sqrt(sd[bnkey + ".running_var"].float() + EPS)
+            w = w * scale.view(-1, 1, 1, 1)
+            b = (b - sd[bnkey + ".running_mean"].float()) * scale + sd[bnkey + ".bias"].float()
+        y = F.conv2d(x, _r(w, policy), b, stride=stride, padding=pad)
+    else:
+        y = F.conv2d(x, w, bias, stride=stride, padding=pad)
+        if bnkey is not None:
+            y = F.batch_norm(y, sd[bnkey + ".running_mean"], sd[bnkey + ".running_var"],
+                             sd[bnkey + ".weight"], sd[bnkey + ".bias"], False, 0.0, EPS)
+    if residual is not None:
+        y = y + residual
+    if relu:
+        y = F.relu(y)
+    return y
+
+
+def ssd_resnet_forward(sd, x, feature_layer, training=False, policy="fp32"):
+    """x fp32 NCHW (already normalised).  Returns (tuple loc, tuple conf) like ssd.py:42-74."""
+    sd = {k: v for k, v in sd.items()}
+    outputs = [l for l in feature_layer[0] if isinstance(l, int)]
+    x = _r(x.float(), policy)
+    x = _r(_conv_bn(x, sd, "backbone.conv1.weight", "backbone.bn1", 2, 3, True, policy), policy)
+    x = F.max_pool2d(x, 3, 2, 1)
+    feats = []
+    for li in range(1, 5):
+        if li + 1 > max(outputs):
+            break
+        bi = 0
+        while f"backbone.layer{li}.{bi}.conv1.weight" in sd:
+            p = f"backbone.layer{li}.{bi}"
+            stride = 2 if (li > 1 and bi == 0) else 1
+            identity = x
+            if (p + ".downsample.0.weight") in sd:
+                identity = _r(_conv_bn(x, sd, p + ".downsample.0.weight", p + ".downsample.1", stride, 0,
+                                       False, policy), policy)
+            if (p + ".conv3.weight") in sd:
+                y = _r(_conv_bn(x, sd, p + ".conv1.weight", p + ".bn1", 1, 0, True, policy), policy)
+                y = _r(_conv_bn(y, sd, p + ".conv2.weight", p + ".bn2", stride, 1, True, policy), policy)
+                x = _r(_conv_bn(y, sd, p + ".conv3.weight", p + ".bn3", 1, 0, True, policy, identity), policy)
+            else:
+                y = _r(_conv_bn(x, sd, p + ".conv1.weight", p + ".bn1", stride, 1, True, policy), policy)
+                x = _r(_conv_bn(y, sd, p + ".conv2.weight", p + ".bn2", 1, 1, True, policy, identity), policy)
+            bi += 1
+        if li + 1 in outputs:
+            feats.append(x)
+    ei = 0
+    for layer in feature_layer[0]:
+        if isinstance(layer, int):
+            continue
+        stride = 2 if layer == "Conv:S" else 1
+        p = f"extras.{ei}"
+        y = _r(_conv_bn(feats[-1], sd, p + ".0.weight", p + ".1", 1, 0, True, policy), policy)
+        y = _r(_conv_bn(y, sd, p + ".3.weight", p + ".4", stride, 1, True, policy), policy)
+        feats.append(y)
+        ei += 1
+    loc, conf = [], []
+    for l, f in enumerate(feats):
+        loc.append(_conv_bn(f, sd, f"loc.{l}.weight", None, 1, 1, False, policy, bias=sd[f"loc.{l}.bias"]))
+        c = _conv_bn(f, sd, f"conf.{l}.weight", None, 1, 1, False, policy, bias=sd[f"conf.{l}.bias"])
+        conf.append(c if training else torch.sigmoid(c))
+    return tuple(loc), tuple(conf)

@@ -1,0 +1,241 @@
+"""SSD + ResNet conv stack on the tcgen05 implicit-GEMM kernel — the drop-in for `model(x)`.
+
+Mirrors the reference graph
+    ssds/modeling/ssds/ssd.py:42-74        SSD.forward (backbone -> extras -> loc/conf heads, eval sigmoid)
+    ssds/modeling/nets/resnet.py:41-56     ResNet.forward (conv1/bn1/relu/maxpool, layer1..4, outputs)
+    torchvision.models.resnet Bottleneck / BasicBlock (v1.5: stride on the 3x3)
+    ssds/modeling/layers/basic_layers.py:41-57  ConvBNReLUx2 ("Conv:S" / "Conv" extras)
+and consumes the reference's own `state_dict()` (same key names), folding eval-mode BatchNorm into
+bf16 weights once at construction.  `forward(x) -> (tuple loc_l [B,A*4,H,W], tuple conf_l
+[B,A*C,H,W])` in fp32 NCHW exactly like the reference; conf is sigmoid-ed iff eval (ssd.py:72-73).
+
+Every conv (+BN +ReLU +residual) is one kernel launch; each level's loc+conf pair is one fused
+launch.  For a fixed input shape the launch sequence is recorded once into static buffers and can be
+replayed as a CUDA graph (`use_graph=True`).
+"""
+import math
+from collections import OrderedDict
+
+import torch
+
+from . import conv as K
+from .box import configure_ratio_scale, generate_anchors
+
+BN_EPS = 1e-5
+
+
+def _bn(sd, prefix):
+    return (sd[prefix + ".weight"], sd[prefix + ".bias"], sd[prefix + ".running_mean"],
+            sd[prefix + ".running_var"], BN_EPS)
+
+
+class _Conv:
+    """One packed conv: bf16 weights [Cout, taps, Cin] + fp32 bias on the device."""
+
+    def __init__(self, weight, bn, bias, stride, pad, relu, device, stem=False):
+        w, b = K.fold_bn(weight, bn, bias)
+        self.KH, self.KW = (4, 4) if stem else (weight.shape[2], weight.shape[3])
+        self.stride, self.pad, self.relu = (1, 2, relu) if stem else (stride, pad, relu)
+        self.w = (K.pack_stem_weight_s2d(w) if stem else K.pack_weight(w)).to(device)
+        self.bias = b.contiguous().to(device)
+        self.cout = weight.shape[0]
+        self.flops_per_pixel = 2 * weight[0].numel() * self.cout   # algorithmic (un-padded) FLOPs
+
+
+class SSDResNet(torch.nn.Module):
+    """B200 engine for SSD over a torchvision-style ResNet backbone (reference cfg: SSDS='SSD',
+    NETS='ResNet18/34/50/101/152')."""
+
+    def __init__(self, state_dict, feature_layer, num_classes, number_box, device="cuda",
+                 mean=0.0, std=1.0):
+        super().__init__()
+        sd = {k[7:] if k.startswith("module.") else k: v for k, v in state_dict.items()}
+        self.device = torch.device(device)
+        self.num_classes = num_classes
+        self.number_box = list(number_box)
+        self.mean, self.std = float(mean), float(std)
+        dev = self.device
+
+        self.stem = _Conv(sd["backbone.conv1.weight"], _bn(sd, "backbone.bn1"), None, 2, 3, True, dev,
+                          stem=True)
+        # backbone levels: level = layer index + 1 (resnet.py:48-54)
+        self.outputs = [l for l in feature_layer[0] if isinstance(l, int)]
+        self.layers = []
+        for li in range(1, 5):
+            if li + 1 > max(self.outputs):
+                break
+            blocks = []
+            bi = 0
+            while f"backbone.layer{li}.{bi}.conv1.weight" in sd:
+                p = f"backbone.layer{li}.{bi}"
+                bottleneck = (p + ".conv3.weight") in sd
+                stride = 2 if (li > 1 and bi == 0) else 1
+                blk = {}
+                if bottleneck:
+                    blk["convs"] = [
+                        _Conv(sd[p + ".conv1.weight"], _bn(sd, p + ".bn1"), None, 1, 0, True, dev),
+                        _Conv(sd[p + ".conv2.weight"], _bn(sd, p + ".bn2"), None, stride, 1, True, dev),
+                        _Conv(sd[p + ".conv3.weight"], _bn(sd, p + ".bn3"), None, 1, 0, True, dev),
+                    ]
+                else:
+                    blk["convs"] = [
+                        _Conv(sd[p + ".conv1.weight"], _bn(sd, p + ".bn1"), None, stride, 1, True, dev),
+                        _Conv(sd[p + ".conv2.weight"], _bn(sd, p + ".bn2"), None, 1, 1, True, dev),
+                    ]
+                if (p + ".downsample.0.weight") in sd:
+                    blk["down"] = _Conv(sd[p + ".downsample.0.weight"], _bn(sd, p + ".downsample.1"),
+                                        None, stride, 0, False, dev)
+                blocks.append(blk)
+                bi += 1
+            self.layers.append(blocks)
+        # extras: ConvBNReLUx2 (layers_parser.py:17-20)
+        self.extras = []
+        ei = 0
+        for layer in feature_layer[0]:
+            if isinstance(layer, int):
+                continue
+            if layer not in ("Conv:S", "Conv"):
+                raise NotImplementedError(f"extra layer {layer!r} is out of scope (SURVEY 2, rows 9-11)")
+            stride = 2 if layer == "Conv:S" else 1
+            p = f"extras.{ei}"
+            self.extras.append([
+                _Conv(sd[p + ".0.weight"], _bn(sd, p + ".1"), None, 1, 0, True, dev),
+                _Conv(sd[p + ".3.weight"], _bn(sd, p + ".4"), None, stride, 1, True, dev),
+            ])
+            ei += 1
+        # heads: loc + conf fused per level (ssd.py:100-103)
+        self.heads = []
+        for l, nb in enumerate(self.number_box):
+            w = torch.cat([sd[f"loc.{l}.weight"], sd[f"conf.{l}.weight"]], 0)
+            b = torch.cat([sd[f"loc.{l}.bias"], sd[f"conf.{l}.bias"]], 0)
+            h = _Conv(w, None, b, 1, 1, False, dev)
+            h.n_loc = nb * 4
+            self.heads.append(h)
+        self._plans = {}
+        self.training = False
+
+    # ------------------------------------------------------------------ plan (static buffers)
+    def _build_plan(self, images):
+        """Record the launch sequence for this input shape/dtype into preallocated buffers."""
+        dev = self.device
+        if images.dtype == torch.uint8:
+            N, H, W, _ = images.shape
+        else:
+            N, _, H, W = images.shape
+        steps = []          # list of zero-arg callables
+        flops = [0]
+        bf = torch.bfloat16
+
+        def buf(n, h, w, c):
+            return torch.empty((n, h, w, c), dtype=bf, device=dev)
+
+        src = torch.empty_like(images, device=dev)
+        packed = buf(N, H // 2, W // 2, 16)
+        mean, std = self.mean, self.std
+        steps.append(lambda: K.pack_image_s2d(src, mean, std, out=packed))
+
+        def add_conv(cv, x, residual=None, relu=None, Ho=0, Wo=0):
+            n, h, w, _ = x.shape
+            ho = Ho or (h + 2 * cv.pad - cv.KH) // cv.stride + 1
+            wo = Wo or (w + 2 * cv.pad - cv.KW) // cv.stride + 1
+            y = buf(n, ho, wo, cv.cout)
+            r = cv.relu if relu is None else relu
+            steps.append(lambda: K.conv2d(x, cv.w, cv.bias, cv.KH, cv.KW, cv.stride, cv.pad, r,
+                                          residual, out=y, Ho=ho, Wo=wo))
+            flops[0] += cv.flops_per_pixel * n * ho * wo
+            return y
+
+        x = add_conv(self.stem, packed, Ho=H // 2, Wo=W // 2)
+        pooled = buf(N, (x.shape[1] - 1) // 2 + 1, (x.shape[2] - 1) // 2 + 1, x.shape[3])
+        xs = x
+        steps.append(lambda: K.maxpool3x3s2(xs, out=pooled))
+        x = pooled
+        feats = []
+        for li, blocks in enumerate(self.layers):
+            for blk in blocks:
+                identity = add_conv(blk["down"], x) if "down" in blk else x
+                y = x
+                for cv in blk["convs"][:-1]:
+                    y = add_conv(cv, y)
+                x = add_conv(blk["convs"][-1], y, residual=identity, relu=True)
+            if li + 2 in self.outputs:
+                feats.append(x)
+        for ex in self.extras:                         # ssd.py:61-64
+            y = feats[-1]
+            for cv in ex:
+                y = add_conv(cv, y)
+            feats.append(y)
+        locs, confs = [], []
+        for f, h in zip(feats, self.heads):            # ssd.py:67-70
+            n, fh, fw, _ = f.shape
+            loc = torch.empty((n, h.n_loc, fh, fw), dtype=torch.float32, device=dev)
+            conf = torch.empty((n, h.cout - h.n_loc, fh, fw), dtype=torch.float32, device=dev)
+            locs.append(loc)
+            confs.append(conf)
+
+            def run_head(f=f, h=h, loc=loc, conf=conf):
+                K.conv2d_head(f, h.w, h.bias, h.n_loc, not self.training, loc=loc, conf=conf)
+            steps.append(run_head)
+            flops[0] += h.flops_per_pixel * n * fh * fw
+        return {"src": src, "steps": steps, "loc": tuple(locs), "conf": tuple(confs),
+                "flops": flops[0], "graph": None, "launches": len(steps)}
+
+    def plan_for(self, images):
+        key = (tuple(images.shape), images.dtype, self.training)
+        plan = self._plans.get(key)
+        if plan is None:
+            plan = self._plans[key] = self._build_plan(images)
+        return plan
+
+    def run_plan(self, plan, use_graph=False):
+        if use_graph:
+            if plan["graph"] is None:
+                for s in plan["steps"]:                # warm-up: sets kernel attributes etc.
+                    s()
+                torch.cuda.synchronize(self.device)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    for s in plan["steps"]:
+                        s()
+                plan["graph"] = g
+            plan["graph"].replay()
+        else:
+            for s in plan["steps"]:
+                s()
+        return plan["loc"], plan["conf"]
+
+    def forward(self, x, use_graph=False):
+        """x: fp32 NCHW [B,3,H,W] (already `(img-mean)/std`-normalised if mean/std were left at
+        0/1) or uint8 NHWC [B,H,W,3].  Returns (tuple loc, tuple conf) like ssd.py:42-74."""
+        if not x.is_cuda:
+            x = x.to(self.device, non_blocking=True)
+        x = x.contiguous()
+        plan = self.plan_for(x)
+        plan["src"].copy_(x, non_blocking=True)
+        return self.run_plan(plan, use_graph)
+
+    def eval(self):
+        self.training = False
+        return self
+
+    def train(self, mode=True):
+        self.training = bool(mode)
+        return self
+
+
+def create_anchors(model_cfg, model, image_size):
+    """reference model_builder.py:30-56: strides = W_in // W_feat of each conf map, then
+    generate_anchors per level.  The feature sizes come from the plan (no dummy forward needed)."""
+    x = torch.zeros((1, 3, image_size[0], image_size[1]), device=model.device)
+    plan = model.plan_for(x)
+    strides = [image_size[1] // c.shape[-1] for c in plan["conf"]]
+    ratios, scales = configure_ratio_scale(len(strides), model_cfg["ASPECT_RATIOS"], model_cfg["SIZES"])
+    return OrderedDict((strides[i], generate_anchors(strides[i], ratios[i], scales[i], model.device))
+                       for i in range(len(strides)))
+
+
+def number_box_from_cfg(model_cfg):
+    """reference model_builder.py:14-15."""
+    ratios, scales = configure_ratio_scale(len(model_cfg["SIZES"]), model_cfg["ASPECT_RATIOS"],
+                                           [s if isinstance(s, list) else s for s in model_cfg["SIZES"]])
+    return [len(r) * len(s) for r, s in zip(ratios, scales)]

@@ -1,0 +1,112 @@
+"""Synthetic (seeded) weights with the reference's `state_dict()` key names and shapes for
+SSD + ResNet models — there is no network for pretrained checkpoints, and the reference's own random
+init cannot travel to the GPU box.  tests/golden/make_golden_model.py checks that this key/shape set
+equals `create_model(cfg).state_dict()` of the reference.
+
+Key scheme: torchvision ResNet under `backbone.` (resnet.py:9-35), `extras.{j}.{0,1,3,4}` for
+ConvBNReLUx2 (basic_layers.py:41-57), `loc.{l}` / `conf.{l}` heads (ssd.py:100-103).
+"""
+import math
+
+import torch
+
+RESNETS = {
+    "ResNet18": ("basic", [2, 2, 2, 2]), "ResNet34": ("basic", [3, 4, 6, 3]),
+    "ResNet50": ("bottleneck", [3, 4, 6, 3]), "ResNet101": ("bottleneck", [3, 4, 23, 3]),
+    "ResNet152": ("bottleneck", [3, 8, 36, 3]),
+}
+
+
+def ssd_resnet_shapes(nets, feature_layer, number_box, num_classes):
+    """OrderedDict-like list of (key, shape) in the reference's state_dict order."""
+    block, layers = RESNETS[nets]
+    exp = 4 if block == "bottleneck" else 1
+    out = []
+
+    def bn(p, c):
+        out.extend([(p + ".weight", (c,)), (p + ".bias", (c,)), (p + ".running_mean", (c,)),
+                    (p + ".running_var", (c,)), (p + ".num_batches_tracked", ())])
+
+    out.append(("backbone.conv1.weight", (64, 3, 7, 7)))
+    bn("backbone.bn1", 64)
+    inplanes = 64
+    for li, nblocks in enumerate(layers, start=1):
+        planes = 64 * 2 ** (li - 1)
+        for bi in range(nblocks):
+            p = f"backbone.layer{li}.{bi}"
+            stride = 2 if (li > 1 and bi == 0) else 1
+            if block == "bottleneck":
+                out.append((p + ".conv1.weight", (planes, inplanes, 1, 1))); bn(p + ".bn1", planes)
+                out.append((p + ".conv2.weight", (planes, planes, 3, 3))); bn(p + ".bn2", planes)
+                out.append((p + ".conv3.weight", (planes * 4, planes, 1, 1))); bn(p + ".bn3", planes * 4)
+            else:
+                out.append((p + ".conv1.weight", (planes, inplanes, 3, 3))); bn(p + ".bn1", planes)
+                out.append((p + ".conv2.weight", (planes, planes, 3, 3))); bn(p + ".bn2", planes)
+            if stride != 1 or inplanes != planes * exp:
+                out.append((p + ".downsample.0.weight", (planes * exp, inplanes, 1, 1)))
+                bn(p + ".downsample.1", planes * exp)
+            inplanes = planes * exp
+    out.append(("backbone.fc.weight", (1000, 512 * exp)))
+    out.append(("backbone.fc.bias", (1000,)))
+    in_ch, ei = None, 0
+    for layer, depth in zip(feature_layer[0], feature_layer[1]):
+        if not isinstance(layer, int):
+            p = f"extras.{ei}"
+            out.append((p + ".0.weight", (depth // 2, in_ch, 1, 1))); bn(p + ".1", depth // 2)
+            out.append((p + ".3.weight", (depth, depth // 2, 3, 3))); bn(p + ".4", depth)
+            ei += 1
+        in_ch = depth
+    for l, (depth, nb) in enumerate(zip(feature_layer[1], number_box)):
+        out.append((f"loc.{l}.weight", (nb * 4, depth, 3, 3)))
+        out.append((f"loc.{l}.bias", (nb * 4,)))
+    for l, (depth, nb) in enumerate(zip(feature_layer[1], number_box)):
+        out.append((f"conf.{l}.weight", (nb * num_classes, depth, 3, 3)))
+        out.append((f"conf.{l}.bias", (nb * num_classes,)))
+    return out
+
+
+def synthetic_state_dict(nets, feature_layer, number_box, num_classes, seed=0, style="test"):
+    """Deterministic weights.
+    style "init": the reference's initialisation statistics — kaiming-normal convs, BN (1, 0, 0, 1)
+    (torchvision ResNet), xavier extras (ssdsbase.py:27-31), N(0, 0.01) heads with the conf prior bias
+    -log(99) (ssdsbase.py:15-25).
+    style "test": same, but non-trivial BN statistics so that BN folding is actually exercised, with
+    the last BN of each residual block damped to keep activations O(1)."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    prior = -math.log((1 - 0.01) / 0.01)
+    for key, shape in ssd_resnet_shapes(nets, feature_layer, number_box, num_classes):
+        if key.endswith("num_batches_tracked"):
+            sd[key] = torch.tensor(0, dtype=torch.long)
+        elif key.endswith("running_mean"):
+            sd[key] = torch.zeros(shape) if style == "init" else torch.randn(shape, generator=g) * 0.1
+        elif key.endswith("running_var"):
+            sd[key] = torch.ones(shape) if style == "init" else torch.rand(shape, generator=g) + 0.5
+        elif len(shape) == 1 and ".bn" in key or key.endswith((".1.weight", ".1.bias", ".4.weight", ".4.bias")) \
+                and len(shape) == 1:
+            is_w = key.endswith("weight")
+            if style == "init":
+                sd[key] = torch.ones(shape) if is_w else torch.zeros(shape)
+            elif is_w:
+                last = key.endswith(("bn3.weight",)) or ("layer" in key and key.endswith("bn2.weight")
+                                                         and nets in ("ResNet18", "ResNet34"))
+                lo = 0.2 if last else 0.8
+                sd[key] = torch.rand(shape, generator=g) * 0.4 + lo
+            else:
+                sd[key] = torch.randn(shape, generator=g) * 0.1
+        elif key.startswith(("loc.", "conf.")):
+            if key.endswith("weight"):
+                sd[key] = torch.randn(shape, generator=g) * 0.01
+            else:
+                sd[key] = torch.full(shape, prior if key.startswith("conf.") else 0.0)
+        elif key.startswith("backbone.fc"):
+            sd[key] = torch.zeros(shape)
+        elif key.startswith("extras."):
+            fan_in = shape[1] * shape[2] * shape[3]
+            fan_out = shape[0] * shape[2] * shape[3]
+            a = math.sqrt(6.0 / (fan_in + fan_out))
+            sd[key] = (torch.rand(shape, generator=g) * 2 - 1) * a
+        else:  # backbone conv: kaiming normal, fan_out, relu
+            fan_out = shape[0] * shape[2] * shape[3]
+            sd[key] = torch.randn(shape, generator=g) * math.sqrt(2.0 / fan_out)
+    return sd

@@ -1,0 +1,97 @@
+"""Golden vectors for the conv stack, produced by the reference's OWN nn.Module (authoring container
+only; needs /root/reference + the torchvision-compat shim of SURVEY 8c).
+
+    python tests/golden/make_golden_model.py
+
+Builds SSD+ResNet50 / SSD+ResNet18 through the reference's `create_model`, checks that
+ssds_pytorch_b200.synth.ssd_resnet_shapes reproduces its state_dict keys/shapes, loads the synthetic
+weights into it, runs `model.eval()(x)` on a small seeded image batch and stores the outputs
+(fp16-compressed subsample + full-precision checksums) in tests/golden/model_small.npz, together with
+the reference's `create_anchors` strides/anchors and the end-to-end `Decoder` detections.
+"""
+import os
+import sys
+import warnings
+from collections import defaultdict
+from functools import partial
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+REF = os.environ.get("SSDS_REFERENCE", "/root/reference")
+sys.path.insert(0, REF)
+sys.path.insert(1, ROOT)
+warnings.filterwarnings("ignore")
+
+import torchvision as tv                                      # noqa: E402
+tv.models.resnet.model_urls = defaultdict(lambda: None)       # -> url=None: initialize() skips download
+tv.models.densenet.model_urls = defaultdict(lambda: None)
+from torchvision.models import mobilenetv2 as _mv2            # noqa: E402
+tv.models.mobilenet.model_urls = defaultdict(lambda: None)
+tv.models.mobilenet._make_divisible = _mv2._make_divisible
+tv.models.mobilenet.InvertedResidual = _mv2.InvertedResidual
+tv.models.mobilenet.ConvBNReLU = partial(tv.ops.misc.Conv2dNormActivation, norm_layer=torch.nn.BatchNorm2d,
+                                         activation_layer=torch.nn.ReLU6)
+
+from ssds.core import config as rcfg                          # noqa: E402
+from ssds.modeling import model_builder                       # noqa: E402
+from ssds_pytorch_b200 import synth                           # noqa: E402  (pure python part only)
+
+CONF_CH_STRIDE = 7
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "model_small.npz")
+
+
+def build(nets, feature_layer, sizes, ratios, image, num_classes):
+    cfg = rcfg.cfg.MODEL
+    cfg.SSDS, cfg.NETS, cfg.IMAGE_SIZE, cfg.NUM_CLASSES = "SSD", nets, image, num_classes
+    cfg.FEATURE_LAYER, cfg.SIZES, cfg.ASPECT_RATIOS = feature_layer, sizes, ratios
+    return cfg, model_builder.create_model(cfg)
+
+
+def main():
+    G = {}
+    cases = {
+        "r50": ("ResNet50", [[3, 4, 5, "Conv:S", "Conv:S", "Conv:S"], [512, 1024, 2048, 512, 256, 256]],
+                [256, 256], 80, 1),
+        "r18": ("ResNet18", [[3, 4, 5, "Conv:S"], [128, 256, 512, 256]], [96, 160], 20, 3),
+    }
+    for tag, (nets, fl, image, ncls, B) in cases.items():
+        L = len(fl[0])
+        sizes = [[2.0, 2.828] for _ in range(L)]
+        ratios = [[1, 2, 0.5] for _ in range(L)]
+        cfg, model = build(nets, fl, [list(s) for s in sizes], ratios, image, ncls)
+        ref_sd = model.state_dict()
+        nb = [6] * L
+        shapes = synth.ssd_resnet_shapes(nets, fl, nb, ncls)
+        assert [k for k, _ in shapes] == list(ref_sd.keys()), "state_dict key order differs"
+        for k, s in shapes:
+            assert tuple(ref_sd[k].shape) == tuple(s), (k, ref_sd[k].shape, s)
+        sd = synth.synthetic_state_dict(nets, fl, nb, ncls, seed=11, style="test")
+        model.load_state_dict(sd)
+        model.eval()
+        anchors = model_builder.create_anchors(cfg, model, image)
+        g = torch.Generator().manual_seed(1234)
+        x = torch.rand((B, 3, image[0], image[1]), generator=g)
+        with torch.no_grad():
+            loc, conf = model(x)
+        rcfg.cfg.POST_PROCESS.MAX_DETECTIONS_PER_LEVEL = 300
+        decoder = model_builder.create_decoder(rcfg.cfg.POST_PROCESS)
+        with torch.no_grad():
+            det = decoder(loc, conf, anchors)
+        G[tag + "_image"] = np.asarray(image)
+        G[tag + "_x"] = x.numpy().astype(np.float16)          # tests regenerate x from the seed too
+        G[tag + "_strides"] = np.asarray(list(anchors.keys()))
+        for i, (s, a) in enumerate(anchors.items()):
+            G[f"{tag}_anchors{i}"] = a.numpy()
+        for i, (l, c) in enumerate(zip(loc, conf)):
+            G[f"{tag}_loc{i}"] = l.numpy()
+            G[f"{tag}_conf{i}"] = c.numpy()[:, ::CONF_CH_STRIDE]   # channel subsample keeps the file small
+        G[tag + "_det_scores"], G[tag + "_det_boxes"], G[tag + "_det_classes"] = [d.numpy() for d in det]
+        print(tag, "levels", [tuple(c.shape) for c in conf], "dets>0:", int((det[0] > 0).sum()))
+    np.savez_compressed(OUT, **G)
+    print("wrote", OUT, os.path.getsize(OUT) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,63 @@
+"""oracle/model_oracle.py (functional restatement of SSD.forward / ResNet.forward on a state_dict)
+pinned to outputs of the reference's own nn.Module (tests/golden/model_small.npz), and the synthetic
+state_dict key/shape scheme + anchor strides pinned to the reference's create_model/create_anchors."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import box_oracle as O
+from oracle import model_oracle as M
+from ssds_pytorch_b200 import synth
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "model_small.npz")
+
+CASES = {
+    "r50": ("ResNet50", [[3, 4, 5, "Conv:S", "Conv:S", "Conv:S"], [512, 1024, 2048, 512, 256, 256]], 80, 1),
+    "r18": ("ResNet18", [[3, 4, 5, "Conv:S"], [128, 256, 512, 256]], 20, 3),
+}
+
+
+def case_inputs(tag, gold):
+    nets, fl, ncls, B = CASES[tag]
+    L = len(fl[0])
+    sd = synth.synthetic_state_dict(nets, fl, [6] * L, ncls, seed=11, style="test")
+    image = [int(v) for v in gold[tag + "_image"]]
+    x = torch.rand((B, 3, image[0], image[1]), generator=torch.Generator().manual_seed(1234))
+    return sd, fl, x, image, ncls
+
+
+@pytest.mark.parametrize("tag", ["r18", "r50"])
+def test_model_oracle_matches_reference_module(tag):
+    gold = np.load(GOLD)
+    sd, fl, x, image, ncls = case_inputs(tag, gold)
+    np.testing.assert_array_equal(x.numpy().astype(np.float16), gold[tag + "_x"])
+    torch.set_num_threads(8)
+    with torch.no_grad():
+        loc, conf = M.ssd_resnet_forward(sd, x, fl, training=False, policy="fp32")
+    for i, (l, c) in enumerate(zip(loc, conf)):
+        np.testing.assert_allclose(l.numpy(), gold[f"{tag}_loc{i}"], rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(c.numpy()[:, ::7], gold[f"{tag}_conf{i}"], rtol=1e-4, atol=1e-6)
+    # anchors / strides like model_builder.create_anchors (strides = W_in // W_feat)
+    strides = [image[1] // c.shape[-1] for c in conf]
+    np.testing.assert_array_equal(strides, gold[tag + "_strides"])
+    for i, s in enumerate(strides):
+        np.testing.assert_array_equal(O.generate_anchors(s, [1, 2, 0.5], [2.0, 2.828]),
+                                      gold[f"{tag}_anchors{i}"])
+
+
+def test_end_to_end_oracle_detections_r18():
+    """model oracle + box oracle == reference model + reference Decoder, end to end."""
+    from collections import OrderedDict
+    gold = np.load(GOLD)
+    tag = "r18"
+    sd, fl, x, image, ncls = case_inputs(tag, gold)
+    with torch.no_grad():
+        loc, conf = M.ssd_resnet_forward(sd, x, fl, training=False, policy="fp32")
+    loc, conf = [l.numpy() for l in loc], [c.numpy() for c in conf]
+    anchors = OrderedDict((int(s), gold[f"{tag}_anchors{i}"]) for i, s in enumerate(gold[tag + "_strides"]))
+    s, b, c = O.decoder_call(loc, conf, anchors, 0.01, 0.6, 100, 300, True, True)
+    np.testing.assert_array_equal(c, gold[tag + "_det_classes"])
+    np.testing.assert_allclose(s, gold[tag + "_det_scores"], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(b, gold[tag + "_det_boxes"], rtol=1e-4, atol=1e-3)
