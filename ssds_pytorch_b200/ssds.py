@@ -73,6 +73,7 @@ class SSDDetector(object):
         self.decoder = create_decoder(cfg["POST_PROCESS"])
         self.use_graph = use_graph
         self._stage = {}
+        self._copy_stream = None
 
     # -------------------------------------------------------------- device-side entry points
     def detect_device(self, images):
@@ -82,31 +83,47 @@ class SSDDetector(object):
         loc, conf = self.model(images, use_graph=self.use_graph)
         return self.decoder(loc, conf, self.anchors)
 
-    def detect_host(self, imgs, out=None):
-        """Host numpy/torch batch -> pinned staging -> H2D -> detect -> packed [B,D,6] on the host
-        (score, x1, y1, x2, y2, class).  One D2H copy; the caller synchronises the stream."""
+    def detect_host(self, imgs, out=None, slot=0, gather=False):
+        """Host numpy/torch batch -> pinned staging -> H2D -> detect -> [all-gather] -> packed
+        [B,D,6] on the host (score, x1, y1, x2, y2, class).  The H2D copy runs on a side stream into
+        one of two device slots, so the copy of step i+1 overlaps the kernels of step i when callers
+        alternate `slot`.  One small D2H copy; the caller synchronises the current stream."""
         t = torch.as_tensor(imgs)
-        key = (tuple(t.shape), t.dtype)
+        key = (tuple(t.shape), t.dtype, slot)
         st = self._stage.get(key)
         if st is None:
             D = self.decoder.top_n
             st = {"pin_in": torch.empty(t.shape, dtype=t.dtype).pin_memory(),
                   "dev_in": torch.empty(t.shape, dtype=t.dtype, device=self.device),
                   "dev_out": torch.empty((t.shape[0], D, 6), dtype=torch.float32, device=self.device),
-                  "pin_out": torch.empty((t.shape[0], D, 6), dtype=torch.float32).pin_memory()}
+                  "pin_out": None, "copied": torch.cuda.Event(), "consumed": torch.cuda.Event()}
+            st["consumed"].record()
             self._stage[key] = st
-        if not (t.is_pinned() if hasattr(t, "is_pinned") else False):
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        if not t.is_pinned():
             st["pin_in"].copy_(t)
             t = st["pin_in"]
-        st["dev_in"].copy_(t, non_blocking=True)
+        cur = torch.cuda.current_stream()
+        self._copy_stream.wait_event(st["consumed"])      # the slot's previous user has read it
+        with torch.cuda.stream(self._copy_stream):
+            st["dev_in"].copy_(t, non_blocking=True)
+            st["copied"].record()
+        cur.wait_event(st["copied"])
         s, b, c = self.detect_device(st["dev_in"])
+        st["consumed"].record()
         o = st["dev_out"]
         o[:, :, 0] = s
         o[:, :, 1:5] = b
         o[:, :, 5] = c
-        dst = out if out is not None else st["pin_out"]
-        dst.copy_(o, non_blocking=True)
-        return dst
+        if gather:
+            o = gather_detections(o)
+        if out is None:
+            if st["pin_out"] is None or st["pin_out"].shape != o.shape:
+                st["pin_out"] = torch.empty(o.shape, dtype=torch.float32).pin_memory()
+            out = st["pin_out"]
+        out.copy_(o, non_blocking=True)
+        return out
 
     # -------------------------------------------------------------- reference-compatible call
     def __call__(self, imgs):
