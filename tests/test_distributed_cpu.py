@@ -1,0 +1,47 @@
+"""N > 1 host logic on CPU: world_size-2 gloo — contiguous batch sharding + all-gather of the
+fixed-size detection block reproduces the un-sharded result."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from ssds_pytorch_b200.ssds import gather_detections, shard_batch
+    full = torch.arange(6 * 5 * 6, dtype=torch.float32).reshape(6, 5, 6)     # [B=6, D=5, 6]
+    lo, hi = shard_batch(6, rank, world)
+    out = gather_detections(full[lo:hi].clone())
+    q.put((rank, (lo, hi), torch.equal(out, full)))
+    dist.destroy_process_group()
+
+
+def test_shard_and_gather_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+    assert res[0][1] == (0, 3) and res[1][1] == (3, 6)
+    assert all(r[2] for r in res)
+
+
+def test_shard_batch_ragged():
+    from ssds_pytorch_b200.ssds import shard_batch
+    assert [shard_batch(10, r, 4) for r in range(4)] == [(0, 3), (3, 6), (6, 9), (9, 10)]
+    assert shard_batch(2, 3, 4) == (2, 2)
