@@ -155,12 +155,19 @@ SSDSB_API int ssdsb_multibox_loss_sum(const float* d_logits /*[B,A,C,H,W]*/,
  *   whatever Ho/Wo imply (TMA zero-fills out-of-bounds reads).
  * ------------------------------------------------------------------------------------------- */
 enum { SSDSB_CONV_OUT_NHWC_BF16 = 0, SSDSB_CONV_OUT_HEAD_NCHW_F32 = 1 };
+/* x_kind: 0 = plain NHWC.  1 = "windowed stem": x is the space-to-depth image of
+ * ssdsb_pack_image_s2d written with 2 zero pixels of left padding into rows of x_row_pixels
+ * (>= W + 3) pixels; KH = KW = 4, Cin = 16; one K-block = the 4 horizontally adjacent taps x 16
+ * channels = 64 contiguous bf16, fetched through an overlapping-window tensor map. */
+enum { SSDSB_CONV_X_PLAIN = 0, SSDSB_CONV_X_WINDOWED_STEM = 1 };
 
 typedef struct {
   int N, H, W, Cin;
   int Cout, KH, KW, stride, pad;
   int Ho, Wo;
   int x_cstride, out_cstride, res_cstride;
+  int x_row_pixels; /* pixels per image row in memory (0 => W) */
+  int x_kind;
   int w_rows;
   int relu;
   int out_mode;
@@ -178,7 +185,10 @@ SSDSB_API int ssdsb_conv2d_bf16(const ssdsb_conv_desc* desc, const void* d_x, co
  * channels 12..15 zero) on which the 7x7/s2 stem is a 4x4/s1 convolution.
  * src_format 0: fp32 NCHW [N,3,H,W]; 1: uint8 NHWC [N,H,W,3].  H and W must be even. */
 SSDSB_API int ssdsb_pack_image_s2d(const void* d_src, int src_format, int N, int H, int W,
-                                   float mean, float std, void* d_out, void* stream);
+                                   float mean, float std, int out_row_pixels /*0 => W/2*/,
+                                   int left_pad /*pixels skipped at the start of each output row;
+                                   the caller zeroes the padding once*/,
+                                   void* d_out, void* stream);
 
 /* 3x3 / stride 2 / pad 1 max pooling on NHWC bf16 (resnet.py:45 `self.maxpool`). C % 8 == 0. */
 SSDSB_API int ssdsb_maxpool3x3s2_nhwc_bf16(const void* d_x, int N, int H, int W, int C, void* d_y,

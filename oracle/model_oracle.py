@@ -29,7 +29,7 @@ def _r(t, policy):
 def _conv_bn(x, sd, wkey, bnkey, stride, pad, relu, policy, residual=None, bias=None):
     w = sd[wkey].float()
     if policy == "bf16":
-        b = bias.float() if bias is not None else torch.zeros(w.shape[0])
+        b = bias.float() if bias is not None else torch.zeros(w.shape[0], device=w.device)
         if bnkey is not None:
             scale = sd[bnkey + ".weight"].float() / torch.sqrt(sd[bnkey + ".running_var"].float() + EPS)
             w = w * scale.view(-1, 1, 1, 1)

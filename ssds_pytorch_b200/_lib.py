@@ -26,7 +26,7 @@ class ConvDesc(C.Structure):
     """mirror of `ssdsb_conv_desc` (include/ssdsb200.h)."""
     _fields_ = [(n, C.c_int) for n in (
         "N", "H", "W", "Cin", "Cout", "KH", "KW", "stride", "pad", "Ho", "Wo",
-        "x_cstride", "out_cstride", "res_cstride", "w_rows", "relu", "out_mode", "n_loc",
+        "x_cstride", "out_cstride", "res_cstride", "x_row_pixels", "x_kind", "w_rows", "relu", "out_mode", "n_loc",
         "sigmoid")]
 
 
@@ -55,7 +55,7 @@ def _load():
         "ssdsb_multibox_loss": (i, [vp, vp, vp, i, i, i, i, i, i, vp, vp, sz, vp]),
         "ssdsb_multibox_loss_sum": (i, [vp, vp, i, i, i, i, i, i, vp, vp, vp, sz, vp]),
         "ssdsb_conv2d_bf16": (i, [C.POINTER(ConvDesc), vp, vp, vp, vp, vp, vp, vp]),
-        "ssdsb_pack_image_s2d": (i, [vp, i, i, i, i, f, f, vp, vp]),
+        "ssdsb_pack_image_s2d": (i, [vp, i, i, i, i, f, f, i, i, vp, vp]),
         "ssdsb_maxpool3x3s2_nhwc_bf16": (i, [vp, i, i, i, i, vp, vp]),
     }
     for name, (res, args) in sig.items():

@@ -56,9 +56,14 @@ def pack_stem_weight_s2d(w_folded):
     return out.reshape(cout, 16, 16).to(torch.bfloat16).contiguous()
 
 
-def conv2d(x, w, bias, KH, KW, stride, pad, relu=False, residual=None, out=None, Ho=0, Wo=0):
-    """x NHWC bf16 [N,H,W,Cin] -> NHWC bf16 [N,Ho,Wo,Cout]; w bf16 [Cout, KH*KW, Cin]."""
+def conv2d(x, w, bias, KH, KW, stride, pad, relu=False, residual=None, out=None, Ho=0, Wo=0,
+           x_kind=0, x_width=None):
+    """x NHWC bf16 [N,H,W,Cin] -> NHWC bf16 [N,Ho,Wo,Cout]; w bf16 [Cout, KH*KW, Cin].
+    x_kind=1: x is the left-padded s2d image [N,H,row_px,16] (logical width x_width), windowed stem."""
     N, H, W, Cin = x.shape
+    row_px = 0
+    if x_width is not None:
+        row_px, W = W, x_width
     Cout = w.shape[0]
     ho = Ho or (H + 2 * pad - KH) // stride + 1
     wo = Wo or (W + 2 * pad - KW) // stride + 1
@@ -67,6 +72,7 @@ def conv2d(x, w, bias, KH, KW, stride, pad, relu=False, residual=None, out=None,
     d = _lib.ConvDesc(N=N, H=H, W=W, Cin=Cin, Cout=Cout, KH=KH, KW=KW, stride=stride, pad=pad,
                       Ho=ho, Wo=wo, x_cstride=x.stride(2), out_cstride=out.stride(2),
                       res_cstride=residual.stride(2) if residual is not None else 0,
+                      x_row_pixels=row_px, x_kind=x_kind,
                       w_rows=w.shape[0], relu=int(relu), out_mode=0, n_loc=0, sigmoid=0)
     with torch.cuda.device(x.device):
         check(lib.ssdsb_conv2d_bf16(C.byref(d), ptr(x), ptr(w), ptr(bias), ptr(residual), ptr(out),
@@ -87,6 +93,7 @@ def conv2d_head(x, w, bias, n_loc, sigmoid, KH=3, KW=3, stride=1, pad=1, loc=Non
         conf = torch.empty((N, Cout - n_loc, ho, wo), dtype=torch.float32, device=x.device)
     d = _lib.ConvDesc(N=N, H=H, W=W, Cin=Cin, Cout=Cout, KH=KH, KW=KW, stride=stride, pad=pad,
                       Ho=ho, Wo=wo, x_cstride=x.stride(2), out_cstride=0, res_cstride=0,
+                      x_row_pixels=0, x_kind=0,
                       w_rows=w.shape[0], relu=0, out_mode=1, n_loc=n_loc, sigmoid=int(sigmoid))
     with torch.cuda.device(x.device):
         check(lib.ssdsb_conv2d_bf16(C.byref(d), ptr(x), ptr(w), ptr(bias), None, ptr(loc), ptr(conf),
@@ -94,8 +101,13 @@ def conv2d_head(x, w, bias, n_loc, sigmoid, KH=3, KW=3, stride=1, pad=1, loc=Non
     return loc, conf
 
 
-def pack_image_s2d(images, mean=0.0, std=1.0, out=None):
-    """images: fp32 NCHW [N,3,H,W] or uint8 NHWC [N,H,W,3] (CUDA) -> bf16 [N,H/2,W/2,16]."""
+STEM_LEFT_PAD = 2      # zero pixels before each s2d row (the windowed stem reads [w-2, w+2))
+STEM_ROW_EXTRA = 4     # row_px = W/2 + 4 (2 left + >= 1 right, kept even)
+
+
+def pack_image_s2d(images, mean=0.0, std=1.0, out=None, padded=False):
+    """images: fp32 NCHW [N,3,H,W] or uint8 NHWC [N,H,W,3] (CUDA) -> bf16 [N,H/2,W/2,16]
+    (padded=True: [N,H/2,W/2+4,16] with the image at columns [2, 2+W/2) and zero padding)."""
     if images.dtype == torch.uint8:
         N, H, W, _ = images.shape
         fmt = 1
@@ -105,10 +117,16 @@ def pack_image_s2d(images, mean=0.0, std=1.0, out=None):
         fmt = 0
     images = images.contiguous()
     if out is None:
-        out = torch.empty((N, H // 2, W // 2, 16), dtype=torch.bfloat16, device=images.device)
+        if padded:
+            out = torch.zeros((N, H // 2, W // 2 + STEM_ROW_EXTRA, 16), dtype=torch.bfloat16,
+                              device=images.device)
+        else:
+            out = torch.empty((N, H // 2, W // 2, 16), dtype=torch.bfloat16, device=images.device)
+    row_px = out.shape[2]
+    left = STEM_LEFT_PAD if row_px != W // 2 else 0
     with torch.cuda.device(images.device):
-        check(lib.ssdsb_pack_image_s2d(ptr(images), fmt, N, H, W, float(mean), float(std), ptr(out),
-                                       stream_ptr()), "pack_image_s2d")
+        check(lib.ssdsb_pack_image_s2d(ptr(images), fmt, N, H, W, float(mean), float(std), row_px, left,
+                                       ptr(out), stream_ptr()), "pack_image_s2d")
     return out
 
 

@@ -22,6 +22,10 @@
 //     which the stem is a 4x4/s1 convolution; its K-block is one tap x 16 channels (32-byte rows,
 //     SWIZZLE_32B, one K=16 MMA per block) — same kernel, BLOCK_K = 16.
 //
+//   * NHWC epilogue: the 128x64 bf16 sub-tile is staged in 128B-swizzled shared memory and written
+//     with ONE 4-D TMA store (full 128-byte lines, ragged edges clipped by TMA); the residual
+//     sub-tile is TMA-loaded into the same staging buffer two chunks ahead and added in place.
+//
 // Warp roles (256 threads): w0 TMA producer, w1 MMA issuer, w2 TMEM allocator, w4-7 epilogue.
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -95,6 +99,27 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1,
+                                             int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+          reinterpret_cast<uint64_t>(map)),
+      "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() {
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ void epi_bar_sync() {   // the 128 epilogue threads only
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+}
 __device__ __forceinline__ void tcgen05_fence_before() {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 }
@@ -159,33 +184,64 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 // ---------------------------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------------------------
+constexpr int MAX_STAGES = 16;
+constexpr int MAX_STAGING = 4;
+constexpr int STAGING_BYTES = BLOCK_M * 128;   // 128 rows x 64 bf16
+
 template <int BLOCK_N, int BLOCK_K>
 struct ConvSmem {
   static constexpr int ROW_BYTES = BLOCK_K * 2;
   static constexpr int A_STAGE_BYTES = BLOCK_M * ROW_BYTES;
   static constexpr int B_STAGE_BYTES = BLOCK_N * ROW_BYTES;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES = (BLOCK_K == 16) ? 16 : ((BLOCK_N >= 256) ? 4 : (BLOCK_N >= 128 ? 6 : 8));
   static constexpr int TMEM_COLS = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;
-  static constexpr int BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
+  static constexpr int BAR_BYTES = 512;
+  static constexpr int MAX_BYTES = 232448;  // 227 KiB opt-in limit per CTA
   static_assert(STAGE_BYTES % 1024 == 0, "stage bases must stay 1024-byte aligned");
+  static int stages_for(int n_staging) {
+    int s = (MAX_BYTES - 1024 - BAR_BYTES - n_staging * STAGING_BYTES) / STAGE_BYTES;
+    return s > MAX_STAGES ? MAX_STAGES : s;
+  }
+  static int bytes(int stages, int n_staging) {
+    return stages * STAGE_BYTES + n_staging * STAGING_BYTES + 1024 + BAR_BYTES;
+  }
 };
+
+struct TileCoord {
+  int n_tile, w0, h0, n0;
+};
+__device__ __forceinline__ TileCoord tile_coord(const ConvKernelParams& p, int tile) {
+  TileCoord t;
+  t.n_tile = tile % p.n_tiles;
+  const int m = tile / p.n_tiles;
+  const int tw = m % p.tiles_w;
+  const int th = (m / p.tiles_w) % p.tiles_h;
+  const int tn = m / (p.tiles_w * p.tiles_h);
+  t.w0 = tw * p.BW;
+  t.h0 = th * p.BH;
+  t.n0 = tn * p.BN;
+  return t;
+}
 
 template <int BLOCK_N, int BLOCK_K>
 __global__ void __launch_bounds__(CONV_NT, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR,
                   const __grid_constant__ ConvKernelParams p) {
   using S = ConvSmem<BLOCK_N, BLOCK_K>;
   constexpr int A_STAGE_BYTES = S::A_STAGE_BYTES;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>(
       (reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::STAGES * S::STAGE_BYTES);
-  uint64_t* full_bar = bars;                      // [STAGES]
-  uint64_t* empty_bar = bars + S::STAGES;         // [STAGES]
-  uint64_t* tmem_full = bars + 2 * S::STAGES;     // [2]
-  uint64_t* tmem_empty = bars + 2 * S::STAGES + 2;// [2]
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * S::STAGES + 4);
+  const int STAGES = p.stages;
+  unsigned char* staging = smem + STAGES * S::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + p.n_staging * STAGING_BYTES);
+  uint64_t* full_bar = bars;                           // [MAX_STAGES]
+  uint64_t* empty_bar = bars + MAX_STAGES;             // [MAX_STAGES]
+  uint64_t* tmem_full = bars + 2 * MAX_STAGES;         // [2]
+  uint64_t* tmem_empty = bars + 2 * MAX_STAGES + 2;    // [2]
+  uint64_t* res_full = bars + 2 * MAX_STAGES + 4;      // [MAX_STAGING]
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4 + MAX_STAGING);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -193,9 +249,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (p.tma_store) tma_prefetch_desc(&tmY);
+    if (p.residual) tma_prefetch_desc(&tmR);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < S::STAGES; ++s) {
+    for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
@@ -203,6 +261,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_init(&tmem_full[a], 1);
       mbar_init(&tmem_empty[a], 4);  // one arrive per epilogue warp
     }
+    for (int r = 0; r < MAX_STAGING; ++r) mbar_init(&res_full[r], 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -228,12 +287,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int n_tile = tile % p.n_tiles;
-        const int m = tile / p.n_tiles;
-        const int tw = m % p.tiles_w;
-        const int th = (m / p.tiles_w) % p.tiles_h;
-        const int tn = m / (p.tiles_w * p.tiles_h);
-        const int w0 = tw * p.BW, h0 = th * p.BH, n0 = tn * p.BN;
+        const TileCoord t = tile_coord(p, tile);
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           unsigned char* sa = smem + stage * S::STAGE_BYTES;
@@ -242,10 +296,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const int tap = kb / p.kc_per_tap;
           const int kc = kb - tap * p.kc_per_tap;
           const int kh = tap / p.KW, kw = tap - kh * p.KW;
-          tma_load_4d(sa, &tmA, &full_bar[stage], kc * BLOCK_K, w0 * p.stride + kw - p.pad,
-                      h0 * p.stride + kh - p.pad, n0);
-          tma_load_2d(sb, &tmB, &full_bar[stage], kb * BLOCK_K, n_tile * BLOCK_N);
-          if (++stage == S::STAGES) {
+          tma_load_4d(sa, &tmA, &full_bar[stage], kc * BLOCK_K, t.w0 * p.stride + kw - p.pad_w,
+                      t.h0 * p.stride + kh - p.pad_h, t.n0);
+          tma_load_2d(sb, &tmB, &full_bar[stage], kb * BLOCK_K, t.n_tile * BLOCK_N);
+          if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
@@ -277,7 +331,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                       (kb > 0 || k > 0) ? 1u : 0u);
           }
           tcgen05_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
-          if (++stage == S::STAGES) {
+          if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
@@ -293,84 +347,177 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // =============================== epilogue ===============================
     const int q = warp - 4;                   // TMEM lane quarter this warp may read
     const int r = q * 32 + lane;              // row of the tile == TMEM lane
+    const bool elected = (threadIdx.x == 128);
     int acc = 0;
     uint32_t acc_phase = 0;
+    // staging ring state (TMA-store path)
+    const int R = p.n_staging;
+    int g = 0;                                // chunks processed so far (all epilogue threads)
+    int issued = 0;                           // residual loads issued (elected thread only)
+    int it_tile = blockIdx.x, it_chunk = 0;   // iterator of the residual prefetcher
+    const bool has_res = (p.residual != nullptr);
+
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int n_tile = tile % p.n_tiles;
-      const int m = tile / p.n_tiles;
-      const int tw = m % p.tiles_w;
-      const int th = (m / p.tiles_w) % p.tiles_h;
-      const int tn = m / (p.tiles_w * p.tiles_h);
+      const TileCoord t = tile_coord(p, tile);
       // row r -> (bn, bh, bw) in TMA box order (w fastest)
       const int bw = r % p.BW;
       const int bh = (r / p.BW) % p.BH;
       const int bn = r / (p.BW * p.BH);
-      const int w = tw * p.BW + bw, h = th * p.BH + bh, n = tn * p.BN + bn;
+      const int w = t.w0 + bw, h = t.h0 + bh, n = t.n0 + bn;
       const bool row_ok = (r < rows) && (w < p.Wo) && (h < p.Ho) && (n < p.N);
 
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
-      const size_t pix = ((size_t)n * p.Ho + h) * p.Wo + w;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-        const int col0 = n_tile * BLOCK_N + c0;
-        if (col0 >= p.Cout) break;            // warp-uniform
-        uint32_t v[32];
-        tmem_ld32(t_row + (uint32_t)c0, v);
-        tmem_ld_wait();
-        if (p.mode == CONV_OUT_NHWC_BF16) {
-          float f[32];
+
+      if (p.mode == CONV_OUT_NHWC_BF16 && p.tma_store) {
+        // ---------- staged path: 64-column chunks through swizzled smem + TMA store ----------
+        const int ncols = min(BLOCK_N, p.Cout - t.n_tile * BLOCK_N);
+        const int nchunks = ncols >> 6;
+        for (int c = 0; c < nchunks; ++c, ++g) {
+          const int slot = g % R;
+          unsigned char* sbuf = staging + slot * STAGING_BYTES;
+          const int col0 = t.n_tile * BLOCK_N + c * 64;
+          if (elected) {
+            if (has_res) {
+              // keep residual loads two chunks ahead; a slot is reusable once the store that last
+              // read it (chunk issued - R) has finished reading shared memory
+              while (issued <= g + 2 && it_tile < num_tiles) {
+                // stores committed so far: g; need store (issued - R) read-complete
+                const int pending_ok = g - 1 - (issued - R);   // groups that may stay in flight
+                if (issued >= R) {
+                  if (pending_ok <= 0) tma_store_wait_read<0>();
+                  else if (pending_ok == 1) tma_store_wait_read<1>();
+                  else if (pending_ok == 2) tma_store_wait_read<2>();
+                  else tma_store_wait_read<3>();
+                }
+                const TileCoord ti = tile_coord(p, it_tile);
+                const int islot = issued % R;
+                mbar_expect_tx(&res_full[islot], (uint32_t)rows * 128u);
+                tma_load_4d(staging + islot * STAGING_BYTES, &tmR, &res_full[islot],
+                            ti.n_tile * BLOCK_N + it_chunk * 64, ti.w0, ti.h0, ti.n0);
+                ++issued;
+                const int inc = min(BLOCK_N, p.Cout - ti.n_tile * BLOCK_N) >> 6;
+                if (++it_chunk == inc) {
+                  it_chunk = 0;
+                  it_tile += gridDim.x;
+                }
+              }
+            } else {
+              if (R >= 4) tma_store_wait_read<3>();
+              else tma_store_wait_read<1>();
+            }
+          }
+          if (has_res) {
+            mbar_wait(&res_full[slot], (uint32_t)(g / R) & 1u);
+          } else {
+            epi_bar_sync();                    // slot free for everybody
+          }
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + __ldg(p.bias + col0 + j);
-          if (row_ok) {
-            if (p.residual) {
-              const uint4* rp = reinterpret_cast<const uint4*>(
-                  reinterpret_cast<const __nv_bfloat16*>(p.residual) + pix * p.res_cstride + col0);
+          for (int half = 0; half < 2; ++half) {
+            uint32_t v[32];
+            tmem_ld32(t_row + (uint32_t)(c * 64 + half * 32), v);
+            tmem_ld_wait();
+            const float* bp = p.bias + col0 + half * 32;
 #pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                const uint4 rv = __ldg(rp + g);
+            for (int gq = 0; gq < 4; ++gq) {
+              const int chunk16 = half * 4 + gq;                     // 16-byte piece of the 128B row
+              uint4* sp = reinterpret_cast<uint4*>(sbuf + r * 128 + ((chunk16 ^ (r & 7)) << 4));
+              float f[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[gq * 8 + e]) + __ldg(bp + gq * 8 + e);
+              if (has_res) {
+                const uint4 rv = *sp;
                 const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                   const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&rw[e]);
-                  f[g * 8 + e * 2 + 0] += __bfloat162float(h2.x);
-                  f[g * 8 + e * 2 + 1] += __bfloat162float(h2.y);
+                  f[e * 2 + 0] += __bfloat162float(h2.x);
+                  f[e * 2 + 1] += __bfloat162float(h2.y);
                 }
               }
-            }
-            if (p.relu) {
+              if (p.relu) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
-            }
-            uint4* yp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.y) +
-                                                 pix * p.out_cstride + col0);
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
+                for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.0f);
+              }
               uint4 o;
-              o.x = pack_bf16(f[g * 8 + 0], f[g * 8 + 1]);
-              o.y = pack_bf16(f[g * 8 + 2], f[g * 8 + 3]);
-              o.z = pack_bf16(f[g * 8 + 4], f[g * 8 + 5]);
-              o.w = pack_bf16(f[g * 8 + 6], f[g * 8 + 7]);
-              yp[g] = o;
+              o.x = pack_bf16(f[0], f[1]);
+              o.y = pack_bf16(f[2], f[3]);
+              o.z = pack_bf16(f[4], f[5]);
+              o.w = pack_bf16(f[6], f[7]);
+              *sp = o;
             }
           }
-        } else {
-          // multibox head: channels [0, n_loc) -> loc fp32 NCHW; [n_loc, Cout) -> sigmoid -> conf
-          const size_t hw = (size_t)p.Ho * p.Wo;
-          const size_t sp = (size_t)h * p.Wo + w;
-          float* loc = reinterpret_cast<float*>(p.y) + (size_t)n * p.n_loc * hw + sp;
-          float* conf = reinterpret_cast<float*>(p.y2) + (size_t)n * (p.Cout - p.n_loc) * hw + sp;
+          fence_proxy_async();                 // generic-proxy smem writes -> visible to TMA
+          epi_bar_sync();
+          if (elected) {
+            tma_store_4d(&tmY, sbuf, col0, t.w0, t.h0, t.n0);
+            tma_store_commit();
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+          const int col0 = t.n_tile * BLOCK_N + c0;
+          if (col0 >= p.Cout) break;            // warp-uniform
+          uint32_t v[32];
+          tmem_ld32(t_row + (uint32_t)c0, v);
+          tmem_ld_wait();
+          if (p.mode == CONV_OUT_NHWC_BF16) {
+            // direct path (Cout not a multiple of 64): 16-byte stores from each row owner
+            const size_t pix = ((size_t)n * p.Ho + h) * p.Wo + w;
+            float f[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int col = col0 + j;
-            if (col < p.Cout && row_ok) {
-              const float x = __uint_as_float(v[j]) + __ldg(p.bias + col);
-              if (col < p.n_loc) {
-                loc[(size_t)col * hw] = x;
-              } else {
-                const float s = p.sigmoid ? 1.0f / (1.0f + __expf(-x)) : x;
-                __stcs(conf + (size_t)(col - p.n_loc) * hw, s);
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + __ldg(p.bias + col0 + j);
+            if (row_ok) {
+              if (has_res) {
+                const uint4* rp = reinterpret_cast<const uint4*>(
+                    reinterpret_cast<const __nv_bfloat16*>(p.residual) + pix * p.res_cstride + col0);
+#pragma unroll
+                for (int gq = 0; gq < 4; ++gq) {
+                  const uint4 rv = __ldg(rp + gq);
+                  const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&rw[e]);
+                    f[gq * 8 + e * 2 + 0] += __bfloat162float(h2.x);
+                    f[gq * 8 + e * 2 + 1] += __bfloat162float(h2.y);
+                  }
+                }
+              }
+              if (p.relu) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+              }
+              uint4* yp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.y) +
+                                                   pix * p.out_cstride + col0);
+#pragma unroll
+              for (int gq = 0; gq < 4; ++gq) {
+                uint4 o;
+                o.x = pack_bf16(f[gq * 8 + 0], f[gq * 8 + 1]);
+                o.y = pack_bf16(f[gq * 8 + 2], f[gq * 8 + 3]);
+                o.z = pack_bf16(f[gq * 8 + 4], f[gq * 8 + 5]);
+                o.w = pack_bf16(f[gq * 8 + 6], f[gq * 8 + 7]);
+                yp[gq] = o;
+              }
+            }
+          } else {
+            // multibox head: channels [0, n_loc) -> loc fp32 NCHW; [n_loc, Cout) -> sigmoid -> conf
+            const size_t hw = (size_t)p.Ho * p.Wo;
+            const size_t sp = (size_t)h * p.Wo + w;
+            float* loc = reinterpret_cast<float*>(p.y) + (size_t)n * p.n_loc * hw + sp;
+            float* conf = reinterpret_cast<float*>(p.y2) + (size_t)n * (p.Cout - p.n_loc) * hw + sp;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int col = col0 + j;
+              if (col < p.Cout && row_ok) {
+                const float x = __uint_as_float(v[j]) + __ldg(p.bias + col);
+                if (col < p.n_loc) {
+                  loc[(size_t)col * hw] = x;
+                } else {
+                  const float sg = p.sigmoid ? 1.0f / (1.0f + __expf(-x)) : x;
+                  __stcs(conf + (size_t)(col - p.n_loc) * hw, sg);
+                }
               }
             }
           }
@@ -384,6 +531,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         acc_phase ^= 1;
       }
     }
+    if (elected && p.tma_store) tma_store_wait_all();   // smem must outlive the last store
   }
 
   tcgen05_fence_before();
@@ -423,18 +571,25 @@ int pick_block_n(int cout) {
 }
 
 template <int BLOCK_N, int BLOCK_K>
-int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvKernelParams& kp, int sms,
+int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY,
+           const CUtensorMap& tmR, ConvKernelParams& kp, bool want_staging, int sms,
            cudaStream_t st) {
   using S = ConvSmem<BLOCK_N, BLOCK_K>;
   static bool configured = false;
   if (!configured) {
     SSDSB_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BLOCK_N, BLOCK_K>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, S::BYTES));
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, S::MAX_BYTES));
     configured = true;
   }
+  kp.n_staging = want_staging ? (kp.residual ? 4 : 2) : 0;
+  kp.tma_store = want_staging ? 1 : 0;
+  kp.stages = S::stages_for(kp.n_staging);
+  if (kp.stages > kp.num_k_blocks * 4) kp.stages = kp.num_k_blocks * 4;   // nothing to gain beyond
+  if (kp.stages < 2) kp.stages = 2;
+  const int smem = S::bytes(kp.stages, kp.n_staging);
   const int tiles = kp.tiles_w * kp.tiles_h * kp.tiles_n * kp.n_tiles;
   const int grid = tiles < sms ? tiles : sms;
-  conv_igemm_kernel<BLOCK_N, BLOCK_K><<<grid, CONV_NT, S::BYTES, st>>>(tmA, tmB, kp);
+  conv_igemm_kernel<BLOCK_N, BLOCK_K><<<grid, CONV_NT, smem, st>>>(tmA, tmB, tmY, tmR, kp);
   SSDSB_LAUNCH_CHECK("conv_igemm_kernel");
   return SSDSB_OK;
 }
@@ -456,9 +611,18 @@ extern "C" int ssdsb_conv2d_bf16(const ssdsb_conv_desc* d, const void* x, const 
   const int Ho = d->Ho > 0 ? d->Ho : (d->H + 2 * d->pad - d->KH) / d->stride + 1;
   const int Wo = d->Wo > 0 ? d->Wo : (d->W + 2 * d->pad - d->KW) / d->stride + 1;
   SSDSB_REQUIRE(Ho >= 1 && Wo >= 1, "conv2d: empty output");
-  const int block_k = (d->Cin == 16) ? 16 : 64;
-  SSDSB_REQUIRE(d->Cin % block_k == 0, "conv2d: Cin=%d must be 16 or a multiple of 64", d->Cin);
+  const bool windowed = d->x_kind == SSDSB_CONV_X_WINDOWED_STEM;
+  const int block_k = (d->Cin == 16 && !windowed) ? 16 : 64;
   const int cs = d->x_cstride ? d->x_cstride : d->Cin;
+  const int row_px = d->x_row_pixels ? d->x_row_pixels : d->W;
+  if (windowed) {
+    SSDSB_REQUIRE(d->Cin == 16 && d->KH == 4 && d->KW == 4 && d->stride == 1 && d->pad == 2 && cs == 16,
+                  "conv2d: the windowed stem needs Cin=16, 4x4/s1/p2 on a packed s2d image");
+    SSDSB_REQUIRE(row_px >= d->W + 3, "conv2d: windowed stem rows need >= W+3 pixels (2 left + 1 right pad)");
+  } else {
+    SSDSB_REQUIRE(d->Cin % block_k == 0, "conv2d: Cin=%d must be 16 or a multiple of 64", d->Cin);
+    SSDSB_REQUIRE(row_px >= d->W, "conv2d: x_row_pixels < W");
+  }
   SSDSB_REQUIRE(cs >= d->Cin && cs % 8 == 0, "conv2d: bad input channel stride %d", cs);
   SSDSB_REQUIRE(d->out_mode == CONV_OUT_NHWC_BF16 || d->out_mode == CONV_OUT_HEAD_NCHW_F32,
                 "conv2d: bad out_mode");
@@ -497,11 +661,15 @@ extern "C" int ssdsb_conv2d_bf16(const ssdsb_conv_desc* d, const void* x, const 
   kp.tiles_n = (d->N + BN - 1) / BN;
   const int block_n = pick_block_n(d->Cout);
   kp.n_tiles = (d->Cout + block_n - 1) / block_n;
-  kp.taps = d->KH * d->KW;
-  kp.KW = d->KW;
-  kp.kc_per_tap = d->Cin / block_k;
+  if (windowed) {          // taps = the 4 kernel rows; the 4 horizontal taps live inside the K-block
+    kp.taps = 4; kp.KW = 1; kp.kc_per_tap = 1;
+    kp.pad_w = 0; kp.pad_h = 2;
+  } else {
+    kp.taps = d->KH * d->KW; kp.KW = d->KW; kp.kc_per_tap = d->Cin / block_k;
+    kp.pad_w = d->pad; kp.pad_h = d->pad;
+  }
   kp.num_k_blocks = kp.taps * kp.kc_per_tap;
-  kp.stride = d->stride; kp.pad = d->pad;
+  kp.stride = d->stride;
   kp.Ho = Ho; kp.Wo = Wo; kp.N = d->N;
   kp.Cout = d->Cout;
   kp.out_cstride = d->out_cstride;
@@ -518,13 +686,19 @@ extern "C" int ssdsb_conv2d_bf16(const ssdsb_conv_desc* d, const void* x, const 
   const CUtensorMapSwizzle swz = block_k == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B;
   alignas(64) CUtensorMap tmA;
   alignas(64) CUtensorMap tmB;
+  alignas(64) CUtensorMap tmY;
+  alignas(64) CUtensorMap tmR;
   {
     cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
-    cuuint64_t strides[3] = {(cuuint64_t)cs * 2, (cuuint64_t)d->W * cs * 2,
-                             (cuuint64_t)d->H * d->W * cs * 2};
+    cuuint64_t strides[3] = {(cuuint64_t)cs * 2, (cuuint64_t)row_px * cs * 2,
+                             (cuuint64_t)d->H * row_px * cs * 2};
     cuuint32_t box[4] = {(cuuint32_t)block_k, (cuuint32_t)(BW * d->stride),
                          (cuuint32_t)(BH * d->stride), (cuuint32_t)BN};
     cuuint32_t estr[4] = {1, (cuuint32_t)d->stride, (cuuint32_t)d->stride, 1};
+    if (windowed) {   // window w = padded pixels [w, w+4) x 16 ch = 64 contiguous bf16, next window +32 B
+      dims[0] = 64; dims[1] = (cuuint64_t)Wo;
+      strides[0] = 32;
+    }
     CUresult r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims,
                         strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -544,6 +718,37 @@ extern "C" int ssdsb_conv2d_bf16(const ssdsb_conv_desc* d, const void* x, const 
       return fail(SSDSB_ERR_CUDA, "conv2d: weight tensor map failed (CUresult %d)", (int)r);
   }
 
+  const bool want_staging = d->out_mode == CONV_OUT_NHWC_BF16 && (d->Cout % 64) == 0;
+  if (want_staging) {
+    cuuint64_t dims[4] = {(cuuint64_t)d->Cout, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)d->N};
+    cuuint32_t box[4] = {64, (cuuint32_t)BW, (cuuint32_t)BH, (cuuint32_t)BN};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    {
+      cuuint64_t strides[3] = {(cuuint64_t)d->out_cstride * 2, (cuuint64_t)Wo * d->out_cstride * 2,
+                               (cuuint64_t)Ho * Wo * d->out_cstride * 2};
+      CUresult r = encode(&tmY, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, y, dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS)
+        return fail(SSDSB_ERR_CUDA, "conv2d: output tensor map failed (CUresult %d)", (int)r);
+    }
+    if (residual) {
+      cuuint64_t strides[3] = {(cuuint64_t)d->res_cstride * 2, (cuuint64_t)Wo * d->res_cstride * 2,
+                               (cuuint64_t)Ho * Wo * d->res_cstride * 2};
+      CUresult r = encode(&tmR, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(residual), dims,
+                          strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS)
+        return fail(SSDSB_ERR_CUDA, "conv2d: residual tensor map failed (CUresult %d)", (int)r);
+    } else {
+      tmR = tmY;
+    }
+  } else {
+    tmY = tmA;
+    tmR = tmA;
+  }
+
   static int sms = 0;
   if (!sms) {
     int dev = 0;
@@ -553,14 +758,14 @@ extern "C" int ssdsb_conv2d_bf16(const ssdsb_conv_desc* d, const void* x, const 
   cudaStream_t st = (cudaStream_t)stream;
   if (block_k == 16) {
     switch (block_n) {
-      case 64: return launch<64, 16>(tmA, tmB, kp, sms, st);
-      case 128: return launch<128, 16>(tmA, tmB, kp, sms, st);
-      default: return launch<256, 16>(tmA, tmB, kp, sms, st);
+      case 64: return launch<64, 16>(tmA, tmB, tmY, tmR, kp, want_staging, sms, st);
+      case 128: return launch<128, 16>(tmA, tmB, tmY, tmR, kp, want_staging, sms, st);
+      default: return launch<256, 16>(tmA, tmB, tmY, tmR, kp, want_staging, sms, st);
     }
   }
   switch (block_n) {
-    case 64: return launch<64, 64>(tmA, tmB, kp, sms, st);
-    case 128: return launch<128, 64>(tmA, tmB, kp, sms, st);
-    default: return launch<256, 64>(tmA, tmB, kp, sms, st);
+    case 64: return launch<64, 64>(tmA, tmB, tmY, tmR, kp, want_staging, sms, st);
+    case 128: return launch<128, 64>(tmA, tmB, tmY, tmR, kp, want_staging, sms, st);
+    default: return launch<256, 64>(tmA, tmB, tmY, tmR, kp, want_staging, sms, st);
   }
 }

@@ -10,7 +10,8 @@ struct ConvKernelParams {
   int num_k_blocks;  // taps * kc_per_tap
   int kc_per_tap;    // Cin / BLOCK_K
   int KW, taps;
-  int stride, pad;
+  int stride, pad_w, pad_h;
+  int stages, n_staging, tma_store;
   int BW, BH, BN;    // output-pixel patch of one M tile (product <= 128)
   int tiles_w, tiles_h, tiles_n, n_tiles;
   int Ho, Wo, N;

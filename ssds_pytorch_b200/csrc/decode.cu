@@ -77,17 +77,47 @@ decode_select(const __grid_constant__ DecodeParams p, void* __restrict__ ws) {
   const float thr = p.threshold;
   const int limit = p.cap - DEC_TILE;
   int since_sync = 0;
+  if (tid == 0) {   // adopt whatever bound earlier slices of this map already published
+    unsigned long long g0 = *reinterpret_cast<volatile unsigned long long*>(gthr);
+    if (g0 > s_thr) s_thr = g0;
+  }
+  __syncthreads();
 
-  for (int base = begin; base < end; base += DEC_TILE) {
-    float v[DEC_EPT];
-    const int i0 = base + tid * DEC_EPT;
-    if (vec_ok && i0 + DEC_EPT <= end) {
-      float4 q = __ldcs(reinterpret_cast<const float4*>(src + i0));  // streamed once: evict-first
-      v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
-    } else {
+  // Scan order: the slice is cut into 32 equal runs of 128-byte lines; in every iteration each group
+  // of 8 lanes reads the next line of "its" run.  Loads stay fully coalesced (whole lines), but each
+  // 1024-element tile is a sample spread over the whole slice (all its channels), so the running
+  // K-th score converges after the first tiles instead of being reset by every "record" channel.
+  const int len = end - begin;
+  const int lines = (len + 31) >> 5;                   // 32 floats per 128-byte line
+  const int run = (lines + 31) >> 5;                   // lines per run (32 runs)
+  const int iters = vec_ok ? run : (len + DEC_TILE - 1) / DEC_TILE;
+  auto load_tile = [&](int it, float (&v)[DEC_EPT], int& i0) {
+    if (vec_ok) {
+      const int line = (tid >> 3) * run + it;
+      i0 = begin + line * 32 + (tid & 7) * DEC_EPT;
+      if (it < iters && line < lines && i0 + DEC_EPT <= end) {
+        float4 q = __ldcs(reinterpret_cast<const float4*>(src + i0));  // streamed once: evict-first
+        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+      } else {
+        i0 = end;                                      // nothing for this lane in this iteration
 #pragma unroll
-      for (int e = 0; e < DEC_EPT; ++e) v[e] = (i0 + e < end) ? __ldcs(src + i0 + e) : -1.0f;
+        for (int e = 0; e < DEC_EPT; ++e) v[e] = -1.0f;
+      }
+    } else {
+      i0 = begin + it * DEC_TILE + tid * DEC_EPT;
+#pragma unroll
+      for (int e = 0; e < DEC_EPT; ++e) v[e] = (it < iters && i0 + e < end) ? __ldcs(src + i0 + e) : -1.0f;
     }
+  };
+  float vn[DEC_EPT];
+  int i0n;
+  load_tile(0, vn, i0n);
+  for (int it = 0; it < iters; ++it) {
+    float v[DEC_EPT];
+    const int i0 = i0n;
+#pragma unroll
+    for (int e = 0; e < DEC_EPT; ++e) v[e] = vn[e];
+    load_tile(it + 1, vn, i0n);                        // prefetch: two loads in flight per thread
     unsigned long long k[DEC_EPT];
     bool take[DEC_EPT];
     const unsigned long long cur = s_thr;

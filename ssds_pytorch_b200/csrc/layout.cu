@@ -19,7 +19,7 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 template <int FMT>  // 0: fp32 NCHW, 1: uint8 NHWC
 __global__ void __launch_bounds__(256)
 pack_image_s2d_kernel(const void* __restrict__ src, int N, int H, int W, float mean, float stdv,
-                      uint4* __restrict__ out) {
+                      int row_px, int left_pad, uint4* __restrict__ out) {
   const int Ho = H >> 1, Wo = W >> 1;
   const size_t total = (size_t)N * Ho * Wo;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -46,8 +46,9 @@ pack_image_s2d_kernel(const void* __restrict__ src, int N, int H, int W, float m
     uint4 lo, hi;
     lo.x = pack2(v[0], v[1]); lo.y = pack2(v[2], v[3]); lo.z = pack2(v[4], v[5]); lo.w = pack2(v[6], v[7]);
     hi.x = pack2(v[8], v[9]); hi.y = pack2(v[10], v[11]); hi.z = 0u; hi.w = 0u;
-    out[i * 2 + 0] = lo;
-    out[i * 2 + 1] = hi;
+    const size_t o = ((size_t)n * Ho + ii) * row_px + left_pad + j;   // pixel index in the padded rows
+    out[o * 2 + 0] = lo;
+    out[o * 2 + 1] = hi;
   }
 }
 
@@ -98,7 +99,12 @@ maxpool3x3s2_kernel(const uint4* __restrict__ x, int N, int H, int W, int C8, in
 using namespace ssdsb;
 
 extern "C" int ssdsb_pack_image_s2d(const void* d_src, int src_format, int N, int H, int W,
-                                    float mean, float stdv, void* d_out, void* stream) {
+                                    float mean, float stdv, int out_row_pixels, int left_pad,
+                                    void* d_out, void* stream) {
+  if (out_row_pixels == 0) out_row_pixels = W / 2;
+  SSDSB_REQUIRE(left_pad >= 0 && out_row_pixels >= W / 2 + left_pad,
+                "pack_image_s2d: out_row_pixels=%d too small for W/2=%d + left_pad=%d", out_row_pixels,
+                W / 2, left_pad);
   SSDSB_REQUIRE(d_src && d_out, "pack_image_s2d: NULL argument");
   SSDSB_REQUIRE(N >= 1 && H >= 2 && W >= 2 && (H % 2) == 0 && (W % 2) == 0,
                 "pack_image_s2d: H and W must be even (N=%d H=%d W=%d)", N, H, W);
@@ -110,11 +116,11 @@ extern "C" int ssdsb_pack_image_s2d(const void* d_src, int src_format, int N, in
   if (blocks > 148 * 16) blocks = 148 * 16;
   cudaStream_t st = (cudaStream_t)stream;
   if (src_format == 0)
-    pack_image_s2d_kernel<0><<<blocks, 256, 0, st>>>(d_src, N, H, W, mean, stdv,
-                                                     reinterpret_cast<uint4*>(d_out));
+    pack_image_s2d_kernel<0><<<blocks, 256, 0, st>>>(d_src, N, H, W, mean, stdv, out_row_pixels,
+                                                     left_pad, reinterpret_cast<uint4*>(d_out));
   else
-    pack_image_s2d_kernel<1><<<blocks, 256, 0, st>>>(d_src, N, H, W, mean, stdv,
-                                                     reinterpret_cast<uint4*>(d_out));
+    pack_image_s2d_kernel<1><<<blocks, 256, 0, st>>>(d_src, N, H, W, mean, stdv, out_row_pixels,
+                                                     left_pad, reinterpret_cast<uint4*>(d_out));
   SSDSB_LAUNCH_CHECK("pack_image_s2d_kernel");
   return SSDSB_OK;
 }

@@ -130,22 +130,25 @@ class SSDResNet(torch.nn.Module):
             return torch.empty((n, h, w, c), dtype=bf, device=dev)
 
         src = torch.empty_like(images, device=dev)
-        packed = buf(N, H // 2, W // 2, 16)
+        # s2d image with 2 zero pixels of left padding per row (zeroed once; the pack kernel never
+        # touches the padding) so the stem can fetch 4 taps x 16 ch as one 128-byte window
+        packed = torch.zeros((N, H // 2, W // 2 + K.STEM_ROW_EXTRA, 16), dtype=bf, device=dev)
         mean, std = self.mean, self.std
         steps.append(lambda: K.pack_image_s2d(src, mean, std, out=packed))
 
-        def add_conv(cv, x, residual=None, relu=None, Ho=0, Wo=0):
+        def add_conv(cv, x, residual=None, relu=None, Ho=0, Wo=0, x_kind=0, x_width=None):
             n, h, w, _ = x.shape
             ho = Ho or (h + 2 * cv.pad - cv.KH) // cv.stride + 1
             wo = Wo or (w + 2 * cv.pad - cv.KW) // cv.stride + 1
             y = buf(n, ho, wo, cv.cout)
             r = cv.relu if relu is None else relu
             steps.append(lambda: K.conv2d(x, cv.w, cv.bias, cv.KH, cv.KW, cv.stride, cv.pad, r,
-                                          residual, out=y, Ho=ho, Wo=wo))
+                                          residual, out=y, Ho=ho, Wo=wo, x_kind=x_kind,
+                                          x_width=x_width))
             flops[0] += cv.flops_per_pixel * n * ho * wo
             return y
 
-        x = add_conv(self.stem, packed, Ho=H // 2, Wo=W // 2)
+        x = add_conv(self.stem, packed, Ho=H // 2, Wo=W // 2, x_kind=1, x_width=W // 2)
         pooled = buf(N, (x.shape[1] - 1) // 2 + 1, (x.shape[2] - 1) // 2 + 1, x.shape[3])
         xs = x
         steps.append(lambda: K.maxpool3x3s2(xs, out=pooled))

@@ -100,7 +100,13 @@ def test_stem_s2d_equals_7x7s2(K):
             packed = K.pack_image_s2d(img_u8.cuda(), 0.0, 255.0)
         y = K.conv2d(packed, K.pack_stem_weight_s2d(w).cuda(), b.cuda(), 4, 4, 1, 2, True,
                      Ho=H // 2, Wo=W // 2)
+        # windowed variant: left-padded rows, 4 taps x 16 ch fetched as one 128-byte K-block
+        src_p = src if fmt == "f32" else img_u8.cuda()
+        packed_p = K.pack_image_s2d(src_p, 0.0, 1.0 if fmt == "f32" else 255.0, padded=True)
+        y2 = K.conv2d(packed_p, K.pack_stem_weight_s2d(w).cuda(), b.cuda(), 4, 4, 1, 2, True,
+                      Ho=H // 2, Wo=W // 2, x_kind=1, x_width=W // 2)
         torch.cuda.synchronize()
+        assert torch.equal(y, y2), "windowed stem differs from the per-tap stem"
         xr = (img_u8.float() / 255.0).to(torch.bfloat16).float().permute(0, 3, 1, 2).cuda()
         ref = F.conv2d(xr, w.to(torch.bfloat16).float().cuda(), b.cuda(), stride=2, padding=3).relu()
         ref = ref.permute(0, 2, 3, 1)
