@@ -140,4 +140,91 @@ __device__ __forceinline__ int topk_append(unsigned long long* buf, int* s_cnt,
   return 0;
 }
 
+// Cheaper prune for the streaming phase: block-wide MSB-first radix SELECT of the K-th largest key
+// (8-bit digits, early exit once the candidate set is a single key) followed by an unordered
+// compaction of the K survivors to buf[0..K).  ~5x fewer instructions than sorting the buffer; the
+// final, ordered result is produced once by topk_prune.  `scratch` needs 260 ints of shared memory.
+// Every thread must call; n = *s_cnt must be stable (a barrier has passed); ends with a barrier.
+template <int NT, int MAXPT>
+__device__ __forceinline__ void topk_prune_select(unsigned long long* buf, int* s_cnt,
+                                                  unsigned long long* s_thr, int K, int* scratch,
+                                                  unsigned long long* s_kth) {
+  const int n = *s_cnt;
+  if (n <= K) return;  // block-uniform
+  const int tid = threadIdx.x;
+  unsigned long long mine[MAXPT];
+#pragma unroll
+  for (int j = 0; j < MAXPT; ++j) {
+    const int i = tid + j * NT;
+    mine[j] = (i < n) ? buf[i] : 0ull;
+  }
+  unsigned long long prefix = 0ull, mask = 0ull;
+  int kk = K;
+  bool found = false;
+  for (int byte = 7; byte >= 0; --byte) {
+    for (int k = tid; k < 256; k += NT) scratch[k] = 0;
+    __syncthreads();
+    const int shift = byte * 8;
+#pragma unroll
+    for (int j = 0; j < MAXPT; ++j) {
+      const int i = tid + j * NT;
+      if (i < n && (mine[j] & mask) == prefix) atomicAdd(&scratch[(int)((mine[j] >> shift) & 255ull)], 1);
+    }
+    __syncthreads();
+    if (tid < 32) {  // lane l owns bins 255-8l .. 248-8l (descending)
+      int c[8], sum = 0;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        c[e] = scratch[255 - (tid * 8 + e)];
+        sum += c[e];
+      }
+      int incl = sum;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        int v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (tid >= d) incl += v;
+      }
+      const int excl = incl - sum;
+      if (excl < kk && kk <= incl) {
+        int run = excl;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          if (run < kk && kk <= run + c[e]) {
+            scratch[256] = 255 - (tid * 8 + e);
+            scratch[257] = kk - run;
+            scratch[258] = c[e];
+          }
+          run += c[e];
+        }
+      }
+    }
+    __syncthreads();
+    prefix |= (unsigned long long)scratch[256] << shift;
+    mask |= 255ull << shift;
+    kk = scratch[257];
+    if (scratch[258] == 1) {  // a single key carries this prefix: it is the K-th largest
+      found = true;
+      break;
+    }
+  }
+  if (found) {
+#pragma unroll
+    for (int j = 0; j < MAXPT; ++j) {
+      const int i = tid + j * NT;
+      if (i < n && (mine[j] & mask) == prefix) *s_kth = mine[j];
+    }
+  } else if (tid == 0) {
+    *s_kth = prefix;  // all 8 digits fixed
+  }
+  if (tid == 0) *s_cnt = 0;
+  __syncthreads();
+  const unsigned long long kth = *s_kth;
+  bool take[MAXPT];
+#pragma unroll
+  for (int j = 0; j < MAXPT; ++j) take[j] = (tid + j * NT < n) && (mine[j] >= kth);
+  topk_append<MAXPT>(buf, s_cnt, mine, take);
+  if (tid == 0 && kth > *s_thr) *s_thr = kth;
+  __syncthreads();
+}
+
 }  // namespace ssdsb

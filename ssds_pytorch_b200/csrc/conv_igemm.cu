@@ -26,7 +26,9 @@
 //     with ONE 4-D TMA store (full 128-byte lines, ragged edges clipped by TMA); the residual
 //     sub-tile is TMA-loaded into the same staging buffer two chunks ahead and added in place.
 //
-// Warp roles (256 threads): w0 TMA producer, w1 MMA issuer, w2 TMEM allocator, w4-7 epilogue.
+// Warp roles (384 threads): w0 TMA producer, w1 MMA issuer, w2 TMEM allocator, w4-11 epilogue
+// (two warps per TMEM lane quarter, each owning one 32-column half of every 64-column chunk: a lone
+// warp per scheduler cannot hide its own instruction latency, which made the epilogue the bottleneck).
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -38,7 +40,8 @@ namespace {
 
 constexpr int BLOCK_M = 128;
 constexpr int UMMA_K = 16;
-constexpr int CONV_NT = 256;
+constexpr int CONV_NT = 384;          // 4 control warps + 8 epilogue warps
+constexpr int EPI_THREADS = 256;
 
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -117,8 +120,8 @@ __device__ __forceinline__ void tma_store_wait_read() {
 __device__ __forceinline__ void tma_store_wait_all() {
   asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
-__device__ __forceinline__ void epi_bar_sync() {   // the 128 epilogue threads only
-  asm volatile("bar.sync 1, 128;" ::: "memory");
+__device__ __forceinline__ void epi_bar_sync() {   // the 256 epilogue threads only
+  asm volatile("bar.sync 1, 256;" ::: "memory");
 }
 __device__ __forceinline__ void tcgen05_fence_before() {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -259,7 +262,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 4);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty[a], 8);  // one arrive per epilogue warp
     }
     for (int r = 0; r < MAX_STAGING; ++r) mbar_init(&res_full[r], 1);
     fence_barrier_init();
@@ -345,7 +348,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else if (warp >= 4) {
     // =============================== epilogue ===============================
-    const int q = warp - 4;                   // TMEM lane quarter this warp may read
+    const int q = warp & 3;                   // TMEM lane quarter this warp may read (warp id % 4)
+    const int half = (warp - 4) >> 2;         // which 32-column half of each 64-column chunk
     const int r = q * 32 + lane;              // row of the tile == TMEM lane
     const bool elected = (threadIdx.x == 128);
     int acc = 0;
@@ -356,13 +360,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     int issued = 0;                           // residual loads issued (elected thread only)
     int it_tile = blockIdx.x, it_chunk = 0;   // iterator of the residual prefetcher
     const bool has_res = (p.residual != nullptr);
+    // row r -> (bn, bh, bw) in TMA box order (w fastest); constant across tiles
+    const int bw = r % p.BW;
+    const int bh = (r / p.BW) % p.BH;
+    const int bn = r / (p.BW * p.BH);
 
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const TileCoord t = tile_coord(p, tile);
-      // row r -> (bn, bh, bw) in TMA box order (w fastest)
-      const int bw = r % p.BW;
-      const int bh = (r / p.BW) % p.BH;
-      const int bn = r / (p.BW * p.BH);
       const int w = t.w0 + bw, h = t.h0 + bh, n = t.n0 + bn;
       const bool row_ok = (r < rows) && (w < p.Wo) && (h < p.Ho) && (n < p.N);
 
@@ -383,8 +387,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               // keep residual loads two chunks ahead; a slot is reusable once the store that last
               // read it (chunk issued - R) has finished reading shared memory
               while (issued <= g + 2 && it_tile < num_tiles) {
-                // stores committed so far: g; need store (issued - R) read-complete
-                const int pending_ok = g - 1 - (issued - R);   // groups that may stay in flight
+                const int pending_ok = g - 1 - (issued - R);   // store groups that may stay in flight
                 if (issued >= R) {
                   if (pending_ok <= 0) tma_store_wait_read<0>();
                   else if (pending_ok == 1) tma_store_wait_read<1>();
@@ -413,27 +416,34 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           } else {
             epi_bar_sync();                    // slot free for everybody
           }
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
+          {
             uint32_t v[32];
             tmem_ld32(t_row + (uint32_t)(c * 64 + half * 32), v);
+            const float4* bp = reinterpret_cast<const float4*>(p.bias + col0 + half * 32);
+            float4 bv[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) bv[e] = __ldg(bp + e);
             tmem_ld_wait();
-            const float* bp = p.bias + col0 + half * 32;
 #pragma unroll
             for (int gq = 0; gq < 4; ++gq) {
               const int chunk16 = half * 4 + gq;                     // 16-byte piece of the 128B row
               uint4* sp = reinterpret_cast<uint4*>(sbuf + r * 128 + ((chunk16 ^ (r & 7)) << 4));
               float f[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[gq * 8 + e]) + __ldg(bp + gq * 8 + e);
+              f[0] = __uint_as_float(v[gq * 8 + 0]) + bv[gq * 2].x;
+              f[1] = __uint_as_float(v[gq * 8 + 1]) + bv[gq * 2].y;
+              f[2] = __uint_as_float(v[gq * 8 + 2]) + bv[gq * 2].z;
+              f[3] = __uint_as_float(v[gq * 8 + 3]) + bv[gq * 2].w;
+              f[4] = __uint_as_float(v[gq * 8 + 4]) + bv[gq * 2 + 1].x;
+              f[5] = __uint_as_float(v[gq * 8 + 5]) + bv[gq * 2 + 1].y;
+              f[6] = __uint_as_float(v[gq * 8 + 6]) + bv[gq * 2 + 1].z;
+              f[7] = __uint_as_float(v[gq * 8 + 7]) + bv[gq * 2 + 1].w;
               if (has_res) {
                 const uint4 rv = *sp;
                 const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&rw[e]);
-                  f[e * 2 + 0] += __bfloat162float(h2.x);
-                  f[e * 2 + 1] += __bfloat162float(h2.y);
+                for (int e = 0; e < 4; ++e) {      // bf16 -> fp32 is a 16-bit shift
+                  f[e * 2 + 0] += __uint_as_float(rw[e] << 16);
+                  f[e * 2 + 1] += __uint_as_float(rw[e] & 0xffff0000u);
                 }
               }
               if (p.relu) {
@@ -457,7 +467,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
       } else {
 #pragma unroll 1
-        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        for (int c0 = half * 32; c0 < BLOCK_N; c0 += 64) {
           const int col0 = t.n_tile * BLOCK_N + c0;
           if (col0 >= p.Cout) break;            // warp-uniform
           uint32_t v[32];
@@ -479,9 +489,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                   const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
                   for (int e = 0; e < 4; ++e) {
-                    const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&rw[e]);
-                    f[gq * 8 + e * 2 + 0] += __bfloat162float(h2.x);
-                    f[gq * 8 + e * 2 + 1] += __bfloat162float(h2.y);
+                    f[gq * 8 + e * 2 + 0] += __uint_as_float(rw[e] << 16);
+                    f[gq * 8 + e * 2 + 1] += __uint_as_float(rw[e] & 0xffff0000u);
                   }
                 }
               }
@@ -501,22 +510,46 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 yp[gq] = o;
               }
             }
-          } else {
-            // multibox head: channels [0, n_loc) -> loc fp32 NCHW; [n_loc, Cout) -> sigmoid -> conf
+          } else if (row_ok) {
+            // multibox head: channels [0, n_loc) -> loc fp32 NCHW; [n_loc, Cout) -> sigmoid -> conf.
+            // Consecutive lanes are consecutive pixels, so every column store is a coalesced line.
             const size_t hw = (size_t)p.Ho * p.Wo;
             const size_t sp = (size_t)h * p.Wo + w;
-            float* loc = reinterpret_cast<float*>(p.y) + (size_t)n * p.n_loc * hw + sp;
-            float* conf = reinterpret_cast<float*>(p.y2) + (size_t)n * (p.Cout - p.n_loc) * hw + sp;
+            const int nvalid = min(32, p.Cout - col0);
+            if (col0 >= p.n_loc && nvalid == 32) {          // whole chunk is conf (the common case)
+              float* dst = reinterpret_cast<float*>(p.y2) + ((size_t)n * (p.Cout - p.n_loc) +
+                                                              (size_t)(col0 - p.n_loc)) * hw + sp;
+              const float4* bp = reinterpret_cast<const float4*>(p.bias + col0);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int col = col0 + j;
-              if (col < p.Cout && row_ok) {
-                const float x = __uint_as_float(v[j]) + __ldg(p.bias + col);
-                if (col < p.n_loc) {
-                  loc[(size_t)col * hw] = x;
-                } else {
-                  const float sg = p.sigmoid ? 1.0f / (1.0f + __expf(-x)) : x;
-                  __stcs(conf + (size_t)(col - p.n_loc) * hw, sg);
+              for (int e = 0; e < 8; ++e) {
+                const float4 b4 = __ldg(bp + e);
+                float x0 = __uint_as_float(v[e * 4 + 0]) + b4.x, x1 = __uint_as_float(v[e * 4 + 1]) + b4.y;
+                float x2 = __uint_as_float(v[e * 4 + 2]) + b4.z, x3 = __uint_as_float(v[e * 4 + 3]) + b4.w;
+                if (p.sigmoid) {
+                  x0 = __fdividef(1.0f, 1.0f + __expf(-x0));
+                  x1 = __fdividef(1.0f, 1.0f + __expf(-x1));
+                  x2 = __fdividef(1.0f, 1.0f + __expf(-x2));
+                  x3 = __fdividef(1.0f, 1.0f + __expf(-x3));
+                }
+                __stcs(dst, x0); dst += hw;
+                __stcs(dst, x1); dst += hw;
+                __stcs(dst, x2); dst += hw;
+                __stcs(dst, x3); dst += hw;
+              }
+            } else {
+              float* loc = reinterpret_cast<float*>(p.y) + (size_t)n * p.n_loc * hw + sp;
+              float* conf = reinterpret_cast<float*>(p.y2) + (size_t)n * (p.Cout - p.n_loc) * hw + sp;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const int col = col0 + j;
+                if (j < nvalid) {
+                  const float x = __uint_as_float(v[j]) + __ldg(p.bias + col);
+                  if (col < p.n_loc) {
+                    loc[(size_t)col * hw] = x;
+                  } else {
+                    const float sg = p.sigmoid ? __fdividef(1.0f, 1.0f + __expf(-x)) : x;
+                    __stcs(conf + (size_t)(col - p.n_loc) * hw, sg);
+                  }
                 }
               }
             }

@@ -26,6 +26,7 @@ constexpr int DEC_EPT = 4;                 // one float4 per thread per tile
 constexpr int DEC_TILE = DEC_NT * DEC_EPT; // 1024 scores
 constexpr int DEC_SLICE = 64 * 1024;       // scores per CTA
 constexpr int DEC_MAX_K = 1024;
+constexpr int DEC_MAXPT = 16;               // keys per thread in a prune: cap (<= 4096) / DEC_NT
 
 struct DecodeParams {
   ssdsb_level lv[SSDSB_MAX_LEVELS];
@@ -48,11 +49,12 @@ __device__ __forceinline__ unsigned long long* ws_cand(void* ws, int B, int L) {
   return reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(ws) + head);
 }
 
-__global__ void __launch_bounds__(DEC_NT)
+__global__ void __launch_bounds__(DEC_NT, 4)
 decode_select(const __grid_constant__ DecodeParams p, void* __restrict__ ws) {
   extern __shared__ __align__(16) unsigned long long buf[];  // [p.cap]
   __shared__ int s_cnt;
-  __shared__ unsigned long long s_thr;
+  __shared__ unsigned long long s_thr, s_kth;
+  __shared__ int s_scratch[260];
 
   const int b = blockIdx.y;
   int l = 0;
@@ -101,12 +103,12 @@ decode_select(const __grid_constant__ DecodeParams p, void* __restrict__ ws) {
       } else {
         i0 = end;                                      // nothing for this lane in this iteration
 #pragma unroll
-        for (int e = 0; e < DEC_EPT; ++e) v[e] = -1.0f;
+        for (int e = 0; e < DEC_EPT; ++e) v[e] = -INFINITY;
       }
     } else {
       i0 = begin + it * DEC_TILE + tid * DEC_EPT;
 #pragma unroll
-      for (int e = 0; e < DEC_EPT; ++e) v[e] = (it < iters && i0 + e < end) ? __ldcs(src + i0 + e) : -1.0f;
+      for (int e = 0; e < DEC_EPT; ++e) v[e] = (it < iters && i0 + e < end) ? __ldcs(src + i0 + e) : -INFINITY;
     }
   };
   float vn[DEC_EPT];
@@ -118,17 +120,25 @@ decode_select(const __grid_constant__ DecodeParams p, void* __restrict__ ws) {
 #pragma unroll
     for (int e = 0; e < DEC_EPT; ++e) v[e] = vn[e];
     load_tile(it + 1, vn, i0n);                        // prefetch: two loads in flight per thread
-    unsigned long long k[DEC_EPT];
-    bool take[DEC_EPT];
+    // fast reject in the float domain; the exact 64-bit key test only runs in warps that have a
+    // candidate (rare once the running K-th score has converged)
     const unsigned long long cur = s_thr;
+    const float curF = (cur == 0ull) ? -INFINITY : key_score(cur);
+    const float lim = fmaxf(thr, curF);
+    const bool pre = (v[0] >= lim) | (v[1] >= lim) | (v[2] >= lim) | (v[3] >= lim);
+    int fill = 0;
+    if (__any_sync(0xffffffffu, pre)) {
+      unsigned long long k[DEC_EPT];
+      bool take[DEC_EPT];
 #pragma unroll
-    for (int e = 0; e < DEC_EPT; ++e) {
-      k[e] = make_key(v[e], (uint32_t)(i0 + e));
-      take[e] = (i0 + e < end) && (v[e] >= thr) && (k[e] > cur);
+      for (int e = 0; e < DEC_EPT; ++e) {
+        k[e] = make_key(v[e], (uint32_t)(i0 + e));
+        take[e] = (i0 + e < end) && (v[e] >= thr) && (k[e] > cur);
+      }
+      fill = topk_append<DEC_EPT>(buf, &s_cnt, k, take);
     }
-    const int fill = topk_append<DEC_EPT>(buf, &s_cnt, k, take);
     if (__syncthreads_or(fill > limit)) {
-      topk_prune<DEC_NT>(buf, &s_cnt, &s_thr, p.K);
+      topk_prune_select<DEC_NT, DEC_MAXPT>(buf, &s_cnt, &s_thr, p.K, s_scratch, &s_kth);
       if (tid == 0 && s_cnt >= p.K) {  // publish our K-th key, adopt the best one seen anywhere
         unsigned long long old = atomicMax(gthr, s_thr);
         if (old > s_thr) s_thr = old;

@@ -75,7 +75,8 @@ nms_kernel(const float* __restrict__ scores, const float* __restrict__ boxes,
   __shared__ uint32_t alive_w[NMS_CW];
   __shared__ int keptpos[NMS_CH];
   __shared__ int s_cnt, s_nk;
-  __shared__ unsigned long long s_thr;
+  __shared__ unsigned long long s_thr, s_kth;
+  __shared__ int s_scratch[260];
 
   const int b = blockIdx.x;
   const int tid = threadIdx.x;
@@ -108,7 +109,7 @@ nms_kernel(const float* __restrict__ scores, const float* __restrict__ boxes,
       }
       const int fill = topk_append<NMS_EPT>(keys, &s_cnt, k, take);
       if (__syncthreads_or(fill > NMS_CAP - NMS_TILE)) {  // block-uniform, race-free
-        topk_prune<NMS_NT>(keys, &s_cnt, &s_thr, NMS_SEL);
+        topk_prune_select<NMS_NT, NMS_CAP / NMS_NT>(keys, &s_cnt, &s_thr, NMS_SEL, s_scratch, &s_kth);
         pruned = true;
       }
     }
