@@ -142,22 +142,17 @@ __device__ __forceinline__ int topk_append(unsigned long long* buf, int* s_cnt,
 
 // Cheaper prune for the streaming phase: block-wide MSB-first radix SELECT of the K-th largest key
 // (8-bit digits, early exit once the candidate set is a single key) followed by an unordered
-// compaction of the K survivors to buf[0..K).  ~5x fewer instructions than sorting the buffer; the
-// final, ordered result is produced once by topk_prune.  `scratch` needs 260 ints of shared memory.
+// compaction of the K survivors through `buf2` (K slots) back to buf[0..K).  ~5x fewer instructions
+// than sorting the buffer and no per-thread key arrays (registers stay free for the streaming loop);
+// the final, ordered result is produced once by topk_prune.  `scratch` needs 260 ints of smem.
 // Every thread must call; n = *s_cnt must be stable (a barrier has passed); ends with a barrier.
-template <int NT, int MAXPT>
-__device__ __forceinline__ void topk_prune_select(unsigned long long* buf, int* s_cnt,
-                                                  unsigned long long* s_thr, int K, int* scratch,
-                                                  unsigned long long* s_kth) {
+template <int NT>
+__device__ __noinline__ void topk_prune_select(unsigned long long* buf, unsigned long long* buf2,
+                                               int* s_cnt, unsigned long long* s_thr, int K,
+                                               int* scratch, unsigned long long* s_kth) {
   const int n = *s_cnt;
   if (n <= K) return;  // block-uniform
   const int tid = threadIdx.x;
-  unsigned long long mine[MAXPT];
-#pragma unroll
-  for (int j = 0; j < MAXPT; ++j) {
-    const int i = tid + j * NT;
-    mine[j] = (i < n) ? buf[i] : 0ull;
-  }
   unsigned long long prefix = 0ull, mask = 0ull;
   int kk = K;
   bool found = false;
@@ -165,10 +160,9 @@ __device__ __forceinline__ void topk_prune_select(unsigned long long* buf, int* 
     for (int k = tid; k < 256; k += NT) scratch[k] = 0;
     __syncthreads();
     const int shift = byte * 8;
-#pragma unroll
-    for (int j = 0; j < MAXPT; ++j) {
-      const int i = tid + j * NT;
-      if (i < n && (mine[j] & mask) == prefix) atomicAdd(&scratch[(int)((mine[j] >> shift) & 255ull)], 1);
+    for (int i = tid; i < n; i += NT) {
+      const unsigned long long key = buf[i];
+      if ((key & mask) == prefix) atomicAdd(&scratch[(int)((key >> shift) & 255ull)], 1);
     }
     __syncthreads();
     if (tid < 32) {  // lane l owns bins 255-8l .. 248-8l (descending)
@@ -208,22 +202,26 @@ __device__ __forceinline__ void topk_prune_select(unsigned long long* buf, int* 
     }
   }
   if (found) {
-#pragma unroll
-    for (int j = 0; j < MAXPT; ++j) {
-      const int i = tid + j * NT;
-      if (i < n && (mine[j] & mask) == prefix) *s_kth = mine[j];
+    for (int i = tid; i < n; i += NT) {
+      const unsigned long long key = buf[i];
+      if ((key & mask) == prefix) *s_kth = key;
     }
   } else if (tid == 0) {
     *s_kth = prefix;  // all 8 digits fixed
   }
-  if (tid == 0) *s_cnt = 0;
+  if (tid == 0) scratch[259] = 0;
   __syncthreads();
   const unsigned long long kth = *s_kth;
-  bool take[MAXPT];
-#pragma unroll
-  for (int j = 0; j < MAXPT; ++j) take[j] = (tid + j * NT < n) && (mine[j] >= kth);
-  topk_append<MAXPT>(buf, s_cnt, mine, take);
-  if (tid == 0 && kth > *s_thr) *s_thr = kth;
+  for (int i = tid; i < n; i += NT) {
+    const unsigned long long key = buf[i];
+    if (key >= kth) buf2[atomicAdd(&scratch[259], 1)] = key;   // exactly K survivors
+  }
+  __syncthreads();
+  for (int i = tid; i < K; i += NT) buf[i] = buf2[i];
+  if (tid == 0) {
+    *s_cnt = K;
+    if (kth > *s_thr) *s_thr = kth;
+  }
   __syncthreads();
 }
 

@@ -243,8 +243,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t* empty_bar = bars + MAX_STAGES;             // [MAX_STAGES]
   uint64_t* tmem_full = bars + 2 * MAX_STAGES;         // [2]
   uint64_t* tmem_empty = bars + 2 * MAX_STAGES + 2;    // [2]
-  uint64_t* res_full = bars + 2 * MAX_STAGES + 4;      // [MAX_STAGING]
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4 + MAX_STAGING);
+  uint64_t* slot_ready = bars + 2 * MAX_STAGES + 4;                  // [MAX_STAGING] slot free (+ residual landed)
+  uint64_t* slot_full = bars + 2 * MAX_STAGES + 4 + MAX_STAGING;     // [MAX_STAGING] 8 epilogue warps wrote it
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4 + 2 * MAX_STAGING);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -264,7 +265,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_init(&tmem_full[a], 1);
       mbar_init(&tmem_empty[a], 8);  // one arrive per epilogue warp
     }
-    for (int r = 0; r < MAX_STAGING; ++r) mbar_init(&res_full[r], 1);
+    for (int r = 0; r < MAX_STAGING; ++r) {
+      mbar_init(&slot_ready[r], 1);
+      mbar_init(&slot_full[r], 8);   // one arrive per epilogue warp
+    }
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -346,19 +350,64 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
       }
     }
+  } else if (warp == 3) {
+    // ================= store / residual engine (staged NHWC epilogue only) =================
+    // One thread owns every TMA operation of the epilogue so that the 8 epilogue warps never block
+    // on the copy engine and never barrier with each other: per 64-column chunk g (slot g % R)
+    //   slot_ready[slot]  <- this thread: slot reusable (+ residual sub-tile landed via TMA)
+    //   slot_full[slot]   <- the 8 epilogue warps: sub-tile written (after fence.proxy.async)
+    // and this thread then issues the 4-D TMA store.  Residuals are armed R-1 chunks ahead.
+    if (lane == 0 && p.tma_store) {
+      const int R = p.n_staging;
+      const bool has_res = (p.residual != nullptr);
+      int a_tile = blockIdx.x, a_chunk = 0, armed = 0;       // arming iterator
+      auto arm_next = [&]() {
+        if (a_tile >= num_tiles) return;
+        const TileCoord ta = tile_coord(p, a_tile);
+        const int slot = armed % R;
+        if (has_res) {
+          mbar_expect_tx(&slot_ready[slot], (uint32_t)rows * 128u);
+          tma_load_4d(staging + slot * STAGING_BYTES, &tmR, &slot_ready[slot],
+                      ta.n_tile * BLOCK_N + a_chunk * 64, ta.w0, ta.h0, ta.n0);
+        } else {
+          mbar_arrive(&slot_ready[slot]);
+        }
+        ++armed;
+        const int nch = min(BLOCK_N, p.Cout - ta.n_tile * BLOCK_N) >> 6;
+        if (++a_chunk == nch) {
+          a_chunk = 0;
+          a_tile += gridDim.x;
+        }
+      };
+      for (int i = 0; i < R; ++i) arm_next();
+      int g = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const TileCoord t = tile_coord(p, tile);
+        const int nch = min(BLOCK_N, p.Cout - t.n_tile * BLOCK_N) >> 6;
+        for (int c = 0; c < nch; ++c, ++g) {
+          const int slot = g % R;
+          mbar_wait(&slot_full[slot], (uint32_t)(g / R) & 1u);
+          tma_store_4d(&tmY, staging + slot * STAGING_BYTES, t.n_tile * BLOCK_N + c * 64, t.w0, t.h0,
+                       t.n0);
+          tma_store_commit();
+          if (g >= 1) {                 // store g-1 has been read out of smem -> its slot is free
+            tma_store_wait_read<1>();
+            arm_next();                 // = chunk g-1+R
+          }
+        }
+      }
+      tma_store_wait_all();             // smem must outlive the last store
+    }
   } else if (warp >= 4) {
     // =============================== epilogue ===============================
     const int q = warp & 3;                   // TMEM lane quarter this warp may read (warp id % 4)
     const int half = (warp - 4) >> 2;         // which 32-column half of each 64-column chunk
     const int r = q * 32 + lane;              // row of the tile == TMEM lane
-    const bool elected = (threadIdx.x == 128);
     int acc = 0;
     uint32_t acc_phase = 0;
     // staging ring state (TMA-store path)
     const int R = p.n_staging;
     int g = 0;                                // chunks processed so far (all epilogue threads)
-    int issued = 0;                           // residual loads issued (elected thread only)
-    int it_tile = blockIdx.x, it_chunk = 0;   // iterator of the residual prefetcher
     const bool has_res = (p.residual != nullptr);
     // row r -> (bn, bh, bw) in TMA box order (w fastest); constant across tiles
     const int bw = r % p.BW;
@@ -382,40 +431,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const int slot = g % R;
           unsigned char* sbuf = staging + slot * STAGING_BYTES;
           const int col0 = t.n_tile * BLOCK_N + c * 64;
-          if (elected) {
-            if (has_res) {
-              // keep residual loads two chunks ahead; a slot is reusable once the store that last
-              // read it (chunk issued - R) has finished reading shared memory
-              while (issued <= g + 2 && it_tile < num_tiles) {
-                const int pending_ok = g - 1 - (issued - R);   // store groups that may stay in flight
-                if (issued >= R) {
-                  if (pending_ok <= 0) tma_store_wait_read<0>();
-                  else if (pending_ok == 1) tma_store_wait_read<1>();
-                  else if (pending_ok == 2) tma_store_wait_read<2>();
-                  else tma_store_wait_read<3>();
-                }
-                const TileCoord ti = tile_coord(p, it_tile);
-                const int islot = issued % R;
-                mbar_expect_tx(&res_full[islot], (uint32_t)rows * 128u);
-                tma_load_4d(staging + islot * STAGING_BYTES, &tmR, &res_full[islot],
-                            ti.n_tile * BLOCK_N + it_chunk * 64, ti.w0, ti.h0, ti.n0);
-                ++issued;
-                const int inc = min(BLOCK_N, p.Cout - ti.n_tile * BLOCK_N) >> 6;
-                if (++it_chunk == inc) {
-                  it_chunk = 0;
-                  it_tile += gridDim.x;
-                }
-              }
-            } else {
-              if (R >= 4) tma_store_wait_read<3>();
-              else tma_store_wait_read<1>();
-            }
-          }
-          if (has_res) {
-            mbar_wait(&res_full[slot], (uint32_t)(g / R) & 1u);
-          } else {
-            epi_bar_sync();                    // slot free for everybody
-          }
+          mbar_wait(&slot_ready[slot], (uint32_t)(g / R) & 1u);   // slot free (+ residual landed)
           {
             uint32_t v[32];
             tmem_ld32(t_row + (uint32_t)(c * 64 + half * 32), v);
@@ -459,11 +475,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
           }
           fence_proxy_async();                 // generic-proxy smem writes -> visible to TMA
-          epi_bar_sync();
-          if (elected) {
-            tma_store_4d(&tmY, sbuf, col0, t.w0, t.h0, t.n0);
-            tma_store_commit();
-          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&slot_full[slot]);
         }
       } else {
 #pragma unroll 1
@@ -564,7 +577,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         acc_phase ^= 1;
       }
     }
-    if (elected && p.tma_store) tma_store_wait_all();   // smem must outlive the last store
   }
 
   tcgen05_fence_before();

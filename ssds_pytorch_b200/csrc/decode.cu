@@ -26,7 +26,6 @@ constexpr int DEC_EPT = 4;                 // one float4 per thread per tile
 constexpr int DEC_TILE = DEC_NT * DEC_EPT; // 1024 scores
 constexpr int DEC_SLICE = 64 * 1024;       // scores per CTA
 constexpr int DEC_MAX_K = 1024;
-constexpr int DEC_MAXPT = 16;               // keys per thread in a prune: cap (<= 4096) / DEC_NT
 
 struct DecodeParams {
   ssdsb_level lv[SSDSB_MAX_LEVELS];
@@ -49,9 +48,9 @@ __device__ __forceinline__ unsigned long long* ws_cand(void* ws, int B, int L) {
   return reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(ws) + head);
 }
 
-__global__ void __launch_bounds__(DEC_NT, 4)
+__global__ void __launch_bounds__(DEC_NT)
 decode_select(const __grid_constant__ DecodeParams p, void* __restrict__ ws) {
-  extern __shared__ __align__(16) unsigned long long buf[];  // [p.cap]
+  extern __shared__ __align__(16) unsigned long long buf[];  // [p.cap + p.K] (buffer + compaction scratch)
   __shared__ int s_cnt;
   __shared__ unsigned long long s_thr, s_kth;
   __shared__ int s_scratch[260];
@@ -138,7 +137,7 @@ decode_select(const __grid_constant__ DecodeParams p, void* __restrict__ ws) {
       fill = topk_append<DEC_EPT>(buf, &s_cnt, k, take);
     }
     if (__syncthreads_or(fill > limit)) {
-      topk_prune_select<DEC_NT, DEC_MAXPT>(buf, &s_cnt, &s_thr, p.K, s_scratch, &s_kth);
+      topk_prune_select<DEC_NT>(buf, buf + p.cap, &s_cnt, &s_thr, p.K, s_scratch, &s_kth);
       if (tid == 0 && s_cnt >= p.K) {  // publish our K-th key, adopt the best one seen anywhere
         unsigned long long old = atomicMax(gthr, s_thr);
         if (old > s_thr) s_thr = old;
@@ -356,7 +355,7 @@ extern "C" int ssdsb_decode(const ssdsb_level* levels, int n_levels, int B, floa
   cudaStream_t st = (cudaStream_t)stream;
   const size_t head = (size_t)B * n_levels * 8 + (((size_t)B * n_levels * 4 + 7) / 8) * 8;
   SSDSB_CUDA(cudaMemsetAsync(d_workspace, 0, head, st));
-  const size_t smem = (size_t)p.cap * sizeof(unsigned long long);
+  const size_t smem = (size_t)(p.cap + p.K) * sizeof(unsigned long long);
   SSDSB_CUDA(cudaFuncSetAttribute(decode_select, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
   SSDSB_CUDA(cudaFuncSetAttribute(decode_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -64,7 +64,8 @@ nms_kernel(const float* __restrict__ scores, const float* __restrict__ boxes,
            float* __restrict__ out_classes, int32_t* __restrict__ out_index) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);  // [NMS_CAP]
-  Cand* kbox = reinterpret_cast<Cand*>(keys + NMS_CAP);                         // [D]
+  unsigned long long* keys2 = keys + NMS_CAP;                                   // [NMS_SEL] prune scratch
+  Cand* kbox = reinterpret_cast<Cand*>(keys2 + NMS_SEL);                        // [D]
   float* kcls = reinterpret_cast<float*>(kbox + D);                             // [D]
   float* karea = kcls + D;                                                      // [D]
 
@@ -109,7 +110,7 @@ nms_kernel(const float* __restrict__ scores, const float* __restrict__ boxes,
       }
       const int fill = topk_append<NMS_EPT>(keys, &s_cnt, k, take);
       if (__syncthreads_or(fill > NMS_CAP - NMS_TILE)) {  // block-uniform, race-free
-        topk_prune_select<NMS_NT, NMS_CAP / NMS_NT>(keys, &s_cnt, &s_thr, NMS_SEL, s_scratch, &s_kth);
+        topk_prune_select<NMS_NT>(keys, keys2, &s_cnt, &s_thr, NMS_SEL, s_scratch, &s_kth);
         pruned = true;
       }
     }
@@ -247,7 +248,7 @@ extern "C" int ssdsb_nms(const float* d_scores, const float* d_boxes, const floa
   SSDSB_REQUIRE(N == 0 || (d_scores && d_boxes && d_classes), "nms: NULL input");
   SSDSB_REQUIRE(((uintptr_t)d_boxes & 15) == 0 && ((uintptr_t)d_out_boxes & 15) == 0,
                 "nms: boxes must be 16-byte aligned");
-  const size_t smem = sizeof(unsigned long long) * NMS_CAP + (size_t)ndetections * (16 + 4 + 4);
+  const size_t smem = sizeof(unsigned long long) * (NMS_CAP + NMS_SEL) + (size_t)ndetections * (16 + 4 + 4);
   static_assert(NMS_CAP >= NMS_SEL + NMS_TILE, "buffer too small");
   SSDSB_CUDA(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
