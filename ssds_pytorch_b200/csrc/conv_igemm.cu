@@ -201,12 +201,16 @@ struct ConvSmem {
   static constexpr int BAR_BYTES = 512;
   static constexpr int MAX_BYTES = 232448;  // 227 KiB opt-in limit per CTA
   static_assert(STAGE_BYTES % 1024 == 0, "stage bases must stay 1024-byte aligned");
-  static int stages_for(int n_staging) {
-    int s = (MAX_BYTES - 1024 - BAR_BYTES - n_staging * STAGING_BYTES) / STAGE_BYTES;
+  static int stage_bytes(bool b_resident) { return b_resident ? A_STAGE_BYTES : STAGE_BYTES; }
+  static int stages_for(int n_staging, bool b_resident, int num_k_blocks) {
+    const int fixed = 1024 + BAR_BYTES + n_staging * STAGING_BYTES +
+                      (b_resident ? num_k_blocks * B_STAGE_BYTES : 0);
+    int s = (MAX_BYTES - fixed) / stage_bytes(b_resident);
     return s > MAX_STAGES ? MAX_STAGES : s;
   }
-  static int bytes(int stages, int n_staging) {
-    return stages * STAGE_BYTES + n_staging * STAGING_BYTES + 1024 + BAR_BYTES;
+  static int bytes(int stages, int n_staging, bool b_resident, int num_k_blocks) {
+    return stages * stage_bytes(b_resident) + n_staging * STAGING_BYTES +
+           (b_resident ? num_k_blocks * B_STAGE_BYTES : 0) + 1024 + BAR_BYTES;
   }
 };
 
@@ -237,15 +241,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   unsigned char* smem = reinterpret_cast<unsigned char*>(
       (reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
   const int STAGES = p.stages;
-  unsigned char* staging = smem + STAGES * S::STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + p.n_staging * STAGING_BYTES);
+  const int stage_bytes = p.b_resident ? A_STAGE_BYTES : S::STAGE_BYTES;
+  unsigned char* staging = smem + STAGES * stage_bytes;
+  unsigned char* bres = staging + p.n_staging * STAGING_BYTES;     // resident weights (optional)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bres + (p.b_resident ? p.num_k_blocks * S::B_STAGE_BYTES : 0));
   uint64_t* full_bar = bars;                           // [MAX_STAGES]
   uint64_t* empty_bar = bars + MAX_STAGES;             // [MAX_STAGES]
   uint64_t* tmem_full = bars + 2 * MAX_STAGES;         // [2]
   uint64_t* tmem_empty = bars + 2 * MAX_STAGES + 2;    // [2]
   uint64_t* slot_ready = bars + 2 * MAX_STAGES + 4;                  // [MAX_STAGING] slot free (+ residual landed)
   uint64_t* slot_full = bars + 2 * MAX_STAGES + 4 + MAX_STAGING;     // [MAX_STAGING] 8 epilogue warps wrote it
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4 + 2 * MAX_STAGING);
+  uint64_t* b_full = bars + 2 * MAX_STAGES + 4 + 2 * MAX_STAGING;     // [1] resident weights landed
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 5 + 2 * MAX_STAGING);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -269,6 +276,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_init(&slot_ready[r], 1);
       mbar_init(&slot_full[r], 8);   // one arrive per epilogue warp
     }
+    mbar_init(b_full, 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -286,18 +294,25 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
   const int num_tiles = m_tiles * p.n_tiles;
   const int rows = p.BW * p.BH * p.BN;
-  const uint32_t tx_bytes = (uint32_t)rows * (BLOCK_K * 2) + (uint32_t)S::B_STAGE_BYTES;
+  const uint32_t tx_bytes = (uint32_t)rows * (BLOCK_K * 2) + (p.b_resident ? 0u : (uint32_t)S::B_STAGE_BYTES);
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      if (p.b_resident && (int)blockIdx.x < num_tiles) {
+        // weight-stationary: the grid is a multiple of n_tiles, so this CTA only ever sees one n_tile
+        const int n_tile = (int)blockIdx.x % p.n_tiles;
+        mbar_expect_tx(b_full, (uint32_t)(p.num_k_blocks * S::B_STAGE_BYTES));
+        for (int kb = 0; kb < p.num_k_blocks; ++kb)
+          tma_load_2d(bres + kb * S::B_STAGE_BYTES, &tmB, b_full, kb * BLOCK_K, n_tile * BLOCK_N);
+      }
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const TileCoord t = tile_coord(p, tile);
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          unsigned char* sa = smem + stage * S::STAGE_BYTES;
+          unsigned char* sa = smem + stage * stage_bytes;
           unsigned char* sb = sa + A_STAGE_BYTES;
           mbar_expect_tx(&full_bar[stage], tx_bytes);
           const int tap = kb / p.kc_per_tap;
@@ -305,7 +320,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const int kh = tap / p.KW, kw = tap - kh * p.KW;
           tma_load_4d(sa, &tmA, &full_bar[stage], kc * BLOCK_K, t.w0 * p.stride + kw - p.pad_w,
                       t.h0 * p.stride + kh - p.pad_h, t.n0);
-          tma_load_2d(sb, &tmB, &full_bar[stage], kb * BLOCK_K, t.n_tile * BLOCK_N);
+          if (!p.b_resident)
+            tma_load_2d(sb, &tmB, &full_bar[stage], kb * BLOCK_K, t.n_tile * BLOCK_N);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -321,6 +337,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      if (p.b_resident && (int)blockIdx.x < num_tiles) mbar_wait(b_full, 0);
+      const uint32_t bres_addr = smem_u32(bres);
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tcgen05_fence_after();
@@ -328,9 +346,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tcgen05_fence_after();
-          const uint32_t a_addr = smem_u32(smem + stage * S::STAGE_BYTES);
+          const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
           const uint64_t a_desc = make_smem_desc<S::ROW_BYTES>(a_addr);
-          const uint64_t b_desc = make_smem_desc<S::ROW_BYTES>(a_addr + A_STAGE_BYTES);
+          const uint64_t b_desc = make_smem_desc<S::ROW_BYTES>(
+              p.b_resident ? bres_addr + (uint32_t)(kb * S::B_STAGE_BYTES) : a_addr + A_STAGE_BYTES);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             // advance 16 bf16 = 32 bytes inside the swizzle row: +2 in the (>>4) address field
@@ -628,12 +647,23 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tm
   }
   kp.n_staging = want_staging ? (kp.residual ? 4 : 2) : 0;
   kp.tma_store = want_staging ? 1 : 0;
-  kp.stages = S::stages_for(kp.n_staging);
+  const int tiles = kp.tiles_w * kp.tiles_h * kp.tiles_n * kp.n_tiles;
+  int grid = tiles < sms ? tiles : sms;
+  // weight-stationary mode: small weight slabs (<= 80 KiB per n-tile) are loaded once per CTA instead of
+  // once per tile; needs every CTA to stay on one n_tile => grid must be a multiple of n_tiles
+  const int bres_bytes = kp.num_k_blocks * S::B_STAGE_BYTES;
+  kp.b_resident = 0;
+  if (bres_bytes <= 80 * 1024 && tiles >= 2 * sms && bres_bytes < (1 << 20)) {
+    const int g2 = grid - grid % kp.n_tiles;
+    if (g2 >= sms / 2) {
+      grid = g2;
+      kp.b_resident = 1;
+    }
+  }
+  kp.stages = S::stages_for(kp.n_staging, kp.b_resident, kp.num_k_blocks);
   if (kp.stages > kp.num_k_blocks * 4) kp.stages = kp.num_k_blocks * 4;   // nothing to gain beyond
   if (kp.stages < 2) kp.stages = 2;
-  const int smem = S::bytes(kp.stages, kp.n_staging);
-  const int tiles = kp.tiles_w * kp.tiles_h * kp.tiles_n * kp.n_tiles;
-  const int grid = tiles < sms ? tiles : sms;
+  const int smem = S::bytes(kp.stages, kp.n_staging, kp.b_resident, kp.num_k_blocks);
   conv_igemm_kernel<BLOCK_N, BLOCK_K><<<grid, CONV_NT, smem, st>>>(tmA, tmB, tmY, tmR, kp);
   SSDSB_LAUNCH_CHECK("conv_igemm_kernel");
   return SSDSB_OK;

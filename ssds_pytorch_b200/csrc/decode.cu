@@ -153,31 +153,36 @@ decode_select(const __grid_constant__ DecodeParams p, void* __restrict__ ws) {
       since_sync = 0;
     }
   }
-  topk_prune<DEC_NT>(buf, &s_cnt, &s_thr, p.K);
+  __syncthreads();
+  topk_prune_select<DEC_NT>(buf, buf + p.cap, &s_cnt, &s_thr, p.K, s_scratch, &s_kth);
   if (tid == 0) {
     if (s_cnt >= p.K) atomicMax(gthr, s_thr);
     s_thr = *reinterpret_cast<volatile unsigned long long*>(gthr);
   }
   __syncthreads();
-  // emit keys >= the shared bound (the bound itself is somebody's K-th key and must survive)
+  // emit (unordered) every key >= the shared bound; the bound itself is somebody's K-th key and must
+  // survive.  decode_finalize does the one and only sort.
   const unsigned long long g = s_thr;
   const int cnt = s_cnt;
   __shared__ int s_emit, s_base;
   if (tid == 0) s_emit = 0;
   __syncthreads();
-  // buf is sorted descending: the survivors are a prefix
   int mine = 0;
   for (int i = tid; i < cnt; i += DEC_NT) mine += (buf[i] >= g) ? 1 : 0;
   if (mine) atomicAdd(&s_emit, mine);
   __syncthreads();
   const int ne = s_emit;
   if (tid == 0 && ne > 0) s_base = atomicAdd(ws_gcnt(ws, p.B, L) + (size_t)b * L + l, ne);
+  if (tid == 0) s_emit = 0;
   __syncthreads();
   if (ne > 0) {
     const int cand_total = p.cand_off[L];
     unsigned long long* dst =
         ws_cand(ws, p.B, L) + (size_t)b * cand_total + p.cand_off[l] + s_base;
-    for (int i = tid; i < ne; i += DEC_NT) dst[i] = buf[i];
+    for (int i = tid; i < cnt; i += DEC_NT) {
+      const unsigned long long key = buf[i];
+      if (key >= g) dst[atomicAdd(&s_emit, 1)] = key;
+    }
   }
 }
 

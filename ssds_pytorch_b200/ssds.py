@@ -60,8 +60,8 @@ class SSDDetector(object):
         if m["SSDS"].upper() != "SSD" or not m["NETS"].startswith("ResNet"):
             raise NotImplementedError("this round implements SSDS='SSD' over ResNet backbones")
         self.cfg = cfg
-        self.device = torch.device(device if device is not None else
-                                   ("cuda", torch.cuda.current_device()))
+        self.device = (torch.device(device) if device is not None
+                       else torch.device("cuda", torch.cuda.current_device()))
         self.mean = float(cfg["DATASET"]["PREPROC"]["MEAN"])
         self.std = float(cfg["DATASET"]["PREPROC"]["STD"])
         self.model = SSDResNet(state_dict, m["FEATURE_LAYER"], m["NUM_CLASSES"],
