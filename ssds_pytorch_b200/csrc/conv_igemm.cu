@@ -31,6 +31,7 @@
 // warp per scheduler cannot hide its own instruction latency, which made the epilogue the bottleneck).
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "conv_params.h"
@@ -375,7 +376,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // on the copy engine and never barrier with each other: per 64-column chunk g (slot g % R)
     //   slot_ready[slot]  <- this thread: slot reusable (+ residual sub-tile landed via TMA)
     //   slot_full[slot]   <- the 8 epilogue warps: sub-tile written (after fence.proxy.async)
-    // and this thread then issues the 4-D TMA store.  Residuals are armed R-1 chunks ahead.
+    // and this thread then issues the 4-D TMA store and re-arms the slot as soon as the store has
+    // been read out of shared memory.  Residuals are thereby prefetched R-1 chunks ahead.
     if (lane == 0 && p.tma_store) {
       const int R = p.n_staging;
       const bool has_res = (p.residual != nullptr);
@@ -409,10 +411,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           tma_store_4d(&tmY, staging + slot * STAGING_BYTES, t.n_tile * BLOCK_N + c * 64, t.w0, t.h0,
                        t.n0);
           tma_store_commit();
-          if (g >= 1) {                 // store g-1 has been read out of smem -> its slot is free
-            tma_store_wait_read<1>();
-            arm_next();                 // = chunk g-1+R
-          }
+          tma_store_wait_read<0>();     // store g has been read out of smem -> its slot is free
+          arm_next();                   // = chunk g+R (residual prefetch distance R-1 chunks)
         }
       }
       tma_store_wait_all();             // smem must outlive the last store
@@ -720,6 +720,10 @@ extern "C" int ssdsb_conv2d_bf16(const ssdsb_conv_desc* d, const void* x, const 
   // ---- M tile: (BW, BH, BN) output pixels, product <= 128 --------------------------------------
   int BW = Wo < 16 ? Wo : 16;
   if (Wo > 16 && Wo < 32) BW = Wo;                              // e.g. 19 -> 19x6 = 114 rows
+  if (const char* e = getenv("SSDSB_TILE_W")) {                 // experiment knob (profiling only)
+    const int v = atoi(e);
+    if (v >= 1 && v <= BLOCK_M && v <= Wo) BW = v;
+  }
   int BH = BLOCK_M / BW;
   if (BH > Ho) BH = Ho;
   int BN = BLOCK_M / (BW * BH);
