@@ -194,6 +194,11 @@ SSDSB_API int ssdsb_pack_image_s2d(const void* d_src, int src_format, int N, int
 SSDSB_API int ssdsb_maxpool3x3s2_nhwc_bf16(const void* d_x, int N, int H, int W, int C, void* d_y,
                                            void* stream);
 
+/* FPN top-down merge (ssds/modeling/ssds/fpn.py:80-87): fine[n,h,w,:] += coarse[n,h/2,w/2,:]
+ * (nearest 2x upsample + add), NHWC bf16, in place on `fine` ([N,H,W,C]; coarse is [N,H/2,W/2,C]). */
+SSDSB_API int ssdsb_upsample2x_add_nhwc_bf16(const void* d_coarse, void* d_fine, int N, int H, int W,
+                                             int C, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -31,10 +31,16 @@ class ConvDesc(C.Structure):
 
 
 def _load():
-    if not os.path.exists(LIB_PATH):
-        raise ImportError(
-            f"{LIB_PATH} is missing: build it with `python -m ssds_pytorch_b200.build` "
-            "(or __graft_entry__.build()). There is no CPU/PyTorch fallback for the hot path.")
+    # (re)build in-tree if the library is missing or older than its sources (no-op when the stamp
+    # matches, e.g. on the GPU box where the prebuilt .so travels with the snapshot)
+    from . import build as _build
+    try:
+        _build.build()
+    except Exception as e:   # noqa: BLE001
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing and could not be built ({e}). There is no CPU/PyTorch "
+                "fallback for the hot path.") from e
     lib = C.CDLL(LIB_PATH)
     vp, i, f, sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
     fp = C.POINTER(C.c_float)
@@ -57,6 +63,7 @@ def _load():
         "ssdsb_conv2d_bf16": (i, [C.POINTER(ConvDesc), vp, vp, vp, vp, vp, vp, vp]),
         "ssdsb_pack_image_s2d": (i, [vp, i, i, i, i, f, f, i, i, vp, vp]),
         "ssdsb_maxpool3x3s2_nhwc_bf16": (i, [vp, i, i, i, i, vp, vp]),
+        "ssdsb_upsample2x_add_nhwc_bf16": (i, [vp, vp, i, i, i, i, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)          # AttributeError if the .so does not export it

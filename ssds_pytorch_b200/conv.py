@@ -139,3 +139,13 @@ def maxpool3x3s2(x, out=None):
     with torch.cuda.device(x.device):
         check(lib.ssdsb_maxpool3x3s2_nhwc_bf16(ptr(x), N, H, W, Cc, ptr(out), stream_ptr()), "maxpool")
     return out
+
+
+def upsample2x_add(coarse, fine):
+    """fine += nearest-2x-upsampled coarse (FPN top-down merge, fpn.py:80-87); NHWC bf16, in place."""
+    N, H, W, Cc = fine.shape
+    assert coarse.shape == (N, H // 2, W // 2, Cc), (coarse.shape, fine.shape)
+    with torch.cuda.device(fine.device):
+        check(lib.ssdsb_upsample2x_add_nhwc_bf16(ptr(coarse), ptr(fine), N, H, W, Cc, stream_ptr()),
+              "upsample2x_add")
+    return fine

@@ -22,8 +22,8 @@ namespace ssdsb {
 namespace {
 
 constexpr int DEC_NT = 256;
-constexpr int DEC_EPT = 4;                 // one float4 per thread per tile
-constexpr int DEC_TILE = DEC_NT * DEC_EPT; // 1024 scores
+constexpr int DEC_EPT = 8;                 // two float4 per thread per tile
+constexpr int DEC_TILE = DEC_NT * DEC_EPT; // 2048 scores
 constexpr int DEC_SLICE = 64 * 1024;       // scores per CTA
 constexpr int DEC_MAX_K = 1024;
 
@@ -91,48 +91,59 @@ decode_select(const __grid_constant__ DecodeParams p, void* __restrict__ ws) {
   const int len = end - begin;
   const int lines = (len + 31) >> 5;                   // 32 floats per 128-byte line
   const int run = (lines + 31) >> 5;                   // lines per run (32 runs)
-  const int iters = vec_ok ? run : (len + DEC_TILE - 1) / DEC_TILE;
-  auto load_tile = [&](int it, float (&v)[DEC_EPT], int& i0) {
+  // one iteration = two consecutive lines of this 8-lane group's run (2 x float4 per thread)
+  const int iters = vec_ok ? (run + 1) / 2 : (len + DEC_TILE - 1) / DEC_TILE;
+  auto load_tile = [&](int it, float (&v)[DEC_EPT], int (&i0)[2]) {
     if (vec_ok) {
-      const int line = (tid >> 3) * run + it;
-      i0 = begin + line * 32 + (tid & 7) * DEC_EPT;
-      if (it < iters && line < lines && i0 + DEC_EPT <= end) {
-        float4 q = __ldcs(reinterpret_cast<const float4*>(src + i0));  // streamed once: evict-first
-        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
-      } else {
-        i0 = end;                                      // nothing for this lane in this iteration
 #pragma unroll
-        for (int e = 0; e < DEC_EPT; ++e) v[e] = -INFINITY;
+      for (int h = 0; h < 2; ++h) {
+        const int lr = 2 * it + h;                     // line inside the run
+        const int line = (tid >> 3) * run + lr;
+        i0[h] = begin + line * 32 + (tid & 7) * 4;
+        if (it < iters && lr < run && line < lines && i0[h] + 4 <= end) {
+          float4 q = __ldcs(reinterpret_cast<const float4*>(src + i0[h]));  // streamed once
+          v[h * 4 + 0] = q.x; v[h * 4 + 1] = q.y; v[h * 4 + 2] = q.z; v[h * 4 + 3] = q.w;
+        } else {
+          i0[h] = end;                                 // nothing for this lane in this half
+#pragma unroll
+          for (int e = 0; e < 4; ++e) v[h * 4 + e] = -INFINITY;
+        }
       }
     } else {
-      i0 = begin + it * DEC_TILE + tid * DEC_EPT;
 #pragma unroll
-      for (int e = 0; e < DEC_EPT; ++e) v[e] = (it < iters && i0 + e < end) ? __ldcs(src + i0 + e) : -INFINITY;
+      for (int h = 0; h < 2; ++h) {
+        i0[h] = begin + it * DEC_TILE + h * (DEC_TILE / 2) + tid * 4;
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          v[h * 4 + e] = (it < iters && i0[h] + e < end) ? __ldcs(src + i0[h] + e) : -INFINITY;
+      }
     }
   };
   float vn[DEC_EPT];
-  int i0n;
+  int i0n[2];
   load_tile(0, vn, i0n);
   for (int it = 0; it < iters; ++it) {
     float v[DEC_EPT];
-    const int i0 = i0n;
+    const int i0[2] = {i0n[0], i0n[1]};
 #pragma unroll
     for (int e = 0; e < DEC_EPT; ++e) v[e] = vn[e];
-    load_tile(it + 1, vn, i0n);                        // prefetch: two loads in flight per thread
+    load_tile(it + 1, vn, i0n);                        // prefetch: four loads in flight per thread
     // fast reject in the float domain; the exact 64-bit key test only runs in warps that have a
     // candidate (rare once the running K-th score has converged)
     const unsigned long long cur = s_thr;
     const float curF = (cur == 0ull) ? -INFINITY : key_score(cur);
     const float lim = fmaxf(thr, curF);
-    const bool pre = (v[0] >= lim) | (v[1] >= lim) | (v[2] >= lim) | (v[3] >= lim);
+    const bool pre = (v[0] >= lim) | (v[1] >= lim) | (v[2] >= lim) | (v[3] >= lim) |
+                     (v[4] >= lim) | (v[5] >= lim) | (v[6] >= lim) | (v[7] >= lim);
     int fill = 0;
     if (__any_sync(0xffffffffu, pre)) {
       unsigned long long k[DEC_EPT];
       bool take[DEC_EPT];
 #pragma unroll
       for (int e = 0; e < DEC_EPT; ++e) {
-        k[e] = make_key(v[e], (uint32_t)(i0 + e));
-        take[e] = (i0 + e < end) && (v[e] >= thr) && (k[e] > cur);
+        const int idx = i0[e >> 2] + (e & 3);
+        k[e] = make_key(v[e], (uint32_t)idx);
+        take[e] = (idx < end) && (v[e] >= thr) && (k[e] > cur);
       }
       fill = topk_append<DEC_EPT>(buf, &s_cnt, k, take);
     }
@@ -288,7 +299,7 @@ int fill_params(DecodeParams& p, const ssdsb_level* levels, int n_levels, int B,
   p.n_levels = n_levels;
   p.B = B;
   p.K = top_n;
-  p.cap = next_pow2(2 * top_n + DEC_TILE);
+  p.cap = next_pow2(top_n + DEC_TILE + 1);   // prune when fewer than one tile of slots is left
   if (p.cap < 2 * DEC_TILE) p.cap = 2 * DEC_TILE;
   p.slice_begin[0] = 0;
   p.cand_off[0] = 0;

@@ -93,10 +93,53 @@ maxpool3x3s2_kernel(const uint4* __restrict__ x, int N, int H, int W, int C8, in
   }
 }
 
+// fine[n,h,w,:] += coarse[n,h/2,w/2,:]   (F.interpolate(scale_factor=2, mode="nearest") + lateral,
+// fpn.py:80-87), fp32 add of bf16 operands, 8 channels per thread
+__global__ void __launch_bounds__(256)
+upsample2x_add_kernel(const uint4* __restrict__ coarse, uint4* __restrict__ fine, int N, int H, int W,
+                      int C8) {
+  const size_t total = (size_t)N * H * W * C8;
+  const int Hc = H >> 1, Wc = W >> 1;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C8);
+    const int w = (int)((i / C8) % W);
+    const int h = (int)((i / ((size_t)C8 * W)) % H);
+    const int n = (int)(i / ((size_t)C8 * W * H));
+    const uint4 a = fine[i];
+    const uint4 b = __ldg(coarse + (((size_t)n * Hc + (h >> 1)) * Wc + (w >> 1)) * C8 + c);
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float lo = __uint_as_float(aw[e] << 16) + __uint_as_float(bw[e] << 16);
+      const float hi = __uint_as_float(aw[e] & 0xffff0000u) + __uint_as_float(bw[e] & 0xffff0000u);
+      o[e] = pack2(lo, hi);
+    }
+    fine[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 }  // namespace
 }  // namespace ssdsb
 
 using namespace ssdsb;
+
+extern "C" int ssdsb_upsample2x_add_nhwc_bf16(const void* d_coarse, void* d_fine, int N, int H, int W,
+                                              int C, void* stream) {
+  SSDSB_REQUIRE(d_coarse && d_fine, "upsample2x_add: NULL argument");
+  SSDSB_REQUIRE(N >= 1 && H >= 2 && W >= 2 && (H % 2) == 0 && (W % 2) == 0 && C >= 8 && C % 8 == 0,
+                "upsample2x_add: fine map must be even-sized with C %% 8 == 0 (N=%d H=%d W=%d C=%d)", N, H, W, C);
+  SSDSB_REQUIRE((((uintptr_t)d_coarse | (uintptr_t)d_fine) & 15) == 0,
+                "upsample2x_add: pointers must be 16-byte aligned");
+  const size_t total = (size_t)N * H * W * (C / 8);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  upsample2x_add_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const uint4*>(d_coarse), reinterpret_cast<uint4*>(d_fine), N, H, W, C / 8);
+  SSDSB_LAUNCH_CHECK("upsample2x_add_kernel");
+  return SSDSB_OK;
+}
 
 extern "C" int ssdsb_pack_image_s2d(const void* d_src, int src_format, int N, int H, int W,
                                     float mean, float stdv, int out_row_pixels, int left_pad,

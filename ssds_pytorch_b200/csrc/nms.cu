@@ -72,7 +72,7 @@ nms_kernel(const float* __restrict__ scores, const float* __restrict__ boxes,
   __shared__ Cand cbox[NMS_CH];
   __shared__ float ccls[NMS_CH], carea[NMS_CH], cscore[NMS_CH];
   __shared__ uint32_t cidx[NMS_CH];
-  __shared__ uint32_t mat[NMS_CH][NMS_CW];
+  __shared__ __align__(16) uint32_t mat[NMS_CH][NMS_CW];
   __shared__ uint32_t alive_w[NMS_CW];
   __shared__ int keptpos[NMS_CH];
   __shared__ int s_cnt, s_nk;
@@ -174,21 +174,27 @@ nms_kernel(const float* __restrict__ scores, const float* __restrict__ boxes,
       }
       __syncthreads();
 
-      // (3) sequential scan by warp 0
-      if (tid < 32) {
-        uint32_t alive = (tid < NMS_CW) ? alive_w[tid] : 0u;
+      // (3) sequential scan by ONE thread over the alive bit-mask (4 x 32 bits in registers): only
+      //     alive candidates are visited (find-first-set), each costs one 128-bit row load + 4 ANDs
+      if (tid == 0) {
+        uint32_t a0 = alive_w[0], a1 = alive_w[1], a2 = alive_w[2], a3 = alive_w[3];
         int nk = 0;
         const int room = D - nkept;
-        for (int i = 0; i < m; ++i) {
-          uint32_t wv = __shfl_sync(0xffffffffu, alive, i >> 5);
-          if ((wv >> (i & 31)) & 1u) {
-            if (tid == 0) keptpos[nk] = i;
-            ++nk;
-            if (nk == room) break;
-            if (tid < NMS_CW) alive &= ~mat[i][tid];
-          }
+#define NMS_SCAN_WORD(W, AW)                                                        \
+        while (AW != 0u && nk < room) {                                             \
+          const int bit = __ffs(AW) - 1;                                            \
+          const int i = (W) * 32 + bit;                                             \
+          keptpos[nk++] = i;                                                        \
+          const uint4 row = *reinterpret_cast<const uint4*>(&mat[i][0]);            \
+          a0 &= ~row.x; a1 &= ~row.y; a2 &= ~row.z; a3 &= ~row.w;                   \
+          AW &= ~(1u << bit);                                                       \
         }
-        if (tid == 0) s_nk = nk;
+        NMS_SCAN_WORD(0, a0)
+        NMS_SCAN_WORD(1, a1)
+        NMS_SCAN_WORD(2, a2)
+        NMS_SCAN_WORD(3, a3)
+#undef NMS_SCAN_WORD
+        s_nk = nk;
       }
       __syncthreads();
 

@@ -42,9 +42,8 @@ class _Conv:
         self.flops_per_pixel = 2 * weight[0].numel() * self.cout   # algorithmic (un-padded) FLOPs
 
 
-class SSDResNet(torch.nn.Module):
-    """B200 engine for SSD over a torchvision-style ResNet backbone (reference cfg: SSDS='SSD',
-    NETS='ResNet18/34/50/101/152')."""
+class _ResNetEngine(torch.nn.Module):
+    """Shared machinery: packed ResNet backbone, plan recording (static buffers), CUDA-graph replay."""
 
     def __init__(self, state_dict, feature_layer, num_classes, number_box, device="cuda",
                  mean=0.0, std=1.0):
@@ -54,6 +53,12 @@ class SSDResNet(torch.nn.Module):
         self.num_classes = num_classes
         self.number_box = list(number_box)
         self.mean, self.std = float(mean), float(std)
+        self._plans = {}
+        self.training = False
+        self._build_backbone(sd, feature_layer)
+        self._build_neck(sd, feature_layer)
+
+    def _build_backbone(self, sd, feature_layer):
         dev = self.device
 
         self.stem = _Conv(sd["backbone.conv1.weight"], _bn(sd, "backbone.bn1"), None, 2, 3, True, dev,
@@ -88,31 +93,6 @@ class SSDResNet(torch.nn.Module):
                 blocks.append(blk)
                 bi += 1
             self.layers.append(blocks)
-        # extras: ConvBNReLUx2 (layers_parser.py:17-20)
-        self.extras = []
-        ei = 0
-        for layer in feature_layer[0]:
-            if isinstance(layer, int):
-                continue
-            if layer not in ("Conv:S", "Conv"):
-                raise NotImplementedError(f"extra layer {layer!r} is out of scope (SURVEY 2, rows 9-11)")
-            stride = 2 if layer == "Conv:S" else 1
-            p = f"extras.{ei}"
-            self.extras.append([
-                _Conv(sd[p + ".0.weight"], _bn(sd, p + ".1"), None, 1, 0, True, dev),
-                _Conv(sd[p + ".3.weight"], _bn(sd, p + ".4"), None, stride, 1, True, dev),
-            ])
-            ei += 1
-        # heads: loc + conf fused per level (ssd.py:100-103)
-        self.heads = []
-        for l, nb in enumerate(self.number_box):
-            w = torch.cat([sd[f"loc.{l}.weight"], sd[f"conf.{l}.weight"]], 0)
-            b = torch.cat([sd[f"loc.{l}.bias"], sd[f"conf.{l}.bias"]], 0)
-            h = _Conv(w, None, b, 1, 1, False, dev)
-            h.n_loc = nb * 4
-            self.heads.append(h)
-        self._plans = {}
-        self.training = False
 
     # ------------------------------------------------------------------ plan (static buffers)
     def _build_plan(self, images):
@@ -136,17 +116,29 @@ class SSDResNet(torch.nn.Module):
         mean, std = self.mean, self.std
         steps.append(lambda: K.pack_image_s2d(src, mean, std, out=packed))
 
-        def add_conv(cv, x, residual=None, relu=None, Ho=0, Wo=0, x_kind=0, x_width=None):
+        def add_conv(cv, x, residual=None, relu=None, Ho=0, Wo=0, x_kind=0, x_width=None, out=None):
             n, h, w, _ = x.shape
             ho = Ho or (h + 2 * cv.pad - cv.KH) // cv.stride + 1
             wo = Wo or (w + 2 * cv.pad - cv.KW) // cv.stride + 1
-            y = buf(n, ho, wo, cv.cout)
+            y = out if out is not None else buf(n, ho, wo, cv.cout)
             r = cv.relu if relu is None else relu
             steps.append(lambda: K.conv2d(x, cv.w, cv.bias, cv.KH, cv.KW, cv.stride, cv.pad, r,
                                           residual, out=y, Ho=ho, Wo=wo, x_kind=x_kind,
                                           x_width=x_width))
             flops[0] += cv.flops_per_pixel * n * ho * wo
             return y
+
+        def add_head(f, h, loc=None, conf=None):
+            """fused loc+conf head conv -> fp32 NCHW tensors (n_loc channels go to loc)."""
+            n, fh, fw, _ = f.shape
+            if loc is None:
+                loc = torch.empty((n, h.n_loc, fh, fw), dtype=torch.float32, device=dev)
+            if conf is None:
+                conf = torch.empty((n, h.cout - h.n_loc, fh, fw), dtype=torch.float32, device=dev)
+            steps.append(lambda: K.conv2d_head(f, h.w, h.bias, h.n_loc, not self.training,
+                                               loc=loc, conf=conf))
+            flops[0] += h.flops_per_pixel * n * fh * fw
+            return loc, conf
 
         x = add_conv(self.stem, packed, Ho=H // 2, Wo=W // 2, x_kind=1, x_width=W // 2)
         pooled = buf(N, (x.shape[1] - 1) // 2 + 1, (x.shape[2] - 1) // 2 + 1, x.shape[3])
@@ -163,23 +155,7 @@ class SSDResNet(torch.nn.Module):
                 x = add_conv(blk["convs"][-1], y, residual=identity, relu=True)
             if li + 2 in self.outputs:
                 feats.append(x)
-        for ex in self.extras:                         # ssd.py:61-64
-            y = feats[-1]
-            for cv in ex:
-                y = add_conv(cv, y)
-            feats.append(y)
-        locs, confs = [], []
-        for f, h in zip(feats, self.heads):            # ssd.py:67-70
-            n, fh, fw, _ = f.shape
-            loc = torch.empty((n, h.n_loc, fh, fw), dtype=torch.float32, device=dev)
-            conf = torch.empty((n, h.cout - h.n_loc, fh, fw), dtype=torch.float32, device=dev)
-            locs.append(loc)
-            confs.append(conf)
-
-            def run_head(f=f, h=h, loc=loc, conf=conf):
-                K.conv2d_head(f, h.w, h.bias, h.n_loc, not self.training, loc=loc, conf=conf)
-            steps.append(run_head)
-            flops[0] += h.flops_per_pixel * n * fh * fw
+        locs, confs = self._plan_neck(feats, steps, buf, add_conv, add_head)
         return {"src": src, "steps": steps, "loc": tuple(locs), "conf": tuple(confs),
                 "flops": flops[0], "graph": None, "launches": len(steps)}
 
@@ -224,6 +200,127 @@ class SSDResNet(torch.nn.Module):
     def train(self, mode=True):
         self.training = bool(mode)
         return self
+
+
+class SSDResNet(_ResNetEngine):
+    """B200 engine for SSD over a torchvision-style ResNet backbone (reference cfg: SSDS='SSD',
+    NETS='ResNet18/34/50/101/152'; ssd.py:42-104)."""
+
+    def _build_neck(self, sd, feature_layer):
+        dev = self.device
+        # extras: ConvBNReLUx2 (layers_parser.py:17-20)
+        self.extras = []
+        ei = 0
+        for layer in feature_layer[0]:
+            if isinstance(layer, int):
+                continue
+            if layer not in ("Conv:S", "Conv"):
+                raise NotImplementedError(f"extra layer {layer!r} is out of scope (SURVEY 2, rows 9-11)")
+            stride = 2 if layer == "Conv:S" else 1
+            p = f"extras.{ei}"
+            self.extras.append([
+                _Conv(sd[p + ".0.weight"], _bn(sd, p + ".1"), None, 1, 0, True, dev),
+                _Conv(sd[p + ".3.weight"], _bn(sd, p + ".4"), None, stride, 1, True, dev),
+            ])
+            ei += 1
+        # heads: loc + conf fused per level (ssd.py:100-103)
+        self.heads = []
+        for l, nb in enumerate(self.number_box):
+            w = torch.cat([sd[f"loc.{l}.weight"], sd[f"conf.{l}.weight"]], 0)
+            b = torch.cat([sd[f"loc.{l}.bias"], sd[f"conf.{l}.bias"]], 0)
+            h = _Conv(w, None, b, 1, 1, False, dev)
+            h.n_loc = nb * 4
+            self.heads.append(h)
+
+    def _plan_neck(self, feats, steps, buf, add_conv, add_head):
+        feats = list(feats)
+        for ex in self.extras:                         # ssd.py:61-64
+            y = feats[-1]
+            for cv in ex:
+                y = add_conv(cv, y)
+            feats.append(y)
+        locs, confs = [], []
+        for f, h in zip(feats, self.heads):            # ssd.py:67-70
+            loc, conf = add_head(f, h)
+            locs.append(loc)
+            confs.append(conf)
+        return locs, confs
+
+
+class SSDFPNResNet(_ResNetEngine):
+    """B200 engine for SSDFPN / RetinaNet over ResNet (reference cfg: SSDS='SSDFPN'; fpn.py:58-146).
+
+    transforms: 1x1 lateral convs with bias (no BN/ReLU); top-down nearest-2x upsample + add
+    (fpn.py:80-87); extras: ConvBNReLU 3x3 per pyramid level, 'Conv:S' levels are stride-2 convs on the
+    raw last backbone map / the previous extra (fpn.py:89-95); loc and conf are SHARED towers of
+    4 x ConvBNReLU(256,256,3) + 3x3 conv (fpn.py:10-18).  The first tower layer of loc and conf reads
+    the same input, so the two are fused into one 256->512 conv; the later layers read their own
+    256-channel half through the channel stride."""
+
+    def _build_neck(self, sd, feature_layer):
+        dev = self.device
+        n_back = len(self.outputs)
+        self.transforms = [_Conv(sd[f"transforms.{i}.weight"], None, sd[f"transforms.{i}.bias"], 1, 0,
+                                 False, dev) for i in range(n_back)]
+        self.extras = []
+        for i, layer in enumerate(feature_layer[0]):
+            stride = 1 if isinstance(layer, int) else 2
+            if not isinstance(layer, int) and layer != "Conv:S":
+                raise ValueError(layer + " does not support by SSDFPN")       # fpn.py:144
+            self.extras.append(_Conv(sd[f"extras.{i}.0.weight"], _bn(sd, f"extras.{i}.1"), None, stride, 1,
+                                     True, dev))
+        nb = self.number_box[0]
+        if any(b != nb for b in self.number_box):
+            raise ValueError("For SSDFPN module, the number of box have to be same in every layer")
+        # tower layer 0 of loc and conf fused (same input)
+        w0 = torch.cat([sd["loc.0.0.weight"], sd["conf.0.0.weight"]], 0)
+        bn0 = tuple(torch.cat([a, b], 0) if isinstance(a, torch.Tensor) else a
+                    for a, b in zip(_bn(sd, "loc.0.1"), _bn(sd, "conf.0.1")))
+        self.tower0 = _Conv(w0, bn0, None, 1, 1, True, dev)
+        self.tower = {t: [_Conv(sd[f"{t}.{j}.0.weight"], _bn(sd, f"{t}.{j}.1"), None, 1, 1, True, dev)
+                          for j in (1, 2, 3)] for t in ("loc", "conf")}
+        self.head_loc = _Conv(sd["loc.4.weight"], None, sd["loc.4.bias"], 1, 1, False, dev)
+        self.head_loc.n_loc = self.head_loc.cout                 # every channel goes to `loc`
+        self.head_conf = _Conv(sd["conf.4.weight"], None, sd["conf.4.bias"], 1, 1, False, dev)
+        self.head_conf.n_loc = 0                                 # every channel goes to `conf`
+
+    def _plan_neck(self, feats, steps, buf, add_conv, add_head):
+        n_back = len(feats)
+        raw_top = feats[-1]
+        pyr = [None] * n_back
+        for i in range(n_back - 1, -1, -1):            # fpn.py:79-87
+            lat = add_conv(self.transforms[i], feats[i])
+            if i != n_back - 1:
+                coarse = pyr[i + 1]
+                steps.append(lambda c=coarse, f=lat: K.upsample2x_add(c, f))
+            pyr[i] = lat
+        levels = []
+        xx = None
+        for i, ex in enumerate(self.extras):           # fpn.py:89-95
+            if i < n_back:
+                xx = add_conv(ex, pyr[i])
+            elif i == n_back:
+                xx = add_conv(ex, raw_top)
+            else:
+                xx = add_conv(ex, xx)
+            levels.append(xx)
+        locs, confs = [], []
+        dev = self.device
+        for f in levels:                               # shared towers, fpn.py:94-95
+            t = add_conv(self.tower0, f)               # [.., 512]: loc half | conf half
+            tl, tc = t[..., :256], t[..., 256:]
+            for j in range(3):
+                tl = add_conv(self.tower["loc"][j], tl)
+                tc = add_conv(self.tower["conf"][j], tc)
+            n, fh, fw, _ = f.shape
+            loc = torch.empty((n, self.head_loc.cout, fh, fw), dtype=torch.float32, device=dev)
+            conf = torch.empty((n, self.head_conf.cout, fh, fw), dtype=torch.float32, device=dev)
+            dummy_c = torch.empty((1,), dtype=torch.float32, device=dev)
+            add_head(tl, self.head_loc, loc=loc, conf=dummy_c)
+            add_head(tc, self.head_conf, loc=dummy_c, conf=conf)
+            locs.append(loc)
+            confs.append(conf)
+        return locs, confs
 
 
 def create_anchors(model_cfg, model, image_size):

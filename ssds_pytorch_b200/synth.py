@@ -17,6 +17,67 @@ RESNETS = {
 }
 
 
+def _bn_keys(out, p, c):
+    out.extend([(p + ".weight", (c,)), (p + ".bias", (c,)), (p + ".running_mean", (c,)),
+                (p + ".running_var", (c,)), (p + ".num_batches_tracked", ())])
+
+
+def resnet_backbone_shapes(nets):
+    """(key, shape) list of the torchvision ResNet under `backbone.` (resnet.py:9-35)."""
+    block, layers = RESNETS[nets]
+    exp = 4 if block == "bottleneck" else 1
+    out = []
+
+    def bn(p, c):
+        _bn_keys(out, p, c)
+
+    out.append(("backbone.conv1.weight", (64, 3, 7, 7)))
+    bn("backbone.bn1", 64)
+    inplanes = 64
+    for li, nblocks in enumerate(layers, start=1):
+        planes = 64 * 2 ** (li - 1)
+        for bi in range(nblocks):
+            p = f"backbone.layer{li}.{bi}"
+            stride = 2 if (li > 1 and bi == 0) else 1
+            if block == "bottleneck":
+                out.append((p + ".conv1.weight", (planes, inplanes, 1, 1))); bn(p + ".bn1", planes)
+                out.append((p + ".conv2.weight", (planes, planes, 3, 3))); bn(p + ".bn2", planes)
+                out.append((p + ".conv3.weight", (planes * 4, planes, 1, 1))); bn(p + ".bn3", planes * 4)
+            else:
+                out.append((p + ".conv1.weight", (planes, inplanes, 3, 3))); bn(p + ".bn1", planes)
+                out.append((p + ".conv2.weight", (planes, planes, 3, 3))); bn(p + ".bn2", planes)
+            if stride != 1 or inplanes != planes * exp:
+                out.append((p + ".downsample.0.weight", (planes * exp, inplanes, 1, 1)))
+                bn(p + ".downsample.1", planes * exp)
+            inplanes = planes * exp
+    out.append(("backbone.fc.weight", (1000, 512 * exp)))
+    out.append(("backbone.fc.bias", (1000,)))
+    return out
+
+
+def ssdfpn_resnet_shapes(nets, feature_layer, number_box, num_classes):
+    """SSDFPN (fpn.py:36-146): transforms.{i} 1x1 laterals with bias, extras.{i} ConvBNReLU 3x3,
+    shared towers loc/conf = 4 x ConvBNReLU(256,256,3) + Conv2d(256, A*4 | A*C, 3)."""
+    out = resnet_backbone_shapes(nets)
+    ti = 0
+    for layer, depth in zip(feature_layer[0], feature_layer[1]):
+        if isinstance(layer, int):
+            out.append((f"transforms.{ti}.weight", (256, depth, 1, 1)))
+            out.append((f"transforms.{ti}.bias", (256,)))
+            ti += 1
+    for i, (layer, depth) in enumerate(zip(feature_layer[0], feature_layer[1])):
+        cin = 256 if isinstance(layer, int) else depth
+        out.append((f"extras.{i}.0.weight", (256, cin, 3, 3)))
+        _bn_keys(out, f"extras.{i}.1", 256)
+    for tower, cout in (("loc", number_box[0] * 4), ("conf", number_box[0] * num_classes)):
+        for j in range(4):
+            out.append((f"{tower}.{j}.0.weight", (256, 256, 3, 3)))
+            _bn_keys(out, f"{tower}.{j}.1", 256)
+        out.append((f"{tower}.4.weight", (cout, 256, 3, 3)))
+        out.append((f"{tower}.4.bias", (cout,)))
+    return out
+
+
 def ssd_resnet_shapes(nets, feature_layer, number_box, num_classes):
     """OrderedDict-like list of (key, shape) in the reference's state_dict order."""
     block, layers = RESNETS[nets]
@@ -24,8 +85,7 @@ def ssd_resnet_shapes(nets, feature_layer, number_box, num_classes):
     out = []
 
     def bn(p, c):
-        out.extend([(p + ".weight", (c,)), (p + ".bias", (c,)), (p + ".running_mean", (c,)),
-                    (p + ".running_var", (c,)), (p + ".num_batches_tracked", ())])
+        _bn_keys(out, p, c)
 
     out.append(("backbone.conv1.weight", (64, 3, 7, 7)))
     bn("backbone.bn1", 64)
@@ -65,7 +125,8 @@ def ssd_resnet_shapes(nets, feature_layer, number_box, num_classes):
     return out
 
 
-def synthetic_state_dict(nets, feature_layer, number_box, num_classes, seed=0, style="test"):
+def synthetic_state_dict(nets, feature_layer, number_box, num_classes, seed=0, style="test",
+                         ssds="SSD"):
     """Deterministic weights.
     style "init": the reference's initialisation statistics — kaiming-normal convs, BN (1, 0, 0, 1)
     (torchvision ResNet), xavier extras (ssdsbase.py:27-31), N(0, 0.01) heads with the conf prior bias
@@ -75,15 +136,19 @@ def synthetic_state_dict(nets, feature_layer, number_box, num_classes, seed=0, s
     g = torch.Generator().manual_seed(seed)
     sd = {}
     prior = -math.log((1 - 0.01) / 0.01)
-    for key, shape in ssd_resnet_shapes(nets, feature_layer, number_box, num_classes):
+    shapes = (ssdfpn_resnet_shapes if ssds == "SSDFPN" else ssd_resnet_shapes)(
+        nets, feature_layer, number_box, num_classes)
+    bn_prefixes = {k.rsplit(".", 1)[0] for k, _ in shapes if k.endswith("running_mean")}
+    head_final = {k for k, _ in shapes if k.startswith(("loc.", "conf.")) and
+                  k.rsplit(".", 1)[0] not in bn_prefixes and (ssds != "SSDFPN" or k.split(".")[1] == "4")}
+    for key, shape in shapes:
         if key.endswith("num_batches_tracked"):
             sd[key] = torch.tensor(0, dtype=torch.long)
         elif key.endswith("running_mean"):
             sd[key] = torch.zeros(shape) if style == "init" else torch.randn(shape, generator=g) * 0.1
         elif key.endswith("running_var"):
             sd[key] = torch.ones(shape) if style == "init" else torch.rand(shape, generator=g) + 0.5
-        elif len(shape) == 1 and ".bn" in key or key.endswith((".1.weight", ".1.bias", ".4.weight", ".4.bias")) \
-                and len(shape) == 1:
+        elif len(shape) == 1 and key.rsplit(".", 1)[0] in bn_prefixes:
             is_w = key.endswith("weight")
             if style == "init":
                 sd[key] = torch.ones(shape) if is_w else torch.zeros(shape)
@@ -94,11 +159,20 @@ def synthetic_state_dict(nets, feature_layer, number_box, num_classes, seed=0, s
                 sd[key] = torch.rand(shape, generator=g) * 0.4 + lo
             else:
                 sd[key] = torch.randn(shape, generator=g) * 0.1
-        elif key.startswith(("loc.", "conf.")):
+        elif key in head_final or (ssds != "SSDFPN" and key.startswith(("loc.", "conf."))):
             if key.endswith("weight"):
                 sd[key] = torch.randn(shape, generator=g) * 0.01
             else:
                 sd[key] = torch.full(shape, prior if key.startswith("conf.") else 0.0)
+        elif key.startswith(("loc.", "conf.")):      # SSDFPN tower convs: N(0, 0.01) (ssdsbase.py:21-25)
+            sd[key] = torch.randn(shape, generator=g) * (0.01 if style == "init" else 0.03)
+        elif key.startswith("transforms."):
+            if key.endswith("weight"):
+                fan_in, fan_out = shape[1], shape[0]
+                a = math.sqrt(6.0 / (fan_in + fan_out))
+                sd[key] = (torch.rand(shape, generator=g) * 2 - 1) * a
+            else:
+                sd[key] = torch.zeros(shape) if style == "init" else torch.randn(shape, generator=g) * 0.05
         elif key.startswith("backbone.fc"):
             sd[key] = torch.zeros(shape)
         elif key.startswith("extras."):
