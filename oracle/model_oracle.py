@@ -47,10 +47,8 @@ def _conv_bn(x, sd, wkey, bnkey, stride, pad, relu, policy, residual=None, bias=
     return y
 
 
-def ssd_resnet_forward(sd, x, feature_layer, training=False, policy="fp32"):
-    """x fp32 NCHW (already normalised).  Returns (tuple loc, tuple conf) like ssd.py:42-74."""
-    sd = {k: v for k, v in sd.items()}
-    outputs = [l for l in feature_layer[0] if isinstance(l, int)]
+def resnet_features(sd, x, outputs, policy):
+    """reference resnet.py:41-56: list of the backbone feature maps named in `outputs`."""
     x = _r(x.float(), policy)
     x = _r(_conv_bn(x, sd, "backbone.conv1.weight", "backbone.bn1", 2, 3, True, policy), policy)
     x = F.max_pool2d(x, 3, 2, 1)
@@ -76,6 +74,13 @@ def ssd_resnet_forward(sd, x, feature_layer, training=False, policy="fp32"):
             bi += 1
         if li + 1 in outputs:
             feats.append(x)
+    return feats
+
+
+def ssd_resnet_forward(sd, x, feature_layer, training=False, policy="fp32"):
+    """x fp32 NCHW (already normalised).  Returns (tuple loc, tuple conf) like ssd.py:42-74."""
+    outputs = [l for l in feature_layer[0] if isinstance(l, int)]
+    feats = resnet_features(sd, x, outputs, policy)
     ei = 0
     for layer in feature_layer[0]:
         if isinstance(layer, int):
@@ -91,4 +96,39 @@ def ssd_resnet_forward(sd, x, feature_layer, training=False, policy="fp32"):
         loc.append(_conv_bn(f, sd, f"loc.{l}.weight", None, 1, 1, False, policy, bias=sd[f"loc.{l}.bias"]))
         c = _conv_bn(f, sd, f"conf.{l}.weight", None, 1, 1, False, policy, bias=sd[f"conf.{l}.bias"])
         conf.append(c if training else torch.sigmoid(c))
+    return tuple(loc), tuple(conf)
+
+
+def ssdfpn_resnet_forward(sd, x, feature_layer, training=False, policy="fp32"):
+    """reference fpn.py:58-101 (SSDFPN.forward) on a state_dict.
+
+    bf16 policy mirrors the B200 path: the lateral conv output is stored (rounded) before the
+    upsample-add, the sum is stored again; every tower layer output is stored in bf16."""
+    outputs = [l for l in feature_layer[0] if isinstance(l, int)]
+    feats = resnet_features(sd, x, outputs, policy)
+    n_back = len(feats)
+    raw_top = feats[-1]
+    pyr = [None] * n_back
+    xx = None
+    for i in range(n_back - 1, -1, -1):                                   # fpn.py:79-87
+        lat = _r(_conv_bn(feats[i], sd, f"transforms.{i}.weight", None, 1, 0, False, policy,
+                          bias=sd[f"transforms.{i}.bias"]), policy)
+        if i != n_back - 1:
+            lat = _r(F.interpolate(xx, scale_factor=2, mode="nearest") + lat, policy)
+        xx = lat
+        pyr[i] = lat
+    loc, conf = [], []
+    for i, layer in enumerate(feature_layer[0]):                          # fpn.py:89-97
+        stride = 1 if isinstance(layer, int) else 2
+        src = pyr[i] if i < n_back else (raw_top if i == n_back else xx)
+        xx = _r(_conv_bn(src, sd, f"extras.{i}.0.weight", f"extras.{i}.1", stride, 1, True, policy), policy)
+        outs = []
+        for tower in ("loc", "conf"):                                     # SharedHead fpn.py:10-18
+            t = xx
+            for j in range(4):
+                t = _r(_conv_bn(t, sd, f"{tower}.{j}.0.weight", f"{tower}.{j}.1", 1, 1, True, policy), policy)
+            outs.append(_conv_bn(t, sd, f"{tower}.4.weight", None, 1, 1, False, policy,
+                                 bias=sd[f"{tower}.4.bias"]))
+        loc.append(outs[0])
+        conf.append(outs[1] if training else torch.sigmoid(outs[1]))
     return tuple(loc), tuple(conf)

@@ -42,9 +42,9 @@ CONF_CH_STRIDE = 7
 OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "model_small.npz")
 
 
-def build(nets, feature_layer, sizes, ratios, image, num_classes):
+def build(nets, feature_layer, sizes, ratios, image, num_classes, ssds="SSD"):
     cfg = rcfg.cfg.MODEL
-    cfg.SSDS, cfg.NETS, cfg.IMAGE_SIZE, cfg.NUM_CLASSES = "SSD", nets, image, num_classes
+    cfg.SSDS, cfg.NETS, cfg.IMAGE_SIZE, cfg.NUM_CLASSES = ssds, nets, image, num_classes
     cfg.FEATURE_LAYER, cfg.SIZES, cfg.ASPECT_RATIOS = feature_layer, sizes, ratios
     return cfg, model_builder.create_model(cfg)
 
@@ -52,22 +52,24 @@ def build(nets, feature_layer, sizes, ratios, image, num_classes):
 def main():
     G = {}
     cases = {
-        "r50": ("ResNet50", [[3, 4, 5, "Conv:S", "Conv:S", "Conv:S"], [512, 1024, 2048, 512, 256, 256]],
+        "r50": ("SSD", "ResNet50", [[3, 4, 5, "Conv:S", "Conv:S", "Conv:S"], [512, 1024, 2048, 512, 256, 256]],
                 [256, 256], 80, 1),
-        "r18": ("ResNet18", [[3, 4, 5, "Conv:S"], [128, 256, 512, 256]], [96, 160], 20, 3),
+        "r18": ("SSD", "ResNet18", [[3, 4, 5, "Conv:S"], [128, 256, 512, 256]], [96, 160], 20, 3),
+        "fpn50": ("SSDFPN", "ResNet50", [[3, 4, 5, "Conv:S", "Conv:S"], [512, 1024, 2048, 2048, 256]],
+                  [256, 256], 20, 1),
     }
-    for tag, (nets, fl, image, ncls, B) in cases.items():
+    for tag, (ssds, nets, fl, image, ncls, B) in cases.items():
         L = len(fl[0])
         sizes = [[2.0, 2.828] for _ in range(L)]
         ratios = [[1, 2, 0.5] for _ in range(L)]
-        cfg, model = build(nets, fl, [list(s) for s in sizes], ratios, image, ncls)
+        cfg, model = build(nets, fl, [list(s) for s in sizes], ratios, image, ncls, ssds)
         ref_sd = model.state_dict()
         nb = [6] * L
-        shapes = synth.ssd_resnet_shapes(nets, fl, nb, ncls)
+        shapes = (synth.ssdfpn_resnet_shapes if ssds == "SSDFPN" else synth.ssd_resnet_shapes)(nets, fl, nb, ncls)
         assert [k for k, _ in shapes] == list(ref_sd.keys()), "state_dict key order differs"
         for k, s in shapes:
             assert tuple(ref_sd[k].shape) == tuple(s), (k, ref_sd[k].shape, s)
-        sd = synth.synthetic_state_dict(nets, fl, nb, ncls, seed=11, style="test")
+        sd = synth.synthetic_state_dict(nets, fl, nb, ncls, seed=11, style="test", ssds=ssds)
         model.load_state_dict(sd)
         model.eval()
         anchors = model_builder.create_anchors(cfg, model, image)

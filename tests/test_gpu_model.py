@@ -16,6 +16,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 CASES = {
+    "fpn50": ("ResNet50", [[3, 4, 5, "Conv:S", "Conv:S"], [512, 1024, 2048, 2048, 256]], 20, 2, [256, 256]),
     "r18": ("ResNet18", [[3, 4, 5, "Conv:S"], [128, 256, 512, 256]], 20, 3, [96, 160]),
     "r50": ("ResNet50", [[3, 4, 5, "Conv:S", "Conv:S", "Conv:S"], [512, 1024, 2048, 512, 256, 256]], 80, 1,
             [256, 256]),
@@ -34,16 +35,18 @@ def env():
 
 def build(tag, S):
     from ssds_pytorch_b200 import synth
-    from ssds_pytorch_b200.model import SSDResNet
+    from ssds_pytorch_b200.model import SSDResNet, SSDFPNResNet
     nets, fl, ncls, B, image = CASES[tag]
     L = len(fl[0])
-    sd = synth.synthetic_state_dict(nets, fl, [6] * L, ncls, seed=11, style="test")
+    fpn = tag.startswith("fpn")
+    sd = synth.synthetic_state_dict(nets, fl, [6] * L, ncls, seed=11, style="test",
+                                    ssds="SSDFPN" if fpn else "SSD")
     x = torch.rand((B, 3, image[0], image[1]), generator=torch.Generator().manual_seed(1234))
-    model = SSDResNet(sd, fl, ncls, [6] * L, device="cuda").eval()
+    model = (SSDFPNResNet if fpn else SSDResNet)(sd, fl, ncls, [6] * L, device="cuda").eval()
     return sd, fl, x, model, image, ncls
 
 
-@pytest.mark.parametrize("tag", ["r18", "r50"])
+@pytest.mark.parametrize("tag", ["r18", "r50", "fpn50"])
 def test_conv_stack_vs_oracle_bf16_policy(env, tag):
     from oracle import model_oracle as M
     sd, fl, x, model, image, ncls = build(tag, env)
@@ -51,7 +54,8 @@ def test_conv_stack_vs_oracle_bf16_policy(env, tag):
     torch.cuda.synchronize()
     sd_gpu = {k: v.cuda() for k, v in sd.items()}
     with torch.no_grad():
-        rloc, rconf = M.ssd_resnet_forward(sd_gpu, x.cuda(), fl, training=False, policy="bf16")
+        fwd = M.ssdfpn_resnet_forward if tag.startswith("fpn") else M.ssd_resnet_forward
+        rloc, rconf = fwd(sd_gpu, x.cuda(), fl, training=False, policy="bf16")
     worst_l = worst_c = 0.0
     for l, c, rl, rc in zip(loc, conf, rloc, rconf):
         assert l.shape == rl.shape and c.shape == rc.shape

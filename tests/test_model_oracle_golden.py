@@ -16,26 +16,29 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "model
 CASES = {
     "r50": ("ResNet50", [[3, 4, 5, "Conv:S", "Conv:S", "Conv:S"], [512, 1024, 2048, 512, 256, 256]], 80, 1),
     "r18": ("ResNet18", [[3, 4, 5, "Conv:S"], [128, 256, 512, 256]], 20, 3),
+    "fpn50": ("ResNet50", [[3, 4, 5, "Conv:S", "Conv:S"], [512, 1024, 2048, 2048, 256]], 20, 1),
 }
 
 
 def case_inputs(tag, gold):
     nets, fl, ncls, B = CASES[tag]
     L = len(fl[0])
-    sd = synth.synthetic_state_dict(nets, fl, [6] * L, ncls, seed=11, style="test")
+    sd = synth.synthetic_state_dict(nets, fl, [6] * L, ncls, seed=11, style="test",
+                                    ssds="SSDFPN" if tag.startswith("fpn") else "SSD")
     image = [int(v) for v in gold[tag + "_image"]]
     x = torch.rand((B, 3, image[0], image[1]), generator=torch.Generator().manual_seed(1234))
     return sd, fl, x, image, ncls
 
 
-@pytest.mark.parametrize("tag", ["r18", "r50"])
+@pytest.mark.parametrize("tag", ["r18", "r50", "fpn50"])
 def test_model_oracle_matches_reference_module(tag):
     gold = np.load(GOLD)
     sd, fl, x, image, ncls = case_inputs(tag, gold)
     np.testing.assert_array_equal(x.numpy().astype(np.float16), gold[tag + "_x"])
     torch.set_num_threads(8)
     with torch.no_grad():
-        loc, conf = M.ssd_resnet_forward(sd, x, fl, training=False, policy="fp32")
+        fwd = M.ssdfpn_resnet_forward if tag.startswith("fpn") else M.ssd_resnet_forward
+        loc, conf = fwd(sd, x, fl, training=False, policy="fp32")
     for i, (l, c) in enumerate(zip(loc, conf)):
         np.testing.assert_allclose(l.numpy(), gold[f"{tag}_loc{i}"], rtol=1e-4, atol=1e-5)
         np.testing.assert_allclose(c.numpy()[:, ::7], gold[f"{tag}_conf{i}"], rtol=1e-4, atol=1e-6)
