@@ -143,12 +143,13 @@ SSDSB_API int ssdsb_multibox_loss_sum(const float* d_logits /*[B,A,C,H,W]*/,
  * reference model graph (ssds/modeling/ssds/ssd.py:42-74, nets/resnet.py:41-56, torchvision
  * Bottleneck, layers/basic_layers.py:41-57), or a multibox head pair (ssd.py:100-103) + the eval
  * sigmoid (ssd.py:72-73).
- *   x : NHWC bf16, channel stride x_cstride (0 => Cin); Cin % 64 == 0, or Cin == 16 (the
- *       space-to-depth packed image of the 7x7/s2 stem, see ssdsb_pack_image_s2d).
+ *   x : NHWC bf16, channel stride x_cstride (0 => Cin); Cin % 16 == 0 (K-blocks of 64, 32 or 16
+ *       channels = 128/64/32-byte swizzle rows; Cin == 16 is also the space-to-depth packed image of
+ *       the stride-2 stems, see ssdsb_pack_image_s2d).
  *   w : bf16 [w_rows >= Cout][KH*KW][Cin], BN scale folded in; bias fp32 [Cout] (folded BN shift
  *       or the conv bias).
  *   out_mode 0 : y = NHWC bf16 [N,Ho,Wo,out_cstride], optional residual (same layout, res_cstride)
- *                and ReLU.  Cout % 32 == 0.
+ *                and activation (relu: 0 none, 1 ReLU, 2 ReLU6).  Cout % 32 == 0.
  *   out_mode 1 : multibox head: output channels [0,n_loc) -> y  = fp32 NCHW [N,n_loc,Ho,Wo] (loc),
  *                [n_loc,Cout) -> y2 = fp32 NCHW [N,Cout-n_loc,Ho,Wo] (conf), sigmoid-ed if `sigmoid`.
  *   Ho/Wo: 0 => (H + 2*pad - KH)/stride + 1; pad is the top/left padding, the bottom/right halo is
@@ -193,6 +194,13 @@ SSDSB_API int ssdsb_pack_image_s2d(const void* d_src, int src_format, int N, int
 /* 3x3 / stride 2 / pad 1 max pooling on NHWC bf16 (resnet.py:45 `self.maxpool`). C % 8 == 0. */
 SSDSB_API int ssdsb_maxpool3x3s2_nhwc_bf16(const void* d_x, int N, int H, int W, int C, void* d_y,
                                            void* stream);
+
+/* Depthwise 3x3 / pad 1 / stride 1|2 conv + folded BN + activation (relu: 0 none, 1 ReLU, 2 ReLU6) on
+ * NHWC bf16 — torchvision InvertedResidual's depthwise stage (reference nets/mobilenet.py:78) and
+ * SepConvBNReLU (layers/basic_layers.py:5-24).  w: bf16 [9][C] (tap-major), bias fp32 [C], C % 8 == 0. */
+SSDSB_API int ssdsb_dwconv3x3_nhwc_bf16(const void* d_x, const void* d_w, const float* d_bias, int N,
+                                        int H, int W, int C, int stride, int relu, void* d_y,
+                                        void* stream);
 
 /* FPN top-down merge (ssds/modeling/ssds/fpn.py:80-87): fine[n,h,w,:] += coarse[n,h/2,w/2,:]
  * (nearest 2x upsample + add), NHWC bf16, in place on `fine` ([N,H,W,C]; coarse is [N,H/2,W/2,C]). */

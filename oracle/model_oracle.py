@@ -26,7 +26,8 @@ def _r(t, policy):
     return t.to(torch.bfloat16).float() if policy == "bf16" else t
 
 
-def _conv_bn(x, sd, wkey, bnkey, stride, pad, relu, policy, residual=None, bias=None):
+def _conv_bn(x, sd, wkey, bnkey, stride, pad, relu, policy, residual=None, bias=None, groups=1):
+    """relu: False none, True ReLU, 6 ReLU6."""
     w = sd[wkey].float()
     if policy == "bf16":
         b = bias.float() if bias is not None else torch.zeros(w.shape[0], device=w.device)
@@ -34,9 +35,9 @@ def _conv_bn(x, sd, wkey, bnkey, stride, pad, relu, policy, residual=None, bias=
             scale = sd[bnkey + ".weight"].float() / torch.sqrt(sd[bnkey + ".running_var"].float() + EPS)
             w = w * scale.view(-1, 1, 1, 1)
             b = (b - sd[bnkey + ".running_mean"].float()) * scale + sd[bnkey + ".bias"].float()
-        y = F.conv2d(x, _r(w, policy), b, stride=stride, padding=pad)
+        y = F.conv2d(x, _r(w, policy), b, stride=stride, padding=pad, groups=groups)
     else:
-        y = F.conv2d(x, w, bias, stride=stride, padding=pad)
+        y = F.conv2d(x, w, bias, stride=stride, padding=pad, groups=groups)
         if bnkey is not None:
             y = F.batch_norm(y, sd[bnkey + ".running_mean"], sd[bnkey + ".running_var"],
                              sd[bnkey + ".weight"], sd[bnkey + ".bias"], False, 0.0, EPS)
@@ -44,7 +45,39 @@ def _conv_bn(x, sd, wkey, bnkey, stride, pad, relu, policy, residual=None, bias=
         y = y + residual
     if relu:
         y = F.relu(y)
+    if relu == 6:
+        y = y.clamp(max=6.0)
     return y
+
+
+MBV2_SETTINGS = [[1, 16, 1, 1], [6, 24, 2, 2], [6, 32, 3, 2], [6, 64, 4, 2], [6, 96, 3, 1], [6, 160, 3, 2],
+                 [6, 320, 1, 1]]
+
+
+def mobilenetv2_features(sd, x, outputs, policy):
+    """reference mobilenet.py:180-192 (MobileNetEx.forward, v2) with torchvision InvertedResidual."""
+    x = _r(x.float(), policy)
+    x = _r(_conv_bn(x, sd, "backbone.conv1.0.weight", "backbone.conv1.1", 2, 1, 6, policy), policy)
+    feats = []
+    inp = 32
+    for j, (t, c, n, s_) in enumerate(MBV2_SETTINGS, start=1):
+        if j > max(outputs):
+            break
+        for i in range(n):
+            p = f"backbone.layer{j}.{i}.conv"
+            stride = s_ if i == 0 else 1
+            hid = inp * t
+            y, k = x, 0
+            if t != 1:
+                y = _r(_conv_bn(y, sd, f"{p}.0.0.weight", f"{p}.0.1", 1, 0, 6, policy), policy)
+                k = 1
+            y = _r(_conv_bn(y, sd, f"{p}.{k}.0.weight", f"{p}.{k}.1", stride, 1, 6, policy, groups=hid), policy)
+            res = x if (stride == 1 and inp == c) else None
+            x = _r(_conv_bn(y, sd, f"{p}.{k + 1}.weight", f"{p}.{k + 2}", 1, 0, False, policy, residual=res), policy)
+            inp = c
+        if j in outputs:
+            feats.append(x)
+    return feats
 
 
 def resnet_features(sd, x, outputs, policy):
@@ -77,10 +110,10 @@ def resnet_features(sd, x, outputs, policy):
     return feats
 
 
-def ssd_resnet_forward(sd, x, feature_layer, training=False, policy="fp32"):
+def ssd_resnet_forward(sd, x, feature_layer, training=False, policy="fp32", backbone="resnet"):
     """x fp32 NCHW (already normalised).  Returns (tuple loc, tuple conf) like ssd.py:42-74."""
     outputs = [l for l in feature_layer[0] if isinstance(l, int)]
-    feats = resnet_features(sd, x, outputs, policy)
+    feats = (mobilenetv2_features if backbone == "mobilenetv2" else resnet_features)(sd, x, outputs, policy)
     ei = 0
     for layer in feature_layer[0]:
         if isinstance(layer, int):
@@ -132,3 +165,8 @@ def ssdfpn_resnet_forward(sd, x, feature_layer, training=False, policy="fp32"):
         loc.append(outs[0])
         conf.append(outs[1] if training else torch.sigmoid(outs[1]))
     return tuple(loc), tuple(conf)
+
+
+def ssd_mobilenetv2_forward(sd, x, feature_layer, training=False, policy="fp32"):
+    """SSD.forward (ssd.py:42-74) over the MobileNetV2 backbone."""
+    return ssd_resnet_forward(sd, x, feature_layer, training, policy, backbone="mobilenetv2")

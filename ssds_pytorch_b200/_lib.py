@@ -64,6 +64,7 @@ def _load():
         "ssdsb_pack_image_s2d": (i, [vp, i, i, i, i, f, f, i, i, vp, vp]),
         "ssdsb_maxpool3x3s2_nhwc_bf16": (i, [vp, i, i, i, i, vp, vp]),
         "ssdsb_upsample2x_add_nhwc_bf16": (i, [vp, vp, i, i, i, i, vp]),
+        "ssdsb_dwconv3x3_nhwc_bf16": (i, [vp, vp, vp, i, i, i, i, i, i, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)          # AttributeError if the .so does not export it

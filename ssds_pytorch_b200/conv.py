@@ -34,22 +34,24 @@ def pack_weight(w_folded, cin_pad=None):
     return out.to(torch.bfloat16).contiguous()
 
 
-def pack_stem_weight_s2d(w_folded):
-    """7x7/s2/p3 stem [Cout,3,7,7] -> the equivalent 4x4/s1 kernel on the 2x2 space-to-depth image:
-    bf16 [Cout, 16 taps, 16 ch], channel (a*2+b)*3+c, W'[kh',kw',a,b,c] = W[c, 2kh'+a-1, 2kw'+b-1]
-    (zero where the index is -1); s2d row = ho - 2 + kh'."""
-    cout = w_folded.shape[0]
-    assert tuple(w_folded.shape[1:]) == (3, 7, 7)
+def pack_stem_weight_s2d(w_folded, pad=None):
+    """Stride-2 RGB stem [Cout,3,k,k] (7x7/p3 ResNet, 3x3/p1 MobileNet) -> the equivalent 4x4/s1 kernel
+    on the 2x2 space-to-depth image: bf16 [Cout, 16 taps, 16 ch], channel (a*2+b)*3+c.
+    Output row ho reads original rows 2ho-p+r = s2d row ho-2+kh', sub-row a  =>  r = 2(kh'-2)+a+p
+    (zero weight where r falls outside the kernel)."""
+    cout, _, k, _ = w_folded.shape
+    pad = (k - 1) // 2 if pad is None else pad
+    assert w_folded.shape[1] == 3 and k <= 7 and pad <= 3
     out = torch.zeros((cout, 4, 4, 16), dtype=torch.float32)
     for khp in range(4):
         for a in range(2):
-            r = 2 * khp + a - 1
-            if r < 0:
+            r = 2 * (khp - 2) + a + pad
+            if r < 0 or r >= k:
                 continue
             for kwp in range(4):
                 for b in range(2):
-                    s = 2 * kwp + b - 1
-                    if s < 0:
+                    s = 2 * (kwp - 2) + b + pad
+                    if s < 0 or s >= k:
                         continue
                     for c in range(3):
                         out[:, khp, kwp, (a * 2 + b) * 3 + c] = w_folded[:, c, r, s]
@@ -149,3 +151,24 @@ def upsample2x_add(coarse, fine):
         check(lib.ssdsb_upsample2x_add_nhwc_bf16(ptr(coarse), ptr(fine), N, H, W, Cc, stream_ptr()),
               "upsample2x_add")
     return fine
+
+
+def pack_dw_weight(w_folded, c_pad=None):
+    """depthwise [C,1,3,3] fp32 -> bf16 [9, C_pad] (tap-major)."""
+    c = w_folded.shape[0]
+    c_pad = c_pad or c
+    out = torch.zeros((9, c_pad), dtype=torch.float32)
+    out[:, :c] = w_folded.reshape(c, 9).t()
+    return out.to(torch.bfloat16).contiguous()
+
+
+def dwconv3x3(x, w, bias, stride=1, relu=2, out=None):
+    """NHWC bf16 depthwise 3x3/pad 1 + bias + activation (0 none, 1 ReLU, 2 ReLU6)."""
+    N, H, W, Cc = x.shape
+    ho, wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    if out is None:
+        out = torch.empty((N, ho, wo, Cc), dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib.ssdsb_dwconv3x3_nhwc_bf16(ptr(x), ptr(w), ptr(bias), N, H, W, Cc, stride, int(relu),
+                                            ptr(out), stream_ptr()), "dwconv3x3")
+    return out

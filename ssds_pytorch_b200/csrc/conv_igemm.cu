@@ -163,16 +163,16 @@ __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// K-major swizzled operand tile: rows of ROW_BYTES (= swizzle span: 128 or 32), 8-row groups
+// K-major swizzled operand tile: rows of ROW_BYTES (= swizzle span: 128, 64 or 32), 8-row groups
 // 8*ROW_BYTES apart; one swizzle atom along K, so the leading-dimension offset is unused.
 template <int ROW_BYTES>
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
-  static_assert(ROW_BYTES == 128 || ROW_BYTES == 32, "unsupported swizzle span");
+  static_assert(ROW_BYTES == 128 || ROW_BYTES == 64 || ROW_BYTES == 32, "unsupported swizzle span");
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3ffffu) >> 4);          // start address        bits [0,14)
   d |= (uint64_t)((8u * ROW_BYTES) >> 4) << 32;          // stride byte offset   bits [32,46)
   d |= (uint64_t)1 << 46;                                // descriptor version (Blackwell)
-  d |= (uint64_t)(ROW_BYTES == 128 ? 2 : 6) << 61;       // SWIZZLE_128B / SWIZZLE_32B
+  d |= (uint64_t)(ROW_BYTES == 128 ? 2 : (ROW_BYTES == 64 ? 4 : 6)) << 61;  // SWIZZLE_128B / _64B / _32B
   return d;
 }
 // kind::f16 instruction descriptor: bf16 x bf16 -> f32, both operands K-major
@@ -484,6 +484,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               if (p.relu) {
 #pragma unroll
                 for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.0f);
+                if (p.relu == 2) {             // ReLU6 (MobileNetV2)
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) f[e] = fminf(f[e], 6.0f);
+                }
               }
               uint4 o;
               o.x = pack_bf16(f[0], f[1]);
@@ -529,6 +533,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               if (p.relu) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+                if (p.relu == 2) {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) f[j] = fminf(f[j], 6.0f);
+                }
               }
               uint4* yp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.y) +
                                                    pix * p.out_cstride + col0);
@@ -687,7 +695,8 @@ extern "C" int ssdsb_conv2d_bf16(const ssdsb_conv_desc* d, const void* x, const 
   const int Wo = d->Wo > 0 ? d->Wo : (d->W + 2 * d->pad - d->KW) / d->stride + 1;
   SSDSB_REQUIRE(Ho >= 1 && Wo >= 1, "conv2d: empty output");
   const bool windowed = d->x_kind == SSDSB_CONV_X_WINDOWED_STEM;
-  const int block_k = (d->Cin == 16 && !windowed) ? 16 : 64;
+  // K-block = one swizzle row of channels: 64 (128B) when Cin allows it, else 32 (64B), else 16 (32B)
+  const int block_k = windowed ? 64 : (d->Cin % 64 == 0 ? 64 : (d->Cin % 32 == 0 ? 32 : 16));
   const int cs = d->x_cstride ? d->x_cstride : d->Cin;
   const int row_px = d->x_row_pixels ? d->x_row_pixels : d->W;
   if (windowed) {
@@ -695,7 +704,7 @@ extern "C" int ssdsb_conv2d_bf16(const ssdsb_conv_desc* d, const void* x, const 
                   "conv2d: the windowed stem needs Cin=16, 4x4/s1/p2 on a packed s2d image");
     SSDSB_REQUIRE(row_px >= d->W + 3, "conv2d: windowed stem rows need >= W+3 pixels (2 left + 1 right pad)");
   } else {
-    SSDSB_REQUIRE(d->Cin % block_k == 0, "conv2d: Cin=%d must be 16 or a multiple of 64", d->Cin);
+    SSDSB_REQUIRE(d->Cin % block_k == 0, "conv2d: Cin=%d must be a multiple of 16", d->Cin);
     SSDSB_REQUIRE(row_px >= d->W, "conv2d: x_row_pixels < W");
   }
   SSDSB_REQUIRE(cs >= d->Cin && cs % 8 == 0, "conv2d: bad input channel stride %d", cs);
@@ -762,7 +771,8 @@ extern "C" int ssdsb_conv2d_bf16(const ssdsb_conv_desc* d, const void* x, const 
   kp.y = y; kp.y2 = y2;
 
   // ---- tensor maps ------------------------------------------------------------------------------
-  const CUtensorMapSwizzle swz = block_k == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B;
+  const CUtensorMapSwizzle swz = block_k == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                 : (block_k == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   alignas(64) CUtensorMap tmA;
   alignas(64) CUtensorMap tmB;
   alignas(64) CUtensorMap tmY;
@@ -840,6 +850,13 @@ extern "C" int ssdsb_conv2d_bf16(const ssdsb_conv_desc* d, const void* x, const 
       case 64: return launch<64, 16>(tmA, tmB, tmY, tmR, kp, want_staging, sms, st);
       case 128: return launch<128, 16>(tmA, tmB, tmY, tmR, kp, want_staging, sms, st);
       default: return launch<256, 16>(tmA, tmB, tmY, tmR, kp, want_staging, sms, st);
+    }
+  }
+  if (block_k == 32) {
+    switch (block_n) {
+      case 64: return launch<64, 32>(tmA, tmB, tmY, tmR, kp, want_staging, sms, st);
+      case 128: return launch<128, 32>(tmA, tmB, tmY, tmR, kp, want_staging, sms, st);
+      default: return launch<256, 32>(tmA, tmB, tmY, tmR, kp, want_staging, sms, st);
     }
   }
   switch (block_n) {

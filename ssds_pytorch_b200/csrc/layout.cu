@@ -120,10 +120,80 @@ upsample2x_add_kernel(const uint4* __restrict__ coarse, uint4* __restrict__ fine
   }
 }
 
+// Depthwise 3x3 (pad 1, stride 1|2) + folded BN + ReLU/ReLU6 on NHWC bf16 (torchvision
+// InvertedResidual / reference SepConvBNReLU).  One thread = one output pixel x 8 channels: nine
+// 16-byte input loads (neighbouring threads hit the same lines in L1/L2), bf16 weights [9][C],
+// fp32 bias [C], fp32 accumulation.  HBM-bound: in + out bytes.
+__global__ void __launch_bounds__(256)
+dwconv3x3_kernel(const uint4* __restrict__ x, const uint4* __restrict__ w, const float* __restrict__ bias,
+                 int N, int H, int W, int C8, int stride, int Ho, int Wo, int relu, uint4* __restrict__ y) {
+  const size_t total = (size_t)N * Ho * Wo * C8;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C8);
+    const int wo = (int)((i / C8) % Wo);
+    const int ho = (int)((i / ((size_t)C8 * Wo)) % Ho);
+    const int n = (int)(i / ((size_t)C8 * Wo * Ho));
+    float acc[8];
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias) + c * 2);
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias) + c * 2 + 1);
+    acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w;
+    acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      const int h = ho * stride - 1 + dy;
+      if (h < 0 || h >= H) continue;
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const int ww = wo * stride - 1 + dx;
+        if (ww < 0 || ww >= W) continue;
+        const uint4 xv = __ldg(x + (((size_t)n * H + h) * W + ww) * C8 + c);
+        const uint4 wv = __ldg(w + (size_t)(dy * 3 + dx) * C8 + c);
+        const uint32_t xs[4] = {xv.x, xv.y, xv.z, xv.w}, ws[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          acc[e * 2 + 0] += __uint_as_float(xs[e] << 16) * __uint_as_float(ws[e] << 16);
+          acc[e * 2 + 1] += __uint_as_float(xs[e] & 0xffff0000u) * __uint_as_float(ws[e] & 0xffff0000u);
+        }
+      }
+    }
+    if (relu) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = fmaxf(acc[e], 0.0f);
+      if (relu == 2) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = fminf(acc[e], 6.0f);
+      }
+    }
+    y[i] = make_uint4(pack2(acc[0], acc[1]), pack2(acc[2], acc[3]), pack2(acc[4], acc[5]),
+                      pack2(acc[6], acc[7]));
+  }
+}
+
 }  // namespace
 }  // namespace ssdsb
 
 using namespace ssdsb;
+
+extern "C" int ssdsb_dwconv3x3_nhwc_bf16(const void* d_x, const void* d_w, const float* d_bias, int N,
+                                         int H, int W, int C, int stride, int relu, void* d_y,
+                                         void* stream) {
+  SSDSB_REQUIRE(d_x && d_w && d_bias && d_y, "dwconv3x3: NULL argument");
+  SSDSB_REQUIRE(N >= 1 && H >= 1 && W >= 1 && C >= 8 && C % 8 == 0, "dwconv3x3: bad shape");
+  SSDSB_REQUIRE(stride == 1 || stride == 2, "dwconv3x3: stride=%d", stride);
+  SSDSB_REQUIRE(relu >= 0 && relu <= 2, "dwconv3x3: relu=%d (0 none, 1 ReLU, 2 ReLU6)", relu);
+  SSDSB_REQUIRE((((uintptr_t)d_x | (uintptr_t)d_w | (uintptr_t)d_y | (uintptr_t)d_bias) & 15) == 0,
+                "dwconv3x3: pointers must be 16-byte aligned");
+  const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
+  const size_t total = (size_t)N * Ho * Wo * (C / 8);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  dwconv3x3_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const uint4*>(d_x), reinterpret_cast<const uint4*>(d_w), d_bias, N, H, W, C / 8,
+      stride, Ho, Wo, relu, reinterpret_cast<uint4*>(d_y));
+  SSDSB_LAUNCH_CHECK("dwconv3x3_kernel");
+  return SSDSB_OK;
+}
 
 extern "C" int ssdsb_upsample2x_add_nhwc_bf16(const void* d_coarse, void* d_fine, int N, int H, int W,
                                               int C, void* stream) {

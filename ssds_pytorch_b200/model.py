@@ -29,21 +29,47 @@ def _bn(sd, prefix):
             sd[prefix + ".running_var"], BN_EPS)
 
 
-class _Conv:
-    """One packed conv: bf16 weights [Cout, taps, Cin] + fp32 bias on the device."""
+def _cpad(c, m=32):
+    return (c + m - 1) // m * m
 
-    def __init__(self, weight, bn, bias, stride, pad, relu, device, stem=False):
+
+class _Conv:
+    """One packed conv: bf16 weights [Cout_pad, taps, Cin_pad] + fp32 bias on the device.
+    relu: False/0 none, True/1 ReLU, 2 ReLU6.  cin_pad / cout_pad add zero channels so that every
+    activation tensor has a channel count the K-block (and the 32-column epilogue) can address."""
+
+    def __init__(self, weight, bn, bias, stride, pad, relu, device, stem=False, cin_pad=None,
+                 cout_pad=None):
         w, b = K.fold_bn(weight, bn, bias)
         self.KH, self.KW = (4, 4) if stem else (weight.shape[2], weight.shape[3])
-        self.stride, self.pad, self.relu = (1, 2, relu) if stem else (stride, pad, relu)
-        self.w = (K.pack_stem_weight_s2d(w) if stem else K.pack_weight(w)).to(device)
+        self.stride, self.pad, self.relu = (1, 2, int(relu)) if stem else (stride, pad, int(relu))
+        cout = weight.shape[0]
+        self.cout = cout_pad or cout
+        wp = K.pack_stem_weight_s2d(w) if stem else K.pack_weight(w, cin_pad)
+        if self.cout != cout:
+            wp = torch.cat([wp, torch.zeros((self.cout - cout,) + tuple(wp.shape[1:]), dtype=wp.dtype)], 0)
+            b = torch.cat([b, torch.zeros(self.cout - cout)], 0)
+        self.w = wp.contiguous().to(device)
         self.bias = b.contiguous().to(device)
-        self.cout = weight.shape[0]
-        self.flops_per_pixel = 2 * weight[0].numel() * self.cout   # algorithmic (un-padded) FLOPs
+        self.flops_per_pixel = 2 * weight[0].numel() * cout        # algorithmic (un-padded) FLOPs
 
 
-class _ResNetEngine(torch.nn.Module):
-    """Shared machinery: packed ResNet backbone, plan recording (static buffers), CUDA-graph replay."""
+class _DwConv:
+    """Depthwise 3x3 + folded BN + activation: bf16 weights [9, C_pad], fp32 bias."""
+
+    def __init__(self, weight, bn, stride, relu, device, c_pad=None):
+        w, b = K.fold_bn(weight, bn, None)
+        c = weight.shape[0]
+        self.c = c_pad or c
+        self.stride, self.relu = stride, int(relu)
+        self.w = K.pack_dw_weight(w, self.c).to(device)
+        self.bias = torch.cat([b, torch.zeros(self.c - c)], 0).contiguous().to(device)
+        self.flops_per_pixel = 2 * 9 * c
+
+
+class _Engine(torch.nn.Module):
+    """Shared machinery: plan recording (static buffers), CUDA-graph replay.  Subclasses provide a
+    backbone (`_build_backbone`, `_plan_backbone`) and a neck (`_build_neck`, `_plan_neck`)."""
 
     def __init__(self, state_dict, feature_layer, num_classes, number_box, device="cuda",
                  mean=0.0, std=1.0):
@@ -58,41 +84,6 @@ class _ResNetEngine(torch.nn.Module):
         self._build_backbone(sd, feature_layer)
         self._build_neck(sd, feature_layer)
 
-    def _build_backbone(self, sd, feature_layer):
-        dev = self.device
-
-        self.stem = _Conv(sd["backbone.conv1.weight"], _bn(sd, "backbone.bn1"), None, 2, 3, True, dev,
-                          stem=True)
-        # backbone levels: level = layer index + 1 (resnet.py:48-54)
-        self.outputs = [l for l in feature_layer[0] if isinstance(l, int)]
-        self.layers = []
-        for li in range(1, 5):
-            if li + 1 > max(self.outputs):
-                break
-            blocks = []
-            bi = 0
-            while f"backbone.layer{li}.{bi}.conv1.weight" in sd:
-                p = f"backbone.layer{li}.{bi}"
-                bottleneck = (p + ".conv3.weight") in sd
-                stride = 2 if (li > 1 and bi == 0) else 1
-                blk = {}
-                if bottleneck:
-                    blk["convs"] = [
-                        _Conv(sd[p + ".conv1.weight"], _bn(sd, p + ".bn1"), None, 1, 0, True, dev),
-                        _Conv(sd[p + ".conv2.weight"], _bn(sd, p + ".bn2"), None, stride, 1, True, dev),
-                        _Conv(sd[p + ".conv3.weight"], _bn(sd, p + ".bn3"), None, 1, 0, True, dev),
-                    ]
-                else:
-                    blk["convs"] = [
-                        _Conv(sd[p + ".conv1.weight"], _bn(sd, p + ".bn1"), None, stride, 1, True, dev),
-                        _Conv(sd[p + ".conv2.weight"], _bn(sd, p + ".bn2"), None, 1, 1, True, dev),
-                    ]
-                if (p + ".downsample.0.weight") in sd:
-                    blk["down"] = _Conv(sd[p + ".downsample.0.weight"], _bn(sd, p + ".downsample.1"),
-                                        None, stride, 0, False, dev)
-                blocks.append(blk)
-                bi += 1
-            self.layers.append(blocks)
 
     # ------------------------------------------------------------------ plan (static buffers)
     def _build_plan(self, images):
@@ -140,21 +131,15 @@ class _ResNetEngine(torch.nn.Module):
             flops[0] += h.flops_per_pixel * n * fh * fw
             return loc, conf
 
-        x = add_conv(self.stem, packed, Ho=H // 2, Wo=W // 2, x_kind=1, x_width=W // 2)
-        pooled = buf(N, (x.shape[1] - 1) // 2 + 1, (x.shape[2] - 1) // 2 + 1, x.shape[3])
-        xs = x
-        steps.append(lambda: K.maxpool3x3s2(xs, out=pooled))
-        x = pooled
-        feats = []
-        for li, blocks in enumerate(self.layers):
-            for blk in blocks:
-                identity = add_conv(blk["down"], x) if "down" in blk else x
-                y = x
-                for cv in blk["convs"][:-1]:
-                    y = add_conv(cv, y)
-                x = add_conv(blk["convs"][-1], y, residual=identity, relu=True)
-            if li + 2 in self.outputs:
-                feats.append(x)
+        def add_dw(dw, x):
+            n, h, w, c = x.shape
+            ho, wo = (h - 1) // dw.stride + 1, (w - 1) // dw.stride + 1
+            y = buf(n, ho, wo, c)
+            steps.append(lambda: K.dwconv3x3(x, dw.w, dw.bias, dw.stride, dw.relu, out=y))
+            flops[0] += dw.flops_per_pixel * n * ho * wo
+            return y
+
+        feats = self._plan_backbone(packed, H, W, steps, buf, add_conv, add_dw)
         locs, confs = self._plan_neck(feats, steps, buf, add_conv, add_head)
         return {"src": src, "steps": steps, "loc": tuple(locs), "conf": tuple(confs),
                 "flops": flops[0], "graph": None, "launches": len(steps)}
@@ -202,9 +187,117 @@ class _ResNetEngine(torch.nn.Module):
         return self
 
 
-class SSDResNet(_ResNetEngine):
-    """B200 engine for SSD over a torchvision-style ResNet backbone (reference cfg: SSDS='SSD',
-    NETS='ResNet18/34/50/101/152'; ssd.py:42-104)."""
+class _ResNetBackbone:
+    """torchvision-style ResNet under `backbone.` (reference nets/resnet.py:9-56)."""
+
+    def _build_backbone(self, sd, feature_layer):
+        dev = self.device
+        self.stem = _Conv(sd["backbone.conv1.weight"], _bn(sd, "backbone.bn1"), None, 2, 3, True, dev,
+                          stem=True)
+        # backbone levels: level = layer index + 1 (resnet.py:48-54)
+        self.outputs = [l for l in feature_layer[0] if isinstance(l, int)]
+        self.layers = []
+        for li in range(1, 5):
+            if li + 1 > max(self.outputs):
+                break
+            blocks = []
+            bi = 0
+            while f"backbone.layer{li}.{bi}.conv1.weight" in sd:
+                p = f"backbone.layer{li}.{bi}"
+                bottleneck = (p + ".conv3.weight") in sd
+                stride = 2 if (li > 1 and bi == 0) else 1
+                blk = {}
+                if bottleneck:
+                    blk["convs"] = [
+                        _Conv(sd[p + ".conv1.weight"], _bn(sd, p + ".bn1"), None, 1, 0, True, dev),
+                        _Conv(sd[p + ".conv2.weight"], _bn(sd, p + ".bn2"), None, stride, 1, True, dev),
+                        _Conv(sd[p + ".conv3.weight"], _bn(sd, p + ".bn3"), None, 1, 0, True, dev),
+                    ]
+                else:
+                    blk["convs"] = [
+                        _Conv(sd[p + ".conv1.weight"], _bn(sd, p + ".bn1"), None, stride, 1, True, dev),
+                        _Conv(sd[p + ".conv2.weight"], _bn(sd, p + ".bn2"), None, 1, 1, True, dev),
+                    ]
+                if (p + ".downsample.0.weight") in sd:
+                    blk["down"] = _Conv(sd[p + ".downsample.0.weight"], _bn(sd, p + ".downsample.1"),
+                                        None, stride, 0, False, dev)
+                blocks.append(blk)
+                bi += 1
+            self.layers.append(blocks)
+
+    def _plan_backbone(self, packed, H, W, steps, buf, add_conv, add_dw):
+        x = add_conv(self.stem, packed, Ho=H // 2, Wo=W // 2, x_kind=1, x_width=W // 2)
+        N = x.shape[0]
+        pooled = buf(N, (x.shape[1] - 1) // 2 + 1, (x.shape[2] - 1) // 2 + 1, x.shape[3])
+        xs = x
+        steps.append(lambda: K.maxpool3x3s2(xs, out=pooled))
+        x = pooled
+        feats = []
+        for li, blocks in enumerate(self.layers):
+            for blk in blocks:
+                identity = add_conv(blk["down"], x) if "down" in blk else x
+                y = x
+                for cv in blk["convs"][:-1]:
+                    y = add_conv(cv, y)
+                x = add_conv(blk["convs"][-1], y, residual=identity, relu=True)
+            if li + 2 in self.outputs:
+                feats.append(x)
+        return feats
+
+
+class _MobileNetV2Backbone:
+    """MobileNetV2 under `backbone.` (reference nets/mobilenet.py:40-212, torchvision InvertedResidual:
+    [1x1 expand + ReLU6] -> 3x3 depthwise + ReLU6 -> 1x1 linear project [+ residual]).
+    Every activation tensor is stored with its channels zero-padded to a multiple of 32
+    (16, 24 -> 32; 144 -> 160) so the 64-byte K-block / 32-column epilogue can address it."""
+    SETTINGS = [[1, 16, 1, 1], [6, 24, 2, 2], [6, 32, 3, 2], [6, 64, 4, 2], [6, 96, 3, 1], [6, 160, 3, 2],
+                [6, 320, 1, 1]]
+
+    def _build_backbone(self, sd, feature_layer):
+        dev = self.device
+        self.outputs = [l for l in feature_layer[0] if isinstance(l, int)]
+        self.stem = _Conv(sd["backbone.conv1.0.weight"], _bn(sd, "backbone.conv1.1"), None, 2, 1, 2, dev,
+                          stem=True)
+        self.layers = []
+        inp = 32
+        for j, (t, c, n, s_) in enumerate(self.SETTINGS, start=1):
+            if j > max(self.outputs):
+                break
+            blocks = []
+            for i in range(n):
+                p = f"backbone.layer{j}.{i}.conv"
+                stride = s_ if i == 0 else 1
+                hid = inp * t
+                blk = {"res": stride == 1 and inp == c}
+                k = 0
+                if t != 1:
+                    blk["expand"] = _Conv(sd[f"{p}.0.0.weight"], _bn(sd, f"{p}.0.1"), None, 1, 0, 2, dev,
+                                          cin_pad=_cpad(inp), cout_pad=_cpad(hid))
+                    k = 1
+                blk["dw"] = _DwConv(sd[f"{p}.{k}.0.weight"], _bn(sd, f"{p}.{k}.1"), stride, 2, dev,
+                                    c_pad=_cpad(hid))
+                blk["project"] = _Conv(sd[f"{p}.{k + 1}.weight"], _bn(sd, f"{p}.{k + 2}"), None, 1, 0, 0, dev,
+                                       cin_pad=_cpad(hid), cout_pad=_cpad(c))
+                blocks.append(blk)
+                inp = c
+            self.layers.append(blocks)
+
+    def _plan_backbone(self, packed, H, W, steps, buf, add_conv, add_dw):
+        x = add_conv(self.stem, packed, Ho=H // 2, Wo=W // 2, x_kind=1, x_width=W // 2)
+        feats = []
+        for j, blocks in enumerate(self.layers, start=1):
+            for blk in blocks:
+                y = add_conv(blk["expand"], x) if "expand" in blk else x
+                y = add_dw(blk["dw"], y)
+                x = add_conv(blk["project"], y, residual=x if blk["res"] else None)
+            if j in self.outputs:
+                feats.append(x)
+        return feats
+
+
+class _SSDNeck:
+    """SSD extras (ConvBNReLUx2, layers_parser.py:17-20) + per-level fused loc/conf heads
+    (ssd.py:42-104).  Input channel counts may be padded (see _MobileNetV2Backbone)."""
 
     def _build_neck(self, sd, feature_layer):
         dev = self.device
@@ -219,7 +312,8 @@ class SSDResNet(_ResNetEngine):
             stride = 2 if layer == "Conv:S" else 1
             p = f"extras.{ei}"
             self.extras.append([
-                _Conv(sd[p + ".0.weight"], _bn(sd, p + ".1"), None, 1, 0, True, dev),
+                _Conv(sd[p + ".0.weight"], _bn(sd, p + ".1"), None, 1, 0, True, dev,
+                      cin_pad=_cpad(sd[p + ".0.weight"].shape[1])),
                 _Conv(sd[p + ".3.weight"], _bn(sd, p + ".4"), None, stride, 1, True, dev),
             ])
             ei += 1
@@ -228,7 +322,7 @@ class SSDResNet(_ResNetEngine):
         for l, nb in enumerate(self.number_box):
             w = torch.cat([sd[f"loc.{l}.weight"], sd[f"conf.{l}.weight"]], 0)
             b = torch.cat([sd[f"loc.{l}.bias"], sd[f"conf.{l}.bias"]], 0)
-            h = _Conv(w, None, b, 1, 1, False, dev)
+            h = _Conv(w, None, b, 1, 1, False, dev, cin_pad=_cpad(w.shape[1]))
             h.n_loc = nb * 4
             self.heads.append(h)
 
@@ -247,7 +341,7 @@ class SSDResNet(_ResNetEngine):
         return locs, confs
 
 
-class SSDFPNResNet(_ResNetEngine):
+class _FPNNeck:
     """B200 engine for SSDFPN / RetinaNet over ResNet (reference cfg: SSDS='SSDFPN'; fpn.py:58-146).
 
     transforms: 1x1 lateral convs with bias (no BN/ReLU); top-down nearest-2x upsample + add
@@ -321,6 +415,30 @@ class SSDFPNResNet(_ResNetEngine):
             locs.append(loc)
             confs.append(conf)
         return locs, confs
+
+
+class SSDResNet(_SSDNeck, _ResNetBackbone, _Engine):
+    """SSD + ResNet18/34/50/101/152 (reference cfg SSDS='SSD', NETS='ResNet*')."""
+
+
+class SSDFPNResNet(_FPNNeck, _ResNetBackbone, _Engine):
+    """SSDFPN (RetinaNet) + ResNet (reference cfg SSDS='SSDFPN', NETS='ResNet*')."""
+
+
+class SSDMobileNetV2(_SSDNeck, _MobileNetV2Backbone, _Engine):
+    """SSD + MobileNetV2 (reference cfg SSDS='SSD', NETS='MobileNetV2'; BASELINE configs[0]/[2])."""
+
+
+ENGINES = {("SSD", "ResNet"): SSDResNet, ("SSDFPN", "ResNet"): SSDFPNResNet,
+           ("SSD", "MobileNetV2"): SSDMobileNetV2}
+
+
+def engine_for(ssds, nets):
+    key = (ssds.upper(), "ResNet" if nets.startswith("ResNet") else nets)
+    if key not in ENGINES:
+        raise NotImplementedError(f"SSDS={ssds!r} / NETS={nets!r} is not on the tcgen05 conv stack yet "
+                                  f"(have: {sorted(ENGINES)})")
+    return ENGINES[key]
 
 
 def create_anchors(model_cfg, model, image_size):

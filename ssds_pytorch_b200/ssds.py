@@ -6,8 +6,8 @@
 `cfg` uses the reference's config keys (ssds/core/config.py): MODEL.{SSDS,NETS,IMAGE_SIZE,
 NUM_CLASSES,FEATURE_LAYER,SIZES,ASPECT_RATIOS}, POST_PROCESS.{SCORE_THRESHOLD,IOU_THRESHOLD,
 MAX_DETECTIONS,MAX_DETECTIONS_PER_LEVEL,USE_DIOU,RESCORE_CENTER}, DATASET.PREPROC.{MEAN,STD}; a path to
-a yml file is accepted too.  SSDS in {"SSD", "SSDFPN"} with a ResNet backbone run on the tcgen05 conv stack in this round
-(BiFPN / MobileNetV2 / RegNet are the next rows; YOLO/FSSD/FCOS are out of scope).
+a yml file is accepted too.  On the tcgen05 conv stack in this round: SSD + ResNet*, SSDFPN + ResNet*, SSD + MobileNetV2
+(BiFPN / RegNet are the next rows; YOLO/FSSD/FCOS are out of scope).
 
 One process per GPU.  Under torch.distributed each rank runs its shard of the batch and
 `gather_detections` all-gathers the fixed-size [B,D,6] detection block over NCCL — the only
@@ -19,7 +19,7 @@ import numpy as np
 import torch
 
 from .decoder import Decoder
-from .model import SSDResNet, SSDFPNResNet, create_anchors, number_box_from_cfg
+from .model import engine_for, create_anchors, number_box_from_cfg
 
 DEFAULTS = {   # the values of ssds/core/config.py:42-74,166-175,206-207 that this path reads
     "MODEL": {"SSDS": "SSD", "NETS": "ResNet50", "IMAGE_SIZE": [300, 300], "NUM_CLASSES": 21},
@@ -57,17 +57,14 @@ class SSDDetector(object):
     def __init__(self, cfg, state_dict, device=None, use_graph=True):
         cfg = load_cfg(cfg)
         m = cfg["MODEL"]
-        engines = {"SSD": SSDResNet, "SSDFPN": SSDFPNResNet}
-        if m["SSDS"].upper() not in engines or not m["NETS"].startswith("ResNet"):
-            raise NotImplementedError("this round implements SSDS in {'SSD','SSDFPN'} over ResNet backbones")
+        engine = engine_for(m["SSDS"], m["NETS"])
         self.cfg = cfg
         self.device = (torch.device(device) if device is not None
                        else torch.device("cuda", torch.cuda.current_device()))
         self.mean = float(cfg["DATASET"]["PREPROC"]["MEAN"])
         self.std = float(cfg["DATASET"]["PREPROC"]["STD"])
-        self.model = engines[m["SSDS"].upper()](state_dict, m["FEATURE_LAYER"], m["NUM_CLASSES"],
-                                                number_box_from_cfg(m), device=self.device,
-                                                mean=self.mean, std=self.std).eval()
+        self.model = engine(state_dict, m["FEATURE_LAYER"], m["NUM_CLASSES"], number_box_from_cfg(m),
+                            device=self.device, mean=self.mean, std=self.std).eval()
         self.image_size = tuple(m["IMAGE_SIZE"])
         self.num_classes = m["NUM_CLASSES"]
         self.anchors = create_anchors(m, self.model, m["IMAGE_SIZE"])

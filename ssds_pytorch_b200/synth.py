@@ -55,6 +55,57 @@ def resnet_backbone_shapes(nets):
     return out
 
 
+MBV2_SETTINGS = [[1, 16, 1, 1], [6, 24, 2, 2], [6, 32, 3, 2], [6, 64, 4, 2], [6, 96, 3, 1], [6, 160, 3, 2],
+                 [6, 320, 1, 1]]
+
+
+def mobilenetv2_backbone_shapes():
+    """(key, shape) list of the reference MobileNetEx v2 under `backbone.` (mobilenet.py:40-100):
+    conv1 = ConvBNReLU(3,32,s2); layer{j}.{i} = torchvision InvertedResidual; head_conv; classifier."""
+    out = [("backbone.conv1.0.weight", (32, 3, 3, 3))]
+    _bn_keys(out, "backbone.conv1.1", 32)
+    inp = 32
+    for j, (t, c, n, s) in enumerate(MBV2_SETTINGS, start=1):
+        for i in range(n):
+            p = f"backbone.layer{j}.{i}.conv"
+            hid = inp * t
+            k = 0
+            if t != 1:
+                out.append((f"{p}.0.0.weight", (hid, inp, 1, 1))); _bn_keys(out, f"{p}.0.1", hid)
+                k = 1
+            out.append((f"{p}.{k}.0.weight", (hid, 1, 3, 3))); _bn_keys(out, f"{p}.{k}.1", hid)
+            out.append((f"{p}.{k + 1}.weight", (c, hid, 1, 1))); _bn_keys(out, f"{p}.{k + 2}", c)
+            inp = c
+    out.append(("backbone.head_conv.0.weight", (1280, 320, 1, 1)))
+    _bn_keys(out, "backbone.head_conv.1", 1280)
+    out.append(("backbone.classifier.1.weight", (1000, 1280)))
+    out.append(("backbone.classifier.1.bias", (1000,)))
+    return out
+
+
+def ssd_neck_shapes(feature_layer, number_box, num_classes):
+    out = []
+    in_ch, ei = None, 0
+    for layer, depth in zip(feature_layer[0], feature_layer[1]):
+        if not isinstance(layer, int):
+            p = f"extras.{ei}"
+            out.append((p + ".0.weight", (depth // 2, in_ch, 1, 1))); _bn_keys(out, p + ".1", depth // 2)
+            out.append((p + ".3.weight", (depth, depth // 2, 3, 3))); _bn_keys(out, p + ".4", depth)
+            ei += 1
+        in_ch = depth
+    for l, (depth, nb) in enumerate(zip(feature_layer[1], number_box)):
+        out.append((f"loc.{l}.weight", (nb * 4, depth, 3, 3)))
+        out.append((f"loc.{l}.bias", (nb * 4,)))
+    for l, (depth, nb) in enumerate(zip(feature_layer[1], number_box)):
+        out.append((f"conf.{l}.weight", (nb * num_classes, depth, 3, 3)))
+        out.append((f"conf.{l}.bias", (nb * num_classes,)))
+    return out
+
+
+def ssd_mobilenetv2_shapes(nets, feature_layer, number_box, num_classes):
+    return mobilenetv2_backbone_shapes() + ssd_neck_shapes(feature_layer, number_box, num_classes)
+
+
 def ssdfpn_resnet_shapes(nets, feature_layer, number_box, num_classes):
     """SSDFPN (fpn.py:36-146): transforms.{i} 1x1 laterals with bias, extras.{i} ConvBNReLU 3x3,
     shared towers loc/conf = 4 x ConvBNReLU(256,256,3) + Conv2d(256, A*4 | A*C, 3)."""
@@ -136,8 +187,9 @@ def synthetic_state_dict(nets, feature_layer, number_box, num_classes, seed=0, s
     g = torch.Generator().manual_seed(seed)
     sd = {}
     prior = -math.log((1 - 0.01) / 0.01)
-    shapes = (ssdfpn_resnet_shapes if ssds == "SSDFPN" else ssd_resnet_shapes)(
-        nets, feature_layer, number_box, num_classes)
+    shape_fn = (ssd_mobilenetv2_shapes if nets == "MobileNetV2"
+                else (ssdfpn_resnet_shapes if ssds == "SSDFPN" else ssd_resnet_shapes))
+    shapes = shape_fn(nets, feature_layer, number_box, num_classes)
     bn_prefixes = {k.rsplit(".", 1)[0] for k, _ in shapes if k.endswith("running_mean")}
     head_final = {k for k, _ in shapes if k.startswith(("loc.", "conf.")) and
                   k.rsplit(".", 1)[0] not in bn_prefixes and (ssds != "SSDFPN" or k.split(".")[1] == "4")}
@@ -173,7 +225,7 @@ def synthetic_state_dict(nets, feature_layer, number_box, num_classes, seed=0, s
                 sd[key] = (torch.rand(shape, generator=g) * 2 - 1) * a
             else:
                 sd[key] = torch.zeros(shape) if style == "init" else torch.randn(shape, generator=g) * 0.05
-        elif key.startswith("backbone.fc"):
+        elif key.startswith(("backbone.fc", "backbone.classifier")):
             sd[key] = torch.zeros(shape)
         elif key.startswith("extras."):
             fan_in = shape[1] * shape[2] * shape[3]

@@ -57,6 +57,9 @@ def main():
         "r18": ("SSD", "ResNet18", [[3, 4, 5, "Conv:S"], [128, 256, 512, 256]], [96, 160], 20, 3),
         "fpn50": ("SSDFPN", "ResNet50", [[3, 4, 5, "Conv:S", "Conv:S"], [512, 1024, 2048, 2048, 256]],
                   [256, 256], 20, 1),
+        # BASELINE configs[0]/[2] model: SSD + MobileNetV2 at 300x300 (SURVEY 8a cfg 1b geometry)
+        "mbv2": ("SSD", "MobileNetV2", [[5, 7, "Conv:S", "Conv:S", "Conv:S", "Conv:S"],
+                                        [96, 320, 512, 256, 256, 128]], [300, 300], 20, 1),
     }
     for tag, (ssds, nets, fl, image, ncls, B) in cases.items():
         L = len(fl[0])
@@ -65,7 +68,9 @@ def main():
         cfg, model = build(nets, fl, [list(s) for s in sizes], ratios, image, ncls, ssds)
         ref_sd = model.state_dict()
         nb = [6] * L
-        shapes = (synth.ssdfpn_resnet_shapes if ssds == "SSDFPN" else synth.ssd_resnet_shapes)(nets, fl, nb, ncls)
+        shape_fn = (synth.ssd_mobilenetv2_shapes if nets == "MobileNetV2" else
+                    (synth.ssdfpn_resnet_shapes if ssds == "SSDFPN" else synth.ssd_resnet_shapes))
+        shapes = shape_fn(nets, fl, nb, ncls)
         assert [k for k, _ in shapes] == list(ref_sd.keys()), "state_dict key order differs"
         for k, s in shapes:
             assert tuple(ref_sd[k].shape) == tuple(s), (k, ref_sd[k].shape, s)

@@ -28,6 +28,8 @@ def ref_conv(x_nhwc, w, b, stride, pad, relu, residual=None):
         y = y + residual.float().permute(0, 3, 1, 2)
     if relu:
         y = y.relu()
+    if relu == 2:
+        y = y.clamp(max=6.0)
     return y.permute(0, 2, 3, 1)
 
 
@@ -45,6 +47,11 @@ CASES = [
     (2, 19, 19, 64, 96, 3, 1, 1, True, False),      # 19x19 (MobileNet-SSD level): ragged tile rows
     (1, 40, 24, 192, 320, 3, 1, 1, True, True),     # non-pow2 channels, several K blocks, edges
     (2, 64, 64, 512, 64, 1, 1, 0, True, False),     # long K
+    (2, 38, 38, 32, 192, 1, 1, 0, 2, False),        # MobileNetV2 expand: Cin=32 (64B K-blocks), ReLU6
+    (2, 19, 19, 576, 96, 1, 1, 0, False, True),     # MobileNetV2 project + residual, Cout=96 (direct path)
+    (2, 19, 19, 96, 64, 3, 1, 1, True, False),      # Cin=96 = 3 x 32
+    (3, 10, 10, 160, 160, 3, 1, 1, 2, False),       # Cin=160 (32-blocks), 10x10 ragged tile, ReLU6
+    (2, 75, 75, 160, 32, 1, 1, 0, False, False),    # Cout=32 (padded 24-channel layer)
 ]
 
 
@@ -112,6 +119,55 @@ def test_stem_s2d_equals_7x7s2(K):
         ref = ref.permute(0, 2, 3, 1)
         err = (y.float() - ref).abs() / ref.abs().clamp(min=1.0)
         assert err.max().item() <= 2e-2, (fmt, err.max().item())
+
+
+def test_stem_3x3s2_mobilenet(K):
+    """MobileNetV2 conv1 (mobilenet.py:78: ConvBNReLU(3, 32, stride=2), 3x3/p1) on the same s2d path."""
+    g = torch.Generator().manual_seed(6)
+    N, H, W = 2, 60, 84
+    w = torch.randn((32, 3, 3, 3), generator=g) * 0.2
+    b = torch.randn((32,), generator=g) * 0.1
+    img = torch.rand((N, 3, H, W), generator=g)
+    packed = K.pack_image_s2d(img.cuda(), 0.0, 1.0, padded=True)
+    y = K.conv2d(packed, K.pack_stem_weight_s2d(w).cuda(), b.cuda(), 4, 4, 1, 2, 2,
+                 Ho=H // 2, Wo=W // 2, x_kind=1, x_width=W // 2)
+    torch.cuda.synchronize()
+    ref = F.conv2d(img.to(torch.bfloat16).float().cuda(), w.to(torch.bfloat16).float().cuda(), b.cuda(),
+                   stride=2, padding=1).clamp(0, 6).permute(0, 2, 3, 1)
+    err = (y.float() - ref).abs() / ref.abs().clamp(min=1.0)
+    assert err.max().item() <= 2e-2, err.max().item()
+
+
+@pytest.mark.parametrize("case", [(2, 38, 38, 192, 1, 2), (2, 38, 38, 192, 2, 2), (1, 75, 75, 160, 2, 1),
+                                  (3, 10, 10, 960, 1, 2), (2, 19, 19, 96, 2, 0), (2, 3, 3, 32, 1, 2)])
+def test_dwconv3x3(K, case):
+    """depthwise 3x3 + folded BN + ReLU6 (torchvision InvertedResidual) vs F.conv2d(groups=C)."""
+    N, H, W, Cc, stride, relu = case
+    g = torch.Generator().manual_seed(sum(case))
+    x = torch.randn((N, H, W, Cc), generator=g).to(torch.bfloat16).cuda()
+    w = torch.randn((Cc, 1, 3, 3), generator=g) * 0.3
+    b = torch.randn((Cc,), generator=g) * 0.2
+    y = K.dwconv3x3(x, K.pack_dw_weight(w).cuda(), b.cuda(), stride, relu)
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.to(torch.bfloat16).float().cuda(), b.cuda(), stride=stride,
+                   padding=1, groups=Cc)
+    if relu:
+        ref = ref.relu()
+    if relu == 2:
+        ref = ref.clamp(max=6.0)
+    ref = ref.permute(0, 2, 3, 1)
+    err = (y.float() - ref).abs() / ref.abs().clamp(min=1.0)
+    assert y.shape == ref.shape and err.max().item() <= 1e-2, err.max().item()
+
+
+def test_upsample2x_add(K):
+    g = torch.Generator().manual_seed(12)
+    coarse = torch.randn((2, 5, 7, 256), generator=g).to(torch.bfloat16).cuda()
+    fine = torch.randn((2, 10, 14, 256), generator=g).to(torch.bfloat16).cuda()
+    ref = (F.interpolate(coarse.float().permute(0, 3, 1, 2), scale_factor=2, mode="nearest") +
+           fine.float().permute(0, 3, 1, 2)).permute(0, 2, 3, 1).to(torch.bfloat16)
+    K.upsample2x_add(coarse, fine)
+    assert torch.equal(fine, ref)
 
 
 def test_maxpool(K):

@@ -17,7 +17,11 @@ CASES = {
     "r50": ("ResNet50", [[3, 4, 5, "Conv:S", "Conv:S", "Conv:S"], [512, 1024, 2048, 512, 256, 256]], 80, 1),
     "r18": ("ResNet18", [[3, 4, 5, "Conv:S"], [128, 256, 512, 256]], 20, 3),
     "fpn50": ("ResNet50", [[3, 4, 5, "Conv:S", "Conv:S"], [512, 1024, 2048, 2048, 256]], 20, 1),
+    "mbv2": ("MobileNetV2", [[5, 7, "Conv:S", "Conv:S", "Conv:S", "Conv:S"], [96, 320, 512, 256, 256, 128]], 20, 1),
 }
+
+FWD = {"r18": M.ssd_resnet_forward, "r50": M.ssd_resnet_forward, "fpn50": M.ssdfpn_resnet_forward,
+       "mbv2": M.ssd_mobilenetv2_forward}
 
 
 def case_inputs(tag, gold):
@@ -30,15 +34,14 @@ def case_inputs(tag, gold):
     return sd, fl, x, image, ncls
 
 
-@pytest.mark.parametrize("tag", ["r18", "r50", "fpn50"])
+@pytest.mark.parametrize("tag", ["r18", "r50", "fpn50", "mbv2"])
 def test_model_oracle_matches_reference_module(tag):
     gold = np.load(GOLD)
     sd, fl, x, image, ncls = case_inputs(tag, gold)
     np.testing.assert_array_equal(x.numpy().astype(np.float16), gold[tag + "_x"])
     torch.set_num_threads(8)
     with torch.no_grad():
-        fwd = M.ssdfpn_resnet_forward if tag.startswith("fpn") else M.ssd_resnet_forward
-        loc, conf = fwd(sd, x, fl, training=False, policy="fp32")
+        loc, conf = FWD[tag](sd, x, fl, training=False, policy="fp32")
     for i, (l, c) in enumerate(zip(loc, conf)):
         np.testing.assert_allclose(l.numpy(), gold[f"{tag}_loc{i}"], rtol=1e-4, atol=1e-5)
         np.testing.assert_allclose(c.numpy()[:, ::7], gold[f"{tag}_conf{i}"], rtol=1e-4, atol=1e-6)
