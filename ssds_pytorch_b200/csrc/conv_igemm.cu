@@ -218,10 +218,9 @@ struct ConvSmem {
 struct TileCoord {
   int n_tile, w0, h0, n0;
 };
-__device__ __forceinline__ TileCoord tile_coord(const ConvKernelParams& p, int tile) {
+__device__ __forceinline__ TileCoord tile_coord(const ConvKernelParams& p, int m, int n_tile) {
   TileCoord t;
-  t.n_tile = tile % p.n_tiles;
-  const int m = tile / p.n_tiles;
+  t.n_tile = n_tile;
   const int tw = m % p.tiles_w;
   const int th = (m / p.tiles_w) % p.tiles_h;
   const int tn = m / (p.tiles_w * p.tiles_h);
@@ -257,6 +256,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // WAYS M-tiles of one n-tile form a group: their MMAs are issued interleaved into WAYS separate
+  // accumulators, because back-to-back MMAs on ONE accumulator retire only every ~146 cycles whatever
+  // N is (tools/umma_bench.cu: N=64 146 -> 78 cycles/MMA with 4 accumulators, N=128 146 -> 116 with 2)
+  const int WAYS = p.ways;
+  const uint32_t tmem_cols = (uint32_t)max(32, 2 * WAYS * BLOCK_N);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -283,7 +287,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      smem_u32(tmem_holder)),
-                 "r"((uint32_t)S::TMEM_COLS)
+                 "r"(tmem_cols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -293,39 +297,45 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t tmem_base = *tmem_holder;
 
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
-  const int num_tiles = m_tiles * p.n_tiles;
+  const int m_groups = (m_tiles + WAYS - 1) / WAYS;
+  const int num_groups = m_groups * p.n_tiles;
   const int rows = p.BW * p.BH * p.BN;
-  const uint32_t tx_bytes = (uint32_t)rows * (BLOCK_K * 2) + (p.b_resident ? 0u : (uint32_t)S::B_STAGE_BYTES);
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      if (p.b_resident && (int)blockIdx.x < num_tiles) {
+      if (p.b_resident && (int)blockIdx.x < num_groups) {
         // weight-stationary: the grid is a multiple of n_tiles, so this CTA only ever sees one n_tile
         const int n_tile = (int)blockIdx.x % p.n_tiles;
         mbar_expect_tx(b_full, (uint32_t)(p.num_k_blocks * S::B_STAGE_BYTES));
         for (int kb = 0; kb < p.num_k_blocks; ++kb)
           tma_load_2d(bres + kb * S::B_STAGE_BYTES, &tmB, b_full, kb * BLOCK_K, n_tile * BLOCK_N);
       }
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const TileCoord t = tile_coord(p, tile);
+      const uint32_t a_bytes = (uint32_t)rows * (BLOCK_K * 2);
+      for (int group = blockIdx.x; group < num_groups; group += gridDim.x) {
+        const int n_tile = group % p.n_tiles;
+        const int m0 = (group / p.n_tiles) * WAYS;
+        const int nways = min(WAYS, m_tiles - m0);
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          unsigned char* sa = smem + stage * stage_bytes;
-          unsigned char* sb = sa + A_STAGE_BYTES;
-          mbar_expect_tx(&full_bar[stage], tx_bytes);
           const int tap = kb / p.kc_per_tap;
           const int kc = kb - tap * p.kc_per_tap;
           const int kh = tap / p.KW, kw = tap - kh * p.KW;
-          tma_load_4d(sa, &tmA, &full_bar[stage], kc * BLOCK_K, t.w0 * p.stride + kw - p.pad_w,
-                      t.h0 * p.stride + kh - p.pad_h, t.n0);
-          if (!p.b_resident)
-            tma_load_2d(sb, &tmB, &full_bar[stage], kb * BLOCK_K, t.n_tile * BLOCK_N);
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1;
+          for (int w = 0; w < nways; ++w) {        // one stage per (k-block, way); B rides with way 0
+            const TileCoord t = tile_coord(p, m0 + w, n_tile);
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            unsigned char* sa = smem + stage * stage_bytes;
+            const bool with_b = (w == 0) && !p.b_resident;
+            mbar_expect_tx(&full_bar[stage], a_bytes + (with_b ? (uint32_t)S::B_STAGE_BYTES : 0u));
+            tma_load_4d(sa, &tmA, &full_bar[stage], kc * BLOCK_K, t.w0 * p.stride + kw - p.pad_w,
+                        t.h0 * p.stride + kh - p.pad_h, t.n0);
+            if (with_b)
+              tma_load_2d(sa + A_STAGE_BYTES, &tmB, &full_bar[stage], kb * BLOCK_K, n_tile * BLOCK_N);
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
           }
         }
       }
@@ -338,32 +348,48 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      if (p.b_resident && (int)blockIdx.x < num_tiles) mbar_wait(b_full, 0);
+      if (p.b_resident && (int)blockIdx.x < num_groups) mbar_wait(b_full, 0);
       const uint32_t bres_addr = smem_u32(bres);
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int group = blockIdx.x; group < num_groups; group += gridDim.x) {
+        const int m0 = (group / p.n_tiles) * WAYS;
+        const int nways = min(WAYS, m_tiles - m0);
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * WAYS * BLOCK_N);
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
+          // the nways stages of this k-block are consecutive in the ring
+          uint32_t a_addr[4];
+          int st = stage;
+          uint32_t ph = phase;
+          for (int w = 0; w < nways; ++w) {
+            mbar_wait(&full_bar[st], ph);
+            a_addr[w] = smem_u32(smem + st * stage_bytes);
+            if (++st == STAGES) {
+              st = 0;
+              ph ^= 1;
+            }
+          }
           tcgen05_fence_after();
-          const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
-          const uint64_t a_desc = make_smem_desc<S::ROW_BYTES>(a_addr);
           const uint64_t b_desc = make_smem_desc<S::ROW_BYTES>(
-              p.b_resident ? bres_addr + (uint32_t)(kb * S::B_STAGE_BYTES) : a_addr + A_STAGE_BYTES);
+              p.b_resident ? bres_addr + (uint32_t)(kb * S::B_STAGE_BYTES) : a_addr[0] + A_STAGE_BYTES);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            // advance 16 bf16 = 32 bytes inside the swizzle row: +2 in the (>>4) address field
-            umma_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
-                      (kb > 0 || k > 0) ? 1u : 0u);
+            // advance 16 bf16 = 32 bytes inside the swizzle row: +2 in the (>>4) address field;
+            // consecutive MMAs go to different accumulators
+            for (int w = 0; w < nways; ++w)
+              umma_bf16(d_tmem + (uint32_t)(w * BLOCK_N),
+                        make_smem_desc<S::ROW_BYTES>(a_addr[w]) + (uint64_t)(2 * k),
+                        b_desc + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
           }
-          tcgen05_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1;
+          for (int w = 0; w < nways; ++w) {
+            tcgen05_commit(&empty_bar[stage]);  // frees the smem slots when these MMAs retire
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
           }
         }
-        tcgen05_commit(&tmem_full[acc]);      // accumulator ready for the epilogue
+        tcgen05_commit(&tmem_full[acc]);      // accumulators ready for the epilogue
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
@@ -381,10 +407,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (lane == 0 && p.tma_store) {
       const int R = p.n_staging;
       const bool has_res = (p.residual != nullptr);
-      int a_tile = blockIdx.x, a_chunk = 0, armed = 0;       // arming iterator
+      int a_group = blockIdx.x, a_way = 0, a_chunk = 0, armed = 0;       // arming iterator
       auto arm_next = [&]() {
-        if (a_tile >= num_tiles) return;
-        const TileCoord ta = tile_coord(p, a_tile);
+        if (a_group >= num_groups) return;
+        const int a_m0 = (a_group / p.n_tiles) * WAYS;
+        const TileCoord ta = tile_coord(p, a_m0 + a_way, a_group % p.n_tiles);
         const int slot = armed % R;
         if (has_res) {
           mbar_expect_tx(&slot_ready[slot], (uint32_t)rows * 128u);
@@ -397,22 +424,29 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int nch = min(BLOCK_N, p.Cout - ta.n_tile * BLOCK_N) >> 6;
         if (++a_chunk == nch) {
           a_chunk = 0;
-          a_tile += gridDim.x;
+          if (++a_way == min(WAYS, m_tiles - a_m0)) {
+            a_way = 0;
+            a_group += gridDim.x;
+          }
         }
       };
       for (int i = 0; i < R; ++i) arm_next();
       int g = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const TileCoord t = tile_coord(p, tile);
-        const int nch = min(BLOCK_N, p.Cout - t.n_tile * BLOCK_N) >> 6;
-        for (int c = 0; c < nch; ++c, ++g) {
-          const int slot = g % R;
-          mbar_wait(&slot_full[slot], (uint32_t)(g / R) & 1u);
-          tma_store_4d(&tmY, staging + slot * STAGING_BYTES, t.n_tile * BLOCK_N + c * 64, t.w0, t.h0,
-                       t.n0);
-          tma_store_commit();
-          tma_store_wait_read<0>();     // store g has been read out of smem -> its slot is free
-          arm_next();                   // = chunk g+R (residual prefetch distance R-1 chunks)
+      for (int group = blockIdx.x; group < num_groups; group += gridDim.x) {
+        const int m0 = (group / p.n_tiles) * WAYS;
+        const int nways = min(WAYS, m_tiles - m0);
+        for (int w = 0; w < nways; ++w) {
+          const TileCoord t = tile_coord(p, m0 + w, group % p.n_tiles);
+          const int nch = min(BLOCK_N, p.Cout - t.n_tile * BLOCK_N) >> 6;
+          for (int c = 0; c < nch; ++c, ++g) {
+            const int slot = g % R;
+            mbar_wait(&slot_full[slot], (uint32_t)(g / R) & 1u);
+            tma_store_4d(&tmY, staging + slot * STAGING_BYTES, t.n_tile * BLOCK_N + c * 64, t.w0, t.h0,
+                         t.n0);
+            tma_store_commit();
+            tma_store_wait_read<0>();     // store g has been read out of smem -> its slot is free
+            arm_next();                   // = chunk g+R (residual prefetch distance R-1 chunks)
+          }
         }
       }
       tma_store_wait_all();             // smem must outlive the last store
@@ -433,14 +467,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int bh = (r / p.BW) % p.BH;
     const int bn = r / (p.BW * p.BH);
 
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const TileCoord t = tile_coord(p, tile);
+    for (int group = blockIdx.x; group < num_groups; group += gridDim.x) {
+     const int m0 = (group / p.n_tiles) * WAYS;
+     const int nways = min(WAYS, m_tiles - m0);
+     mbar_wait(&tmem_full[acc], acc_phase);
+     tcgen05_fence_after();
+     for (int way = 0; way < nways; ++way) {
+      const TileCoord t = tile_coord(p, m0 + way, group % p.n_tiles);
       const int w = t.w0 + bw, h = t.h0 + bh, n = t.n0 + bn;
       const bool row_ok = (r < rows) && (w < p.Wo) && (h < p.Ho) && (n < p.N);
-
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tcgen05_fence_after();
-      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) +
+                             (uint32_t)((acc * WAYS + way) * BLOCK_N);
 
       if (p.mode == CONV_OUT_NHWC_BF16 && p.tma_store) {
         // ---------- staged path: 64-column chunks through swizzled smem + TMA store ----------
@@ -596,6 +633,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
         }
       }
+     }  // ways
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -611,7 +649,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 2) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                 "r"((uint32_t)S::TMEM_COLS)
+                 "r"(tmem_cols)
                  : "memory");
   }
 }
@@ -655,7 +693,17 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tm
   }
   kp.n_staging = want_staging ? (kp.residual ? 4 : 2) : 0;
   kp.tma_store = want_staging ? 1 : 0;
-  const int tiles = kp.tiles_w * kp.tiles_h * kp.tiles_n * kp.n_tiles;
+  const int m_tiles = kp.tiles_w * kp.tiles_h * kp.tiles_n;
+  // interleaved accumulators: as many M tiles per group as TMEM allows (2 buffers x ways x BLOCK_N <= 512
+  // columns), as long as there are enough groups to keep every SM busy
+  kp.ways = 512 / (2 * BLOCK_N);
+  if (kp.ways > 4) kp.ways = 4;
+  if (const char* e = getenv("SSDSB_WAYS")) {               // experiment knob (profiling only)
+    const int v = atoi(e);
+    if (v == 1 || v == 2 || v == 4) kp.ways = v < kp.ways ? v : kp.ways;
+  }
+  while (kp.ways > 1 && ((m_tiles + kp.ways - 1) / kp.ways) * kp.n_tiles < 2 * sms) kp.ways >>= 1;
+  const int tiles = ((m_tiles + kp.ways - 1) / kp.ways) * kp.n_tiles;   // groups
   int grid = tiles < sms ? tiles : sms;
   // weight-stationary mode: small weight slabs (<= 80 KiB per n-tile) are loaded once per CTA instead of
   // once per tile; needs every CTA to stay on one n_tile => grid must be a multiple of n_tiles
@@ -669,7 +717,13 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tm
     }
   }
   kp.stages = S::stages_for(kp.n_staging, kp.b_resident, kp.num_k_blocks);
-  if (kp.stages > kp.num_k_blocks * 4) kp.stages = kp.num_k_blocks * 4;   // nothing to gain beyond
+  if (kp.b_resident && kp.stages < 2 * kp.ways) {           // resident weights must not starve the A ring
+    kp.b_resident = 0;
+    grid = tiles < sms ? tiles : sms;
+    kp.stages = S::stages_for(kp.n_staging, false, kp.num_k_blocks);
+  }
+  while (kp.ways > 1 && kp.stages < 2 * kp.ways) kp.ways >>= 1;
+  if (kp.stages > kp.num_k_blocks * 4 * kp.ways) kp.stages = kp.num_k_blocks * 4 * kp.ways;
   if (kp.stages < 2) kp.stages = 2;
   const int smem = S::bytes(kp.stages, kp.n_staging, kp.b_resident, kp.num_k_blocks);
   conv_igemm_kernel<BLOCK_N, BLOCK_K><<<grid, CONV_NT, smem, st>>>(tmA, tmB, tmY, tmR, kp);
