@@ -230,7 +230,7 @@ __device__ __forceinline__ TileCoord tile_coord(const ConvKernelParams& p, int m
   return t;
 }
 
-template <int BLOCK_N, int BLOCK_K>
+template <int BLOCK_N, int BLOCK_K, int WAYS>
 __global__ void __launch_bounds__(CONV_NT, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR,
@@ -259,8 +259,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   // WAYS M-tiles of one n-tile form a group: their MMAs are issued interleaved into WAYS separate
   // accumulators, because back-to-back MMAs on ONE accumulator retire only every ~146 cycles whatever
   // N is (tools/umma_bench.cu: N=64 146 -> 78 cycles/MMA with 4 accumulators, N=128 146 -> 116 with 2)
-  const int WAYS = p.ways;
-  const uint32_t tmem_cols = (uint32_t)max(32, 2 * WAYS * BLOCK_N);
+  // (WAYS is a template parameter: the single-thread producer / MMA loops must stay in registers.)
+  // A trailing partial group simply runs "ghost" tiles whose coordinates are out of range: TMA
+  // zero-fills their loads and clips their stores.
+  constexpr uint32_t tmem_cols = (2 * WAYS * BLOCK_N < 32) ? 32u : (uint32_t)(2 * WAYS * BLOCK_N);
+  static_assert(2 * WAYS * BLOCK_N <= 512, "TMEM has 512 columns");
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -317,24 +320,36 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int group = blockIdx.x; group < num_groups; group += gridDim.x) {
         const int n_tile = group % p.n_tiles;
         const int m0 = (group / p.n_tiles) * WAYS;
-        const int nways = min(WAYS, m_tiles - m0);
+        int cw[WAYS], ch[WAYS], cn[WAYS];          // input-space origin of each way's tile
+#pragma unroll
+        for (int w = 0; w < WAYS; ++w) {
+          const TileCoord t = tile_coord(p, m0 + w, n_tile);
+          cw[w] = t.w0 * p.stride - p.pad_w;
+          ch[w] = t.h0 * p.stride - p.pad_h;
+          cn[w] = t.n0;
+        }
+        int tap = 0, kc = 0, kh = 0, kw = 0;       // incremental (no divisions in the K loop)
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-          const int tap = kb / p.kc_per_tap;
-          const int kc = kb - tap * p.kc_per_tap;
-          const int kh = tap / p.KW, kw = tap - kh * p.KW;
-          for (int w = 0; w < nways; ++w) {        // one stage per (k-block, way); B rides with way 0
-            const TileCoord t = tile_coord(p, m0 + w, n_tile);
+#pragma unroll
+          for (int w = 0; w < WAYS; ++w) {         // one stage per (k-block, way); B rides with way 0
             mbar_wait(&empty_bar[stage], phase ^ 1);
             unsigned char* sa = smem + stage * stage_bytes;
             const bool with_b = (w == 0) && !p.b_resident;
             mbar_expect_tx(&full_bar[stage], a_bytes + (with_b ? (uint32_t)S::B_STAGE_BYTES : 0u));
-            tma_load_4d(sa, &tmA, &full_bar[stage], kc * BLOCK_K, t.w0 * p.stride + kw - p.pad_w,
-                        t.h0 * p.stride + kh - p.pad_h, t.n0);
+            tma_load_4d(sa, &tmA, &full_bar[stage], kc * BLOCK_K, cw[w] + kw, ch[w] + kh, cn[w]);
             if (with_b)
               tma_load_2d(sa + A_STAGE_BYTES, &tmB, &full_bar[stage], kb * BLOCK_K, n_tile * BLOCK_N);
             if (++stage == STAGES) {
               stage = 0;
               phase ^= 1;
+            }
+          }
+          if (++kc == p.kc_per_tap) {
+            kc = 0;
+            ++tap;
+            if (++kw == p.KW) {
+              kw = 0;
+              ++kh;
             }
           }
         }
@@ -351,37 +366,38 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       if (p.b_resident && (int)blockIdx.x < num_groups) mbar_wait(b_full, 0);
       const uint32_t bres_addr = smem_u32(bres);
       for (int group = blockIdx.x; group < num_groups; group += gridDim.x) {
-        const int m0 = (group / p.n_tiles) * WAYS;
-        const int nways = min(WAYS, m_tiles - m0);
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * WAYS * BLOCK_N);
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-          // the nways stages of this k-block are consecutive in the ring
-          uint32_t a_addr[4];
+          // the WAYS stages of this k-block are consecutive in the ring
+          uint64_t a_desc[WAYS];
           int st = stage;
           uint32_t ph = phase;
-          for (int w = 0; w < nways; ++w) {
+#pragma unroll
+          for (int w = 0; w < WAYS; ++w) {
             mbar_wait(&full_bar[st], ph);
-            a_addr[w] = smem_u32(smem + st * stage_bytes);
+            a_desc[w] = make_smem_desc<S::ROW_BYTES>(smem_u32(smem + st * stage_bytes));
             if (++st == STAGES) {
               st = 0;
               ph ^= 1;
             }
           }
           tcgen05_fence_after();
-          const uint64_t b_desc = make_smem_desc<S::ROW_BYTES>(
-              p.b_resident ? bres_addr + (uint32_t)(kb * S::B_STAGE_BYTES) : a_addr[0] + A_STAGE_BYTES);
+          const uint64_t b_desc = p.b_resident
+              ? make_smem_desc<S::ROW_BYTES>(bres_addr + (uint32_t)(kb * S::B_STAGE_BYTES))
+              : a_desc[0] + (uint64_t)(A_STAGE_BYTES >> 4);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             // advance 16 bf16 = 32 bytes inside the swizzle row: +2 in the (>>4) address field;
             // consecutive MMAs go to different accumulators
-            for (int w = 0; w < nways; ++w)
-              umma_bf16(d_tmem + (uint32_t)(w * BLOCK_N),
-                        make_smem_desc<S::ROW_BYTES>(a_addr[w]) + (uint64_t)(2 * k),
+#pragma unroll
+            for (int w = 0; w < WAYS; ++w)
+              umma_bf16(d_tmem + (uint32_t)(w * BLOCK_N), a_desc[w] + (uint64_t)(2 * k),
                         b_desc + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
           }
-          for (int w = 0; w < nways; ++w) {
+#pragma unroll
+          for (int w = 0; w < WAYS; ++w) {
             tcgen05_commit(&empty_bar[stage]);  // frees the smem slots when these MMAs retire
             if (++stage == STAGES) {
               stage = 0;
@@ -424,7 +440,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int nch = min(BLOCK_N, p.Cout - ta.n_tile * BLOCK_N) >> 6;
         if (++a_chunk == nch) {
           a_chunk = 0;
-          if (++a_way == min(WAYS, m_tiles - a_m0)) {
+          if (++a_way == WAYS) {
             a_way = 0;
             a_group += gridDim.x;
           }
@@ -434,8 +450,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int g = 0;
       for (int group = blockIdx.x; group < num_groups; group += gridDim.x) {
         const int m0 = (group / p.n_tiles) * WAYS;
-        const int nways = min(WAYS, m_tiles - m0);
-        for (int w = 0; w < nways; ++w) {
+        for (int w = 0; w < WAYS; ++w) {
           const TileCoord t = tile_coord(p, m0 + w, group % p.n_tiles);
           const int nch = min(BLOCK_N, p.Cout - t.n_tile * BLOCK_N) >> 6;
           for (int c = 0; c < nch; ++c, ++g) {
@@ -469,10 +484,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
     for (int group = blockIdx.x; group < num_groups; group += gridDim.x) {
      const int m0 = (group / p.n_tiles) * WAYS;
-     const int nways = min(WAYS, m_tiles - m0);
      mbar_wait(&tmem_full[acc], acc_phase);
      tcgen05_fence_after();
-     for (int way = 0; way < nways; ++way) {
+     for (int way = 0; way < WAYS; ++way) {
       const TileCoord t = tile_coord(p, m0 + way, group % p.n_tiles);
       const int w = t.w0 + bw, h = t.h0 + bh, n = t.n0 + bn;
       const bool row_ok = (r < rows) && (w < p.Wo) && (h < p.Ho) && (n < p.N);
@@ -680,17 +694,26 @@ int pick_block_n(int cout) {
   return 256;
 }
 
+template <int BLOCK_N, int BLOCK_K, int WAYS>
+int launch_ways(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY,
+                const CUtensorMap& tmR, const ConvKernelParams& kp, int grid, int smem, cudaStream_t st) {
+  using S = ConvSmem<BLOCK_N, BLOCK_K>;
+  static bool configured = false;
+  if (!configured) {
+    SSDSB_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BLOCK_N, BLOCK_K, WAYS>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, S::MAX_BYTES));
+    configured = true;
+  }
+  conv_igemm_kernel<BLOCK_N, BLOCK_K, WAYS><<<grid, CONV_NT, smem, st>>>(tmA, tmB, tmY, tmR, kp);
+  SSDSB_LAUNCH_CHECK("conv_igemm_kernel");
+  return SSDSB_OK;
+}
+
 template <int BLOCK_N, int BLOCK_K>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY,
            const CUtensorMap& tmR, ConvKernelParams& kp, bool want_staging, int sms,
            cudaStream_t st) {
   using S = ConvSmem<BLOCK_N, BLOCK_K>;
-  static bool configured = false;
-  if (!configured) {
-    SSDSB_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BLOCK_N, BLOCK_K>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, S::MAX_BYTES));
-    configured = true;
-  }
   kp.n_staging = want_staging ? (kp.residual ? 4 : 2) : 0;
   kp.tma_store = want_staging ? 1 : 0;
   const int m_tiles = kp.tiles_w * kp.tiles_h * kp.tiles_n;
@@ -726,9 +749,16 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tm
   if (kp.stages > kp.num_k_blocks * 4 * kp.ways) kp.stages = kp.num_k_blocks * 4 * kp.ways;
   if (kp.stages < 2) kp.stages = 2;
   const int smem = S::bytes(kp.stages, kp.n_staging, kp.b_resident, kp.num_k_blocks);
-  conv_igemm_kernel<BLOCK_N, BLOCK_K><<<grid, CONV_NT, smem, st>>>(tmA, tmB, tmY, tmR, kp);
-  SSDSB_LAUNCH_CHECK("conv_igemm_kernel");
-  return SSDSB_OK;
+  const int groups = ((m_tiles + kp.ways - 1) / kp.ways) * kp.n_tiles;
+  if (grid > groups) grid = groups;
+  if constexpr (BLOCK_N <= 64) {
+    if (kp.ways == 4) return launch_ways<BLOCK_N, BLOCK_K, 4>(tmA, tmB, tmY, tmR, kp, grid, smem, st);
+  }
+  if constexpr (BLOCK_N <= 128) {
+    if (kp.ways == 2) return launch_ways<BLOCK_N, BLOCK_K, 2>(tmA, tmB, tmY, tmR, kp, grid, smem, st);
+  }
+  kp.ways = 1;
+  return launch_ways<BLOCK_N, BLOCK_K, 1>(tmA, tmB, tmY, tmR, kp, grid, smem, st);
 }
 
 }  // namespace
