@@ -49,6 +49,16 @@ def cfg_dict():
             "DATASET": {"PREPROC": {"MEAN": 0, "STD": 255}}}
 
 
+def measured_conv_traffic():
+    """DRAM bytes of all conv_igemm launches of one step, from the committed ncu capture
+    (profiles/r1_conv_traffic.json; dram__bytes_read.sum + dram__bytes_write.sum), or None."""
+    p = os.path.join(ROOT, "profiles", "r1_conv_traffic.json")
+    try:
+        return json.load(open(p))["conv_dram_bytes_per_step"]
+    except Exception:
+        return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -258,7 +268,8 @@ def run_b200(args):
             "gpu_launches": launches_step * K,
             "roofline": {"bound": "tensor", "kernel": "conv_igemm_kernel (all conv launches of a step)",
                          "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
-                         "peak_source": f"{src} bf16 sustained", "traffic": None,
+                         "peak_source": f"{src} bf16 sustained", "traffic": measured_conv_traffic(),
+                         "traffic_unit": "DRAM bytes per step over the conv launches (ncu, profiles/r1_conv_traffic.json)",
                          "flops_per_step": flops_step, "conv_ms_per_step": conv_ms},
             "clocks": sampler.summary(),
         }

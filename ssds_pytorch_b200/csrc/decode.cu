@@ -32,20 +32,29 @@ struct DecodeParams {
   int slice_begin[SSDSB_MAX_LEVELS + 1];  // prefix sum of slices per image
   int cand_off[SSDSB_MAX_LEVELS + 1];     // prefix sum of candidate capacity per image
   int n_levels, B, K, cap;
+  int K_total;   // slots per (image, level) in the outputs (= top_n)
+  int out_off;   // first slot written by this round (top_n > 1024 runs several rounds of <= 1024)
   float threshold;
   int rescore;
 };
 
-// workspace layout: [gthr: B*L u64][gcnt: B*L i32 (padded)][cand: B*cand_total u64]
+// workspace layout: [gthr: B*L u64][gcnt: B*L i32 (padded)][upper: B*L u64][cand: B*cand_total u64]
+// `upper` = exclusive upper key bound of the current round per (image, level): ~0 in round 0, then the
+// smallest key emitted by the previous round, 0 once a map is exhausted.
 __device__ __forceinline__ unsigned long long* ws_gthr(void* ws) {
   return reinterpret_cast<unsigned long long*>(ws);
 }
 __device__ __forceinline__ int* ws_gcnt(void* ws, int B, int L) {
   return reinterpret_cast<int*>(reinterpret_cast<unsigned long long*>(ws) + (size_t)B * L);
 }
+__device__ __host__ __forceinline__ size_t ws_head_bytes(int B, int L) {
+  return (size_t)B * L * 8 + (((size_t)B * L * 4 + 7) / 8) * 8;
+}
+__device__ __forceinline__ unsigned long long* ws_upper(void* ws, int B, int L) {
+  return reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(ws) + ws_head_bytes(B, L));
+}
 __device__ __forceinline__ unsigned long long* ws_cand(void* ws, int B, int L) {
-  size_t head = (size_t)B * L * 8 + (((size_t)B * L * 4 + 7) / 8) * 8;
-  return reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(ws) + head);
+  return ws_upper(ws, B, L) + (size_t)B * L;
 }
 
 __global__ void __launch_bounds__(DEC_NT)
@@ -67,6 +76,9 @@ decode_select(const __grid_constant__ DecodeParams p, void* __restrict__ ws) {
   const int tid = threadIdx.x;
   const int L = p.n_levels;
   unsigned long long* gthr = ws_gthr(ws) + (size_t)b * L + l;
+  const unsigned long long upper = ws_upper(ws, p.B, L)[(size_t)b * L + l];
+  if (upper == 0ull) return;                 // this map was exhausted by an earlier round (uniform)
+  const float upperF = (upper == ~0ull) ? INFINITY : key_score(upper);
 
   if (tid == 0) {
     s_cnt = 0;
@@ -133,8 +145,9 @@ decode_select(const __grid_constant__ DecodeParams p, void* __restrict__ ws) {
     const unsigned long long cur = s_thr;
     const float curF = (cur == 0ull) ? -INFINITY : key_score(cur);
     const float lim = fmaxf(thr, curF);
-    const bool pre = (v[0] >= lim) | (v[1] >= lim) | (v[2] >= lim) | (v[3] >= lim) |
-                     (v[4] >= lim) | (v[5] >= lim) | (v[6] >= lim) | (v[7] >= lim);
+    bool pre = false;
+#pragma unroll
+    for (int e = 0; e < DEC_EPT; ++e) pre |= (v[e] >= lim) & (v[e] <= upperF);
     int fill = 0;
     if (__any_sync(0xffffffffu, pre)) {
       unsigned long long k[DEC_EPT];
@@ -143,7 +156,7 @@ decode_select(const __grid_constant__ DecodeParams p, void* __restrict__ ws) {
       for (int e = 0; e < DEC_EPT; ++e) {
         const int idx = i0[e >> 2] + (e & 3);
         k[e] = make_key(v[e], (uint32_t)idx);
-        take[e] = (idx < end) && (v[e] >= thr) && (k[e] > cur);
+        take[e] = (idx < end) && (v[e] >= thr) && (k[e] > cur) && (k[e] < upper);
       }
       fill = topk_append<DEC_EPT>(buf, &s_cnt, k, take);
     }
@@ -247,7 +260,9 @@ decode_finalize(const __grid_constant__ DecodeParams p, void* __restrict__ ws,
   const float Mx = (float)W * stride_f - 1.0f;  // box.py:83  size=[W,H] * stride - 1
   const float My = (float)H * stride_f - 1.0f;
   const float* loc = lv.loc + (size_t)b * lv.A * 4 * HW;
-  const size_t row = (size_t)b * L * K + (size_t)l * K;
+  const size_t row = (size_t)b * L * p.K_total + (size_t)l * p.K_total + p.out_off;
+  if (tid == 0)   // bound for the next round: the smallest key emitted now, or "exhausted"
+    ws_upper(ws, p.B, L)[(size_t)b * L + l] = (nout == K) ? buf[K - 1] : 0ull;
 
   for (int t = tid; t < K; t += DEC_NT) {
     float score = 0.f, cls = 0.f, x1 = 0.f, y1 = 0.f, x2 = 0.f, y2 = 0.f;
@@ -295,10 +310,13 @@ decode_finalize(const __grid_constant__ DecodeParams p, void* __restrict__ ws,
   }
 }
 
-int fill_params(DecodeParams& p, const ssdsb_level* levels, int n_levels, int B, int top_n) {
+int fill_params(DecodeParams& p, const ssdsb_level* levels, int n_levels, int B, int top_n_total) {
+  const int top_n = top_n_total < DEC_MAX_K ? top_n_total : DEC_MAX_K;   // per round
   p.n_levels = n_levels;
   p.B = B;
   p.K = top_n;
+  p.K_total = top_n_total;
+  p.out_off = 0;
   p.cap = next_pow2(top_n + DEC_TILE + 1);   // prune when fewer than one tile of slots is left
   if (p.cap < 2 * DEC_TILE) p.cap = 2 * DEC_TILE;
   p.slice_begin[0] = 0;
@@ -326,8 +344,8 @@ static int validate_levels(const ssdsb_level* levels, int n_levels, int B, int t
                 n_levels, SSDSB_MAX_LEVELS);
   SSDSB_REQUIRE(B >= 0, "decode: negative batch");
   SSDSB_REQUIRE(top_n >= 1, "decode: top_n=%d must be >= 1", top_n);
-  if (top_n > DEC_MAX_K)
-    return fail(SSDSB_ERR_UNSUPPORTED, "decode: top_n=%d > %d not implemented", top_n, DEC_MAX_K);
+  if (top_n > 64 * DEC_MAX_K)
+    return fail(SSDSB_ERR_UNSUPPORTED, "decode: top_n=%d > %d not implemented", top_n, 64 * DEC_MAX_K);
   for (int l = 0; l < n_levels; ++l) {
     const ssdsb_level& v = levels[l];
     SSDSB_REQUIRE(v.A >= 1 && v.C >= 1 && v.H >= 1 && v.W >= 1 && v.stride >= 1,
@@ -347,8 +365,7 @@ extern "C" size_t ssdsb_decode_workspace_bytes(const ssdsb_level* levels, int n_
   if (validate_levels(levels, n_levels, B, top_n, false) != SSDSB_OK) return 0;
   DecodeParams p;
   fill_params(p, levels, n_levels, B, top_n);
-  size_t head = (size_t)B * n_levels * 8 + (((size_t)B * n_levels * 4 + 7) / 8) * 8;
-  return head + (size_t)B * p.cand_off[n_levels] * 8 + 16;
+  return ws_head_bytes(B, n_levels) + (size_t)B * n_levels * 8 + (size_t)B * p.cand_off[n_levels] * 8 + 16;
 }
 
 extern "C" int ssdsb_decode(const ssdsb_level* levels, int n_levels, int B, float threshold,
@@ -369,18 +386,28 @@ extern "C" int ssdsb_decode(const ssdsb_level* levels, int n_levels, int B, floa
   p.threshold = threshold;
   p.rescore = rescore;
   cudaStream_t st = (cudaStream_t)stream;
-  const size_t head = (size_t)B * n_levels * 8 + (((size_t)B * n_levels * 4 + 7) / 8) * 8;
-  SSDSB_CUDA(cudaMemsetAsync(d_workspace, 0, head, st));
+  const size_t head = ws_head_bytes(B, n_levels);
+  // upper bounds start at "none"
+  SSDSB_CUDA(cudaMemsetAsync(reinterpret_cast<unsigned char*>(d_workspace) + head, 0xff,
+                             (size_t)B * n_levels * 8, st));
   const size_t smem = (size_t)(p.cap + p.K) * sizeof(unsigned long long);
   SSDSB_CUDA(cudaFuncSetAttribute(decode_select, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
   SSDSB_CUDA(cudaFuncSetAttribute(decode_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
   dim3 g1(p.slice_begin[n_levels], B);
-  decode_select<<<g1, DEC_NT, smem, st>>>(p, d_workspace);
-  SSDSB_LAUNCH_CHECK("decode_select");
   dim3 g2(n_levels, B);
-  decode_finalize<<<g2, DEC_NT, smem, st>>>(p, d_workspace, d_scores, d_boxes, d_classes, d_index);
-  SSDSB_LAUNCH_CHECK("decode_finalize");
+  // top_n <= 1024: one round.  Larger top_n (the 20 000-per-level NMS stress of SURVEY 8d cfg 5):
+  // successive rounds each extract the next <= 1024 keys below the previous round's smallest key.
+  const int per_round = p.K;
+  for (int off = 0; off < top_n; off += per_round) {
+    p.K = (top_n - off) < per_round ? (top_n - off) : per_round;
+    p.out_off = off;
+    SSDSB_CUDA(cudaMemsetAsync(d_workspace, 0, head, st));
+    decode_select<<<g1, DEC_NT, smem, st>>>(p, d_workspace);
+    SSDSB_LAUNCH_CHECK("decode_select");
+    decode_finalize<<<g2, DEC_NT, smem, st>>>(p, d_workspace, d_scores, d_boxes, d_classes, d_index);
+    SSDSB_LAUNCH_CHECK("decode_finalize");
+  }
   return SSDSB_OK;
 }

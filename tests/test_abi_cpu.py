@@ -42,7 +42,7 @@ def test_argument_errors_without_gpu():
         _lib.check(rc, "nms")
     lv = (_lib.Level * 1)(_lib.Level(None, None, None, 3, 5, 4, 4, 8))
     assert lib.ssdsb_decode_workspace_bytes(lv, 1, 2, 300) > 0
-    rc = lib.ssdsb_decode(lv, 1, 2, 0.01, 5000, 1, None, None, None, None, None, 0, None)
+    rc = lib.ssdsb_decode(lv, 1, 2, 0.01, 100000, 1, None, None, None, None, None, 0, None)
     assert rc == _lib.ERR_UNSUPPORTED
     rc = lib.ssdsb_decode(lv, 0, 2, 0.01, 300, 1, None, None, None, None, None, 0, None)
     assert rc == _lib.ERR_INVALID

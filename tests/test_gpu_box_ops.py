@@ -96,6 +96,25 @@ def test_decode_vs_oracle_multislice_and_ties(B):
     np.testing.assert_array_equal(cpu(idx).astype(np.int64), oi)
 
 
+def test_decode_large_top_n_rounds(B):
+    """top_n > 1024 (the 20 000-per-level NMS stress of SURVEY 8d cfg 5) runs in rounds of 1024."""
+    from oracle import box_oracle as O
+    rng = np.random.default_rng(21)
+    A, C, H, W, stride = 3, 20, 24, 24, 8            # 34 560 scores / image
+    anc = O.generate_anchors(stride, [1, 2, 0.5], [4.0])
+    conf = distinct(rng, (2, A * C, H, W), 0.0, 1.0)
+    conf[1, :, :, :] *= (rng.uniform(size=conf[1].shape) < 0.05)   # few candidates: exhausted early
+    loc = rng.normal(0, 0.3, (2, A * 4, H, W)).astype(np.float32)
+    for top_n in (2500, 5000):
+        got = B.decode(torch.from_numpy(conf), torch.from_numpy(loc), stride, 0.3, top_n,
+                       torch.from_numpy(anc), True, return_indices=True)
+        exp = O.decode(conf, loc, stride, 0.3, top_n, anc, True, return_indices=True)
+        np.testing.assert_array_equal(cpu(got[3]).astype(np.int64), exp[3])
+        np.testing.assert_array_equal(cpu(got[2]), exp[2])
+        np.testing.assert_allclose(cpu(got[0]), exp[0], rtol=1e-5, atol=2e-6)
+        np.testing.assert_allclose(cpu(got[1]), exp[1], rtol=1e-5, atol=1e-4)
+
+
 def test_decode_odd_sizes_and_edge_values(B):
     from oracle import box_oracle as O
     rng = np.random.default_rng(11)
