@@ -447,6 +447,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
       };
       for (int i = 0; i < R; ++i) arm_next();
+      // With 4 slots the engine lets two stores stay in flight (waiting for the read of store g right
+      // after issuing it would cap the store rate at one 16 KiB sub-tile per smem-read latency)
+      const bool lag2 = (R >= 4);
       int g = 0;
       for (int group = blockIdx.x; group < num_groups; group += gridDim.x) {
         const int m0 = (group / p.n_tiles) * WAYS;
@@ -459,8 +462,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             tma_store_4d(&tmY, staging + slot * STAGING_BYTES, t.n_tile * BLOCK_N + c * 64, t.w0, t.h0,
                          t.n0);
             tma_store_commit();
-            tma_store_wait_read<0>();     // store g has been read out of smem -> its slot is free
-            arm_next();                   // = chunk g+R (residual prefetch distance R-1 chunks)
+            if (lag2) {
+              if (g >= 2) {
+                tma_store_wait_read<2>(); // store g-2 has been read out of smem -> its slot is free
+                arm_next();               // = chunk g-2+R
+              }
+            } else {
+              tma_store_wait_read<0>();   // store g has been read out of smem -> its slot is free
+              arm_next();                 // = chunk g+R
+            }
           }
         }
       }
@@ -714,7 +724,9 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tm
            const CUtensorMap& tmR, ConvKernelParams& kp, bool want_staging, int sms,
            cudaStream_t st) {
   using S = ConvSmem<BLOCK_N, BLOCK_K>;
-  kp.n_staging = want_staging ? (kp.residual ? 4 : 2) : 0;
+  // 4 staging slots for residual layers (prefetch) and for short-K, write-heavy layers; 2 when the
+  // operand ring needs the shared memory more (long-K, MMA-bound layers)
+  kp.n_staging = want_staging ? ((kp.residual || kp.num_k_blocks <= 8) ? 4 : 2) : 0;
   kp.tma_store = want_staging ? 1 : 0;
   const int m_tiles = kp.tiles_w * kp.tiles_h * kp.tiles_n;
   // interleaved accumulators: as many M tiles per group as TMEM allows (2 buffers x ways x BLOCK_N <= 512

@@ -43,6 +43,9 @@ __device__ __forceinline__ bool suppresses(const Cand& p, float pcls, float pare
   float w = fmaxf(xx2 - xx1 + 1.0f, 0.0f);
   float h = fmaxf(yy2 - yy1 + 1.0f, 0.0f);
   float inter = w * h;
+  // exact shortcut: disjoint boxes give iou = +0 (denominator > 0), the DIoU term only lowers it, so
+  // "iou <= thr" holds for every thr >= 0 — skip the two IEEE divisions
+  if (inter == 0.0f && thr >= 0.0f && (carea + parea) > 0.0f) return false;
   float iou = inter / (carea + parea - inter + 1e-7f);
   if (diou) {
     float olx = fminf(c.x1, p.x1), oly = fminf(c.y1, p.y1);
@@ -158,7 +161,7 @@ nms_kernel(const float* __restrict__ scores, const float* __restrict__ boxes,
         const int i = tid / NMS_CW;
         const int w = tid % NMS_CW;
         uint32_t bits = 0;
-        if (i < m) {
+        if (i < m && w * 32 + 31 > i) {          // words entirely at or before i hold no j > i
           Cand p = cbox[i];
           float pc = ccls[i], pa = carea[i];
           const int j0 = w * 32;

@@ -346,3 +346,28 @@ def test_multibox_loss_cfg4_level_vs_oracle(B):
     esum, enpos = O.multibox_loss_reduced(logits, target, depth, 3)
     np.testing.assert_array_equal(cpu(npos), enpos.astype(np.float32))
     np.testing.assert_allclose(cpu(ls), esum, rtol=2e-4)
+
+
+def test_cls_loss_step_like_reference_pipeline(B):
+    """pipeline_anchor_basic.py:62-97 (classification part): extract_targets per level + MultiBoxLoss
+    + (depth >= 0) mask + normalisation by the foreground count, on an SSDFPN-like 3-level geometry."""
+    from collections import OrderedDict
+    from oracle import box_oracle as O
+    from ssds_pytorch_b200.pipeline import multibox_cls_loss_step
+    rng = np.random.default_rng(77)
+    Bn, C = 3, 20
+    levels = [(8, 20), (16, 10), (32, 5)]
+    anchors = OrderedDict((s, O.generate_anchors(s, [1, 2, 0.5], [4.0, 5.04, 6.35])) for s, _ in levels)
+    tg = make_targets(rng, Bn, 12, C, 160)
+    logits = [rng.normal(-4.6, 1.0, (Bn, 9 * C, hw, hw)).astype(np.float32) for _, hw in levels]
+    got, parts = multibox_cls_loss_step([torch.from_numpy(l) for l in logits], torch.from_numpy(tg),
+                                        OrderedDict((s, torch.from_numpy(a)) for s, a in anchors.items()), C)
+    tot, fg = 0.0, 0
+    for (s, hw), lg in zip(levels, logits):
+        cls_t, box_t, dep = O.extract_targets(tg, anchors, C, s, (hw, hw), [0.5, 0.4])
+        sums, npos = O.multibox_loss_reduced(lg.reshape(Bn, 9, C, hw, hw), cls_t, dep, 3)
+        tot += sums.sum()
+        fg += max(int(npos.sum()), 1)
+    assert fg > 3
+    np.testing.assert_allclose(got.item(), tot / fg, rtol=3e-4)
+    np.testing.assert_array_equal(cpu(parts[0][3]), O.extract_targets(tg, anchors, C, 8, (20, 20), [0.5, 0.4])[2])
