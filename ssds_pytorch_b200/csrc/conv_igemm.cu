@@ -449,7 +449,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int i = 0; i < R; ++i) arm_next();
       // With 4 slots the engine lets two stores stay in flight (waiting for the read of store g right
       // after issuing it would cap the store rate at one 16 KiB sub-tile per smem-read latency)
-      const bool lag2 = (R >= 4);
+      // (not for residual layers: there the re-arm IS the residual prefetch and must run as far ahead
+      // as possible — measured: lag 2 made the conv3 layers 15 % slower)
+      const bool lag2 = (R >= 4) && !has_res;
       int g = 0;
       for (int group = blockIdx.x; group < num_groups; group += gridDim.x) {
         const int m0 = (group / p.n_tiles) * WAYS;
