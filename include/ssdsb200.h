@@ -168,6 +168,11 @@ typedef struct {
   int Ho, Wo;
   int x_cstride, out_cstride, res_cstride;
   int x_row_pixels; /* pixels per image row in memory (0 => W) */
+  int chunk;        /* 0 = dense.  > 0: block-diagonal ("grouped") conv, Cin == Cout, every `chunk`
+                     * consecutive channels form an independent conv (chunk % 32 == 0, <= 128; a
+                     * grouped conv with group width gw uses chunk = lcm(gw, 32)).  w is then
+                     * bf16 [(Cout/chunk)*128][KH*KW][chunk]: one 128-row slab per chunk, rows >= chunk
+                     * zero.  NHWC output only. */
   int x_kind;
   int w_rows;
   int relu;
@@ -201,6 +206,14 @@ SSDSB_API int ssdsb_maxpool3x3s2_nhwc_bf16(const void* d_x, int N, int H, int W,
 SSDSB_API int ssdsb_dwconv3x3_nhwc_bf16(const void* d_x, const void* d_w, const float* d_bias, int N,
                                         int H, int W, int C, int stride, int relu, void* d_y,
                                         void* stream);
+
+/* BiFPN weighted fusion (ssds/modeling/ssds/bifpn.py:41-62), NHWC bf16:
+ *   mode 0: out = w0*a + w1*nearest_up2(b)            a,out [N,H,W,C], b [N,H/2,W/2,C]
+ *   mode 1: out = w0*a + w1*maxpool2x2(b) [+ w2*c]    a,c,out [N,H,W,C], b [N,2H,2W,C]; c may be NULL
+ * w* are the relu-normalised scalars (host-side, bifpn.py:35-38). */
+SSDSB_API int ssdsb_bifpn_fuse_nhwc_bf16(const void* d_a, const void* d_b, const void* d_c, int mode,
+                                         float w0, float w1, float w2, int N, int H, int W, int C,
+                                         void* d_out, void* stream);
 
 /* FPN top-down merge (ssds/modeling/ssds/fpn.py:80-87): fine[n,h,w,:] += coarse[n,h/2,w/2,:]
  * (nearest 2x upsample + add), NHWC bf16, in place on `fine` ([N,H,W,C]; coarse is [N,H/2,W/2,C]). */

@@ -26,7 +26,7 @@ class ConvDesc(C.Structure):
     """mirror of `ssdsb_conv_desc` (include/ssdsb200.h)."""
     _fields_ = [(n, C.c_int) for n in (
         "N", "H", "W", "Cin", "Cout", "KH", "KW", "stride", "pad", "Ho", "Wo",
-        "x_cstride", "out_cstride", "res_cstride", "x_row_pixels", "x_kind", "w_rows", "relu", "out_mode", "n_loc",
+        "x_cstride", "out_cstride", "res_cstride", "x_row_pixels", "chunk", "x_kind", "w_rows", "relu", "out_mode", "n_loc",
         "sigmoid")]
 
 
@@ -65,6 +65,7 @@ def _load():
         "ssdsb_maxpool3x3s2_nhwc_bf16": (i, [vp, i, i, i, i, vp, vp]),
         "ssdsb_upsample2x_add_nhwc_bf16": (i, [vp, vp, i, i, i, i, vp]),
         "ssdsb_dwconv3x3_nhwc_bf16": (i, [vp, vp, vp, i, i, i, i, i, i, vp, vp]),
+        "ssdsb_bifpn_fuse_nhwc_bf16": (i, [vp, vp, vp, i, f, f, f, i, i, i, i, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)          # AttributeError if the .so does not export it

@@ -59,14 +59,14 @@ def pack_stem_weight_s2d(w_folded, pad=None):
 
 
 def conv2d(x, w, bias, KH, KW, stride, pad, relu=False, residual=None, out=None, Ho=0, Wo=0,
-           x_kind=0, x_width=None):
+           x_kind=0, x_width=None, chunk=0):
     """x NHWC bf16 [N,H,W,Cin] -> NHWC bf16 [N,Ho,Wo,Cout]; w bf16 [Cout, KH*KW, Cin].
     x_kind=1: x is the left-padded s2d image [N,H,row_px,16] (logical width x_width), windowed stem."""
     N, H, W, Cin = x.shape
     row_px = 0
     if x_width is not None:
         row_px, W = W, x_width
-    Cout = w.shape[0]
+    Cout = Cin if chunk else w.shape[0]
     ho = Ho or (H + 2 * pad - KH) // stride + 1
     wo = Wo or (W + 2 * pad - KW) // stride + 1
     if out is None:
@@ -74,7 +74,7 @@ def conv2d(x, w, bias, KH, KW, stride, pad, relu=False, residual=None, out=None,
     d = _lib.ConvDesc(N=N, H=H, W=W, Cin=Cin, Cout=Cout, KH=KH, KW=KW, stride=stride, pad=pad,
                       Ho=ho, Wo=wo, x_cstride=x.stride(2), out_cstride=out.stride(2),
                       res_cstride=residual.stride(2) if residual is not None else 0,
-                      x_row_pixels=row_px, x_kind=x_kind,
+                      x_row_pixels=row_px, chunk=chunk, x_kind=x_kind,
                       w_rows=w.shape[0], relu=int(relu), out_mode=0, n_loc=0, sigmoid=0)
     with torch.cuda.device(x.device):
         check(lib.ssdsb_conv2d_bf16(C.byref(d), ptr(x), ptr(w), ptr(bias), ptr(residual), ptr(out),
@@ -95,7 +95,7 @@ def conv2d_head(x, w, bias, n_loc, sigmoid, KH=3, KW=3, stride=1, pad=1, loc=Non
         conf = torch.empty((N, Cout - n_loc, ho, wo), dtype=torch.float32, device=x.device)
     d = _lib.ConvDesc(N=N, H=H, W=W, Cin=Cin, Cout=Cout, KH=KH, KW=KW, stride=stride, pad=pad,
                       Ho=ho, Wo=wo, x_cstride=x.stride(2), out_cstride=0, res_cstride=0,
-                      x_row_pixels=0, x_kind=0,
+                      x_row_pixels=0, chunk=0, x_kind=0,
                       w_rows=w.shape[0], relu=0, out_mode=1, n_loc=n_loc, sigmoid=int(sigmoid))
     with torch.cuda.device(x.device):
         check(lib.ssdsb_conv2d_bf16(C.byref(d), ptr(x), ptr(w), ptr(bias), None, ptr(loc), ptr(conf),
@@ -171,4 +171,32 @@ def dwconv3x3(x, w, bias, stride=1, relu=2, out=None):
     with torch.cuda.device(x.device):
         check(lib.ssdsb_dwconv3x3_nhwc_bf16(ptr(x), ptr(w), ptr(bias), N, H, W, Cc, stride, int(relu),
                                             ptr(out), stream_ptr()), "dwconv3x3")
+    return out
+
+
+def pack_grouped_weight(w_folded, chunk, c_pad):
+    """Grouped conv [C, gw, KH, KW] (groups = C / gw) -> block-diagonal chunk slabs for the chunked
+    igemm: bf16 [(c_pad/chunk)*128, KH*KW, chunk]; slab s covers channels [s*chunk, (s+1)*chunk), its
+    row r < chunk is output channel s*chunk + r, which only sees the gw inputs of its own group."""
+    c, gw, kh, kw = w_folded.shape
+    assert chunk % gw == 0 and c_pad % chunk == 0 and c_pad >= c
+    n_chunks = c_pad // chunk
+    out = torch.zeros((n_chunks, 128, kh * kw, chunk), dtype=torch.float32)
+    wk = w_folded.permute(0, 2, 3, 1).reshape(c, kh * kw, gw)      # [C, taps, gw]
+    for o in range(c):
+        s_, r = divmod(o, chunk)
+        g_local = (o // gw) - s_ * (chunk // gw)                    # group index inside the chunk
+        out[s_, r, :, g_local * gw:(g_local + 1) * gw] = wk[o]
+    return out.reshape(n_chunks * 128, kh * kw, chunk).to(torch.bfloat16).contiguous()
+
+
+def bifpn_fuse(a, b, w0, w1, c=None, w2=0.0, mode=0, out=None):
+    """BiFPN weighted fusion (bifpn.py:41-62): mode 0 out = w0*a + w1*up2(b); mode 1 out = w0*a +
+    w1*maxpool2(b) [+ w2*c].  NHWC bf16."""
+    N, H, W, Cc = a.shape
+    if out is None:
+        out = torch.empty_like(a)
+    with torch.cuda.device(a.device):
+        check(lib.ssdsb_bifpn_fuse_nhwc_bf16(ptr(a), ptr(b), ptr(c), int(mode), float(w0), float(w1),
+                                             float(w2), N, H, W, Cc, ptr(out), stream_ptr()), "bifpn_fuse")
     return out

@@ -336,7 +336,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             unsigned char* sa = smem + stage * stage_bytes;
             const bool with_b = (w == 0) && !p.b_resident;
             mbar_expect_tx(&full_bar[stage], a_bytes + (with_b ? (uint32_t)S::B_STAGE_BYTES : 0u));
-            tma_load_4d(sa, &tmA, &full_bar[stage], kc * BLOCK_K, cw[w] + kw, ch[w] + kh, cn[w]);
+            tma_load_4d(sa, &tmA, &full_bar[stage], kc * BLOCK_K + n_tile * p.chunk_cin, cw[w] + kw,
+                        ch[w] + kh, cn[w]);
             if (with_b)
               tma_load_2d(sa + A_STAGE_BYTES, &tmB, &full_bar[stage], kb * BLOCK_K, n_tile * BLOCK_N);
             if (++stage == STAGES) {
@@ -566,8 +567,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
       } else {
 #pragma unroll 1
-        for (int c0 = half * 32; c0 < BLOCK_N; c0 += 64) {
-          const int col0 = t.n_tile * BLOCK_N + c0;
+        for (int c0 = half * 32; c0 < p.ntile_cout; c0 += 64) {
+          const int col0 = t.n_tile * p.ntile_cout + c0;
           if (col0 >= p.Cout) break;            // warp-uniform
           uint32_t v[32];
           tmem_ld32(t_row + (uint32_t)c0, v);
@@ -793,8 +794,17 @@ extern "C" int ssdsb_conv2d_bf16(const ssdsb_conv_desc* d, const void* x, const 
   const int Wo = d->Wo > 0 ? d->Wo : (d->W + 2 * d->pad - d->KW) / d->stride + 1;
   SSDSB_REQUIRE(Ho >= 1 && Wo >= 1, "conv2d: empty output");
   const bool windowed = d->x_kind == SSDSB_CONV_X_WINDOWED_STEM;
+  const int chunk = d->chunk;
+  if (chunk) {
+    SSDSB_REQUIRE(chunk % 32 == 0 && chunk <= 128 && d->Cin == d->Cout && d->Cin % chunk == 0 && !windowed &&
+                      d->out_mode == CONV_OUT_NHWC_BF16,
+                  "conv2d: chunked conv needs Cin == Cout, chunk %% 32 == 0, chunk <= 128 (chunk=%d Cin=%d)",
+                  chunk, d->Cin);
+    SSDSB_REQUIRE(d->w_rows >= (d->Cout / chunk) * 128, "conv2d: chunked weights need 128 rows per chunk");
+  }
   // K-block = one swizzle row of channels: 64 (128B) when Cin allows it, else 32 (64B), else 16 (32B)
-  const int block_k = windowed ? 64 : (d->Cin % 64 == 0 ? 64 : (d->Cin % 32 == 0 ? 32 : 16));
+  const int cin_k = chunk ? chunk : d->Cin;       // channels contracted per output tile
+  const int block_k = windowed ? 64 : (cin_k % 64 == 0 ? 64 : (cin_k % 32 == 0 ? 32 : 16));
   const int cs = d->x_cstride ? d->x_cstride : d->Cin;
   const int row_px = d->x_row_pixels ? d->x_row_pixels : d->W;
   if (windowed) {
@@ -845,13 +855,15 @@ extern "C" int ssdsb_conv2d_bf16(const ssdsb_conv_desc* d, const void* x, const 
   kp.tiles_w = (Wo + BW - 1) / BW;
   kp.tiles_h = (Ho + BH - 1) / BH;
   kp.tiles_n = (d->N + BN - 1) / BN;
-  const int block_n = pick_block_n(d->Cout);
-  kp.n_tiles = (d->Cout + block_n - 1) / block_n;
+  const int block_n = chunk ? 128 : pick_block_n(d->Cout);
+  kp.n_tiles = chunk ? d->Cout / chunk : (d->Cout + block_n - 1) / block_n;
+  kp.chunk_cin = chunk;
+  kp.ntile_cout = chunk ? chunk : block_n;
   if (windowed) {          // taps = the 4 kernel rows; the 4 horizontal taps live inside the K-block
     kp.taps = 4; kp.KW = 1; kp.kc_per_tap = 1;
     kp.pad_w = 0; kp.pad_h = 2;
   } else {
-    kp.taps = d->KH * d->KW; kp.KW = d->KW; kp.kc_per_tap = d->Cin / block_k;
+    kp.taps = d->KH * d->KW; kp.KW = d->KW; kp.kc_per_tap = cin_k / block_k;
     kp.pad_w = d->pad; kp.pad_h = d->pad;
   }
   kp.num_k_blocks = kp.taps * kp.kc_per_tap;
@@ -905,7 +917,7 @@ extern "C" int ssdsb_conv2d_bf16(const ssdsb_conv_desc* d, const void* x, const 
       return fail(SSDSB_ERR_CUDA, "conv2d: weight tensor map failed (CUresult %d)", (int)r);
   }
 
-  const bool want_staging = d->out_mode == CONV_OUT_NHWC_BF16 && (d->Cout % 64) == 0;
+  const bool want_staging = d->out_mode == CONV_OUT_NHWC_BF16 && (d->Cout % 64) == 0 && !chunk;
   if (want_staging) {
     cuuint64_t dims[4] = {(cuuint64_t)d->Cout, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)d->N};
     cuuint32_t box[4] = {64, (cuuint32_t)BW, (cuuint32_t)BH, (cuuint32_t)BN};

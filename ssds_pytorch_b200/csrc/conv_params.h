@@ -12,6 +12,8 @@ struct ConvKernelParams {
   int KW, taps;
   int stride, pad_w, pad_h;
   int stages, n_staging, tma_store;
+  int chunk_cin;     // block-diagonal (grouped) conv: input-channel offset per n-tile (0 = dense)
+  int ntile_cout;    // output channels covered by one n-tile (BLOCK_N, or the chunk width)
   int ways;          // M tiles processed together with interleaved MMAs (1, 2 or 4 accumulators)
   int b_resident;    // weights of this CTA's n-tile stay in shared memory for the whole kernel
   int BW, BH, BN;    // output-pixel patch of one M tile (product <= 128)

@@ -120,6 +120,67 @@ upsample2x_add_kernel(const uint4* __restrict__ coarse, uint4* __restrict__ fine
   }
 }
 
+// BiFPN weighted fusion (reference ssds/modeling/ssds/bifpn.py:41-62), NHWC bf16, 8 channels/thread:
+//   mode 0 (top-down):  out = w0*a + w1*nearest_up2(b)            a [N,H,W,C], b [N,H/2,W/2,C]
+//   mode 1 (bottom-up): out = w0*a + w1*maxpool2x2(b) [+ w2*c]    a,c [N,H,W,C], b [N,2H,2W,C]
+// fp32 arithmetic in the reference's order, one rounding to bf16 at the store.
+__global__ void __launch_bounds__(256)
+bifpn_fuse_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, const uint4* __restrict__ c,
+                  int mode, float w0, float w1, float w2, int N, int H, int W, int C8,
+                  uint4* __restrict__ out) {
+  const size_t total = (size_t)N * H * W * C8;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % C8);
+    const int w = (int)((i / C8) % W);
+    const int h = (int)((i / ((size_t)C8 * W)) % H);
+    const int n = (int)(i / ((size_t)C8 * W * H));
+    const uint4 av = __ldg(a + i);
+    const uint32_t as[4] = {av.x, av.y, av.z, av.w};
+    float bv[8];
+    if (mode == 0) {
+      const uint4 q = __ldg(b + (((size_t)n * (H >> 1) + (h >> 1)) * (W >> 1) + (w >> 1)) * C8 + ch);
+      const uint32_t qs[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        bv[e * 2] = __uint_as_float(qs[e] << 16);
+        bv[e * 2 + 1] = __uint_as_float(qs[e] & 0xffff0000u);
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) bv[e] = -INFINITY;
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          const uint4 q = __ldg(b + (((size_t)n * (2 * H) + 2 * h + dy) * (2 * W) + 2 * w + dx) * C8 + ch);
+          const uint32_t qs[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            bv[e * 2] = fmaxf(bv[e * 2], __uint_as_float(qs[e] << 16));
+            bv[e * 2 + 1] = fmaxf(bv[e * 2 + 1], __uint_as_float(qs[e] & 0xffff0000u));
+          }
+        }
+    }
+    float r[8];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      r[e * 2] = w0 * __uint_as_float(as[e] << 16) + w1 * bv[e * 2];
+      r[e * 2 + 1] = w0 * __uint_as_float(as[e] & 0xffff0000u) + w1 * bv[e * 2 + 1];
+    }
+    if (c) {
+      const uint4 cv = __ldg(c + i);
+      const uint32_t cs[4] = {cv.x, cv.y, cv.z, cv.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        r[e * 2] += w2 * __uint_as_float(cs[e] << 16);
+        r[e * 2 + 1] += w2 * __uint_as_float(cs[e] & 0xffff0000u);
+      }
+    }
+    out[i] = make_uint4(pack2(r[0], r[1]), pack2(r[2], r[3]), pack2(r[4], r[5]), pack2(r[6], r[7]));
+  }
+}
+
 // Depthwise 3x3 (pad 1, stride 1|2) + folded BN + ReLU/ReLU6 on NHWC bf16 (torchvision
 // InvertedResidual / reference SepConvBNReLU).  One thread = one output pixel x 8 channels: nine
 // 16-byte input loads (neighbouring threads hit the same lines in L1/L2), bf16 weights [9][C],
@@ -174,6 +235,27 @@ dwconv3x3_kernel(const uint4* __restrict__ x, const uint4* __restrict__ w, const
 }  // namespace ssdsb
 
 using namespace ssdsb;
+
+extern "C" int ssdsb_bifpn_fuse_nhwc_bf16(const void* d_a, const void* d_b, const void* d_c, int mode,
+                                          float w0, float w1, float w2, int N, int H, int W, int C,
+                                          void* d_out, void* stream) {
+  SSDSB_REQUIRE(d_a && d_b && d_out, "bifpn_fuse: NULL argument");
+  SSDSB_REQUIRE(mode == 0 || mode == 1, "bifpn_fuse: mode=%d (0 top-down, 1 bottom-up)", mode);
+  SSDSB_REQUIRE(N >= 1 && H >= 1 && W >= 1 && C >= 8 && C % 8 == 0, "bifpn_fuse: bad shape");
+  SSDSB_REQUIRE(mode == 1 || ((H % 2) == 0 && (W % 2) == 0), "bifpn_fuse: top-down needs an even-sized map");
+  SSDSB_REQUIRE(mode == 0 || d_c == nullptr || true, "bifpn_fuse");
+  SSDSB_REQUIRE((((uintptr_t)d_a | (uintptr_t)d_b | (uintptr_t)d_c | (uintptr_t)d_out) & 15) == 0,
+                "bifpn_fuse: pointers must be 16-byte aligned");
+  const size_t total = (size_t)N * H * W * (C / 8);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  bifpn_fuse_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const uint4*>(d_a), reinterpret_cast<const uint4*>(d_b),
+      reinterpret_cast<const uint4*>(d_c), mode, w0, w1, w2, N, H, W, C / 8,
+      reinterpret_cast<uint4*>(d_out));
+  SSDSB_LAUNCH_CHECK("bifpn_fuse_kernel");
+  return SSDSB_OK;
+}
 
 extern "C" int ssdsb_dwconv3x3_nhwc_bf16(const void* d_x, const void* d_w, const float* d_bias, int N,
                                          int H, int W, int C, int stride, int relu, void* d_y,

@@ -160,6 +160,49 @@ def test_dwconv3x3(K, case):
     assert y.shape == ref.shape and err.max().item() <= 1e-2, err.max().item()
 
 
+@pytest.mark.parametrize("case", [(2, 20, 20, 432, 1), (2, 20, 20, 192, 2), (1, 40, 24, 96, 1), (3, 10, 10, 1008, 1)])
+def test_grouped_conv_regnet(K, case):
+    """RegNet 3x3 grouped conv (group width 48; regnet.py:69) as a block-diagonal chunked igemm:
+    channels padded to a multiple of 96 (two groups per chunk), padded channels stay 0."""
+    N, H, W, Cc, stride = case
+    gw, chunk = 48, 96
+    c_pad = (Cc + chunk - 1) // chunk * chunk
+    g = torch.Generator().manual_seed(Cc + stride)
+    x = torch.zeros((N, H, W, c_pad), dtype=torch.bfloat16)
+    x[..., :Cc] = torch.randn((N, H, W, Cc), generator=g).to(torch.bfloat16)
+    w = torch.randn((Cc, gw, 3, 3), generator=g) * (1.0 / np.sqrt(gw * 9))
+    b = torch.zeros(c_pad)
+    b[:Cc] = torch.randn((Cc,), generator=g) * 0.2
+    y = K.conv2d(x.cuda(), K.pack_grouped_weight(w, chunk, c_pad).cuda(), b.cuda(), 3, 3, stride, 1, True,
+                 chunk=chunk)
+    torch.cuda.synchronize()
+    ref = F.conv2d(x[..., :Cc].float().permute(0, 3, 1, 2).cuda(), w.to(torch.bfloat16).float().cuda(),
+                   b[:Cc].cuda(), stride=stride, padding=1, groups=Cc // gw).relu().permute(0, 2, 3, 1)
+    err = (y[..., :Cc].float() - ref).abs() / ref.abs().clamp(min=1.0)
+    assert y.shape[-1] == c_pad and err.max().item() <= 2e-2, err.max().item()
+    assert (y[..., Cc:] == 0).all()
+
+
+def test_bifpn_fuse(K):
+    """BiFPN weighted fusion (bifpn.py:41-62) vs the torch expressions of the reference."""
+    g = torch.Generator().manual_seed(15)
+    a = torch.randn((2, 10, 14, 256), generator=g).to(torch.bfloat16).cuda()
+    coarse = torch.randn((2, 5, 7, 256), generator=g).to(torch.bfloat16).cuda()
+    fine = torch.randn((2, 20, 28, 256), generator=g).to(torch.bfloat16).cuda()
+    c = torch.randn((2, 10, 14, 256), generator=g).to(torch.bfloat16).cuda()
+    nchw = lambda t: t.float().permute(0, 3, 1, 2)
+    w0, w1, w2 = 0.37, 0.41, 0.22
+    up = K.bifpn_fuse(a, coarse, w0, w1, mode=0)
+    ref = (w0 * nchw(a) + w1 * F.interpolate(nchw(coarse), scale_factor=2, mode="nearest")).permute(0, 2, 3, 1)
+    assert (up.float() - ref).abs().max().item() <= 2e-2
+    dn = K.bifpn_fuse(a, fine, w0, w1, c=c, w2=w2, mode=1)
+    ref = (w0 * nchw(a) + w1 * F.max_pool2d(nchw(fine), kernel_size=2) + w2 * nchw(c)).permute(0, 2, 3, 1)
+    assert (dn.float() - ref).abs().max().item() <= 2e-2
+    dn2 = K.bifpn_fuse(a, fine, w0, w1, mode=1)
+    ref = (w0 * nchw(a) + w1 * F.max_pool2d(nchw(fine), kernel_size=2)).permute(0, 2, 3, 1)
+    assert (dn2.float() - ref).abs().max().item() <= 2e-2
+
+
 def test_upsample2x_add(K):
     g = torch.Generator().manual_seed(12)
     coarse = torch.randn((2, 5, 7, 256), generator=g).to(torch.bfloat16).cuda()
