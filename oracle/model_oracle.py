@@ -170,3 +170,85 @@ def ssdfpn_resnet_forward(sd, x, feature_layer, training=False, policy="fp32"):
 def ssd_mobilenetv2_forward(sd, x, feature_layer, training=False, policy="fp32"):
     """SSD.forward (ssd.py:42-74) over the MobileNetV2 backbone."""
     return ssd_resnet_forward(sd, x, feature_layer, training, policy, backbone="mobilenetv2")
+
+
+REGNET_GW = 48
+
+
+def regnetx_features(sd, x, outputs, policy):
+    """reference regnet.py:270-282 (RegNet.forward) with SimpleStemIN / ResBottleneckBlock (:28-107)."""
+    x = _r(x.float(), policy)
+    x = _r(_conv_bn(x, sd, "backbone.stem.conv.weight", "backbone.stem.bn", 2, 1, True, policy), policy)
+    feats = []
+    for si in range(1, 5):
+        if si > max(outputs):
+            break
+        bi = 1
+        while f"backbone.s{si}.b{bi}.f.a.weight" in sd:
+            p = f"backbone.s{si}.b{bi}"
+            stride = 2 if bi == 1 else 1
+            identity = x
+            if (p + ".proj.weight") in sd:
+                identity = _r(_conv_bn(x, sd, p + ".proj.weight", p + ".bn", stride, 0, False, policy), policy)
+            w_b = sd[p + ".f.b.weight"].shape[0]
+            y = _r(_conv_bn(x, sd, p + ".f.a.weight", p + ".f.a_bn", 1, 0, True, policy), policy)
+            y = _r(_conv_bn(y, sd, p + ".f.b.weight", p + ".f.b_bn", stride, 1, True, policy,
+                            groups=w_b // REGNET_GW), policy)
+            x = _r(_conv_bn(y, sd, p + ".f.c.weight", p + ".f.c_bn", 1, 0, True, policy, residual=identity), policy)
+            bi += 1
+        if si in outputs:
+            feats.append(x)
+    return feats
+
+
+def _shared_heads(sd, xx, training, policy):
+    outs = []
+    for tower in ("loc", "conf"):                                     # SharedHead fpn.py:10-18
+        t = xx
+        for j in range(4):
+            t = _r(_conv_bn(t, sd, f"{tower}.{j}.0.weight", f"{tower}.{j}.1", 1, 1, True, policy), policy)
+        outs.append(_conv_bn(t, sd, f"{tower}.4.weight", None, 1, 1, False, policy, bias=sd[f"{tower}.4.bias"]))
+    return outs[0], (outs[1] if training else torch.sigmoid(outs[1]))
+
+
+def ssdbifpn_forward(sd, x, feature_layer, training=False, policy="fp32", backbone="regnetx"):
+    """reference bifpn.py:104-142 (SSDBiFPN.forward) + BiFPNModule.forward (:30-63) on a state_dict."""
+    outputs = [l for l in feature_layer[0] if isinstance(l, int)]
+    feats = (regnetx_features if backbone == "regnetx" else resnet_features)(sd, x, outputs, policy)
+    n_back = len(feats)
+    raw_top = feats[-1]
+    xx = [_r(_conv_bn(f, sd, f"transforms.{i}.weight", None, 1, 0, False, policy,
+                      bias=sd[f"transforms.{i}.bias"]), policy) for i, f in enumerate(feats)]
+    s_ = 0
+    while f"stack_bifpn.{s_}.w1" in sd:
+        p = f"stack_bifpn.{s_}"
+        w1 = F.relu(sd[p + ".w1"].float())
+        w1 = w1 / (w1.sum(0) + 1e-6)
+        w2 = F.relu(sd[p + ".w2"].float())
+        w2 = w2 / (w2.sum(0) + 1e-6)
+        L = n_back
+        xs = list(xx)
+        for i in range(L - 1, 0, -1):
+            f_ = _r(w1[0, i - 1] * xx[i - 1] + w1[1, i - 1] * F.interpolate(xx[i], scale_factor=2, mode="nearest"),
+                    policy)
+            xx[i - 1] = _r(_conv_bn(f_, sd, f"{p}.top-down-{i - 1}.0.weight", f"{p}.top-down-{i - 1}.1", 1, 1, True,
+                                    policy), policy)
+        for i in range(0, L - 2):
+            f_ = _r(w2[0, i] * xx[i + 1] + w2[1, i] * F.max_pool2d(xx[i], kernel_size=2) + w2[2, i] * xs[i + 1],
+                    policy)
+            xx[i + 1] = _r(_conv_bn(f_, sd, f"{p}.bottom-up-{i + 1}.0.weight", f"{p}.bottom-up-{i + 1}.1", 1, 1,
+                                    True, policy), policy)
+        f_ = _r(w1[0, L - 1] * xx[L - 1] + w1[1, L - 1] * F.max_pool2d(xx[L - 2], kernel_size=2), policy)
+        xx[L - 1] = _r(_conv_bn(f_, sd, f"{p}.bottom-up-{L - 1}.0.weight", f"{p}.bottom-up-{L - 1}.1", 1, 1, True,
+                                policy), policy)
+        s_ += 1
+    loc, conf = [], []
+    cur = None
+    for i, layer in enumerate(feature_layer[0]):                          # bifpn.py:131-139
+        stride = 1 if isinstance(layer, int) else 2
+        src = xx[i] if i < n_back else (raw_top if i == n_back else cur)
+        cur = _r(_conv_bn(src, sd, f"extras.{i}.0.weight", f"extras.{i}.1", stride, 1, True, policy), policy)
+        l, c = _shared_heads(sd, cur, training, policy)
+        loc.append(l)
+        conf.append(c)
+    return tuple(loc), tuple(conf)

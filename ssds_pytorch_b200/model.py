@@ -139,6 +139,11 @@ class _Engine(torch.nn.Module):
             flops[0] += dw.flops_per_pixel * n * ho * wo
             return y
 
+        def add_raw(fn, nflops):
+            steps.append(fn)
+            flops[0] += nflops
+
+        self._add_raw = add_raw
         feats = self._plan_backbone(packed, H, W, steps, buf, add_conv, add_dw)
         locs, confs = self._plan_neck(feats, steps, buf, add_conv, add_head)
         return {"src": src, "steps": steps, "loc": tuple(locs), "conf": tuple(confs),
@@ -295,6 +300,73 @@ class _MobileNetV2Backbone:
         return feats
 
 
+class _RegNetXBackbone:
+    """RegNetX under `backbone.` (reference nets/regnet.py:28-282): SimpleStemIN 3x3/s2 (3->32), stages of
+    ResBottleneckBlocks: a 1x1 -> b 3x3 grouped (group width 48, stride) -> c 1x1, + identity or 1x1/s
+    projection, ReLU.  Channel counts are zero-padded to a multiple of 96 (= lcm(48, 32): two groups per
+    block-diagonal chunk of the chunked igemm); padded channels stay exactly 0."""
+    GROUP_W, CHUNK = 48, 96
+
+    def _build_backbone(self, sd, feature_layer):
+        dev = self.device
+        self.outputs = [l for l in feature_layer[0] if isinstance(l, int)]
+        self.stem = _Conv(sd["backbone.stem.conv.weight"], _bn(sd, "backbone.stem.bn"), None, 2, 1, 1, dev,
+                          stem=True)
+        self.layers = []
+        pad = lambda c: _cpad(c, self.CHUNK)
+        cin_pad = 32
+        for si in range(1, 5):
+            if si > max(self.outputs):
+                break
+            blocks = []
+            bi = 1
+            while f"backbone.s{si}.b{bi}.f.a.weight" in sd:
+                p = f"backbone.s{si}.b{bi}"
+                stride = 2 if bi == 1 else 1
+                w_b = sd[p + ".f.a.weight"].shape[0]
+                w_out = sd[p + ".f.c.weight"].shape[0]
+                if sd[p + ".f.b.weight"].shape[1] != self.GROUP_W:
+                    raise NotImplementedError("only group width 48 (RegNetX-3.2GF family) is packed here")
+                blk = {
+                    "a": _Conv(sd[p + ".f.a.weight"], _bn(sd, p + ".f.a_bn"), None, 1, 0, 1, dev,
+                               cin_pad=cin_pad, cout_pad=pad(w_b)),
+                    "b_w": K.pack_grouped_weight(K.fold_bn(sd[p + ".f.b.weight"], _bn(sd, p + ".f.b_bn"), None)[0],
+                                                 self.CHUNK, pad(w_b)).to(dev),
+                    "b_stride": stride,
+                    "c": _Conv(sd[p + ".f.c.weight"], _bn(sd, p + ".f.c_bn"), None, 1, 0, 1, dev,
+                               cin_pad=pad(w_b), cout_pad=pad(w_out)),
+                }
+                bb = K.fold_bn(sd[p + ".f.b.weight"], _bn(sd, p + ".f.b_bn"), None)[1]
+                blk["b_bias"] = torch.cat([bb, torch.zeros(pad(w_b) - w_b)], 0).contiguous().to(dev)
+                blk["b_flops"] = 2 * 9 * self.GROUP_W * w_b
+                if (p + ".proj.weight") in sd:
+                    blk["proj"] = _Conv(sd[p + ".proj.weight"], _bn(sd, p + ".bn"), None, stride, 0, 0, dev,
+                                        cin_pad=cin_pad, cout_pad=pad(w_out))
+                blocks.append(blk)
+                cin_pad = pad(w_out)
+                bi += 1
+            self.layers.append(blocks)
+
+    def _plan_backbone(self, packed, H, W, steps, buf, add_conv, add_dw):
+        x = add_conv(self.stem, packed, Ho=H // 2, Wo=W // 2, x_kind=1, x_width=W // 2)
+        feats = []
+        for si, blocks in enumerate(self.layers, start=1):
+            for blk in blocks:
+                identity = add_conv(blk["proj"], x) if "proj" in blk else x
+                y = add_conv(blk["a"], x)
+                n, h, w, c = y.shape
+                s_ = blk["b_stride"]
+                ho, wo = (h - 1) // s_ + 1, (w - 1) // s_ + 1
+                yb = buf(n, ho, wo, c)
+                self._add_raw(lambda y=y, blk=blk, yb=yb, s_=s_: K.conv2d(
+                    y, blk["b_w"], blk["b_bias"], 3, 3, s_, 1, True, out=yb, chunk=self.CHUNK),
+                    blk["b_flops"] * n * ho * wo)
+                x = add_conv(blk["c"], yb, residual=identity, relu=True)
+            if si in self.outputs:
+                feats.append(x)
+        return feats
+
+
 class _SSDNeck:
     """SSD extras (ConvBNReLUx2, layers_parser.py:17-20) + per-level fused loc/conf heads
     (ssd.py:42-104).  Input channel counts may be padded (see _MobileNetV2Backbone)."""
@@ -354,15 +426,18 @@ class _FPNNeck:
     def _build_neck(self, sd, feature_layer):
         dev = self.device
         n_back = len(self.outputs)
+        cpad = getattr(self, "CHUNK", 32)       # the backbone's channel padding (RegNet: 96)
         self.transforms = [_Conv(sd[f"transforms.{i}.weight"], None, sd[f"transforms.{i}.bias"], 1, 0,
-                                 False, dev) for i in range(n_back)]
+                                 False, dev, cin_pad=_cpad(sd[f"transforms.{i}.weight"].shape[1], cpad))
+                           for i in range(n_back)]
         self.extras = []
         for i, layer in enumerate(feature_layer[0]):
             stride = 1 if isinstance(layer, int) else 2
             if not isinstance(layer, int) and layer != "Conv:S":
                 raise ValueError(layer + " does not support by SSDFPN")       # fpn.py:144
-            self.extras.append(_Conv(sd[f"extras.{i}.0.weight"], _bn(sd, f"extras.{i}.1"), None, stride, 1,
-                                     True, dev))
+            w = sd[f"extras.{i}.0.weight"]
+            self.extras.append(_Conv(w, _bn(sd, f"extras.{i}.1"), None, stride, 1, True, dev,
+                                     cin_pad=_cpad(w.shape[1], cpad) if i == n_back else None))
         nb = self.number_box[0]
         if any(b != nb for b in self.number_box):
             raise ValueError("For SSDFPN module, the number of box have to be same in every layer")
@@ -378,9 +453,8 @@ class _FPNNeck:
         self.head_conf = _Conv(sd["conf.4.weight"], None, sd["conf.4.bias"], 1, 1, False, dev)
         self.head_conf.n_loc = 0                                 # every channel goes to `conf`
 
-    def _plan_neck(self, feats, steps, buf, add_conv, add_head):
+    def _plan_pyramid(self, feats, steps, buf, add_conv):
         n_back = len(feats)
-        raw_top = feats[-1]
         pyr = [None] * n_back
         for i in range(n_back - 1, -1, -1):            # fpn.py:79-87
             lat = add_conv(self.transforms[i], feats[i])
@@ -388,6 +462,12 @@ class _FPNNeck:
                 coarse = pyr[i + 1]
                 steps.append(lambda c=coarse, f=lat: K.upsample2x_add(c, f))
             pyr[i] = lat
+        return pyr
+
+    def _plan_neck(self, feats, steps, buf, add_conv, add_head):
+        n_back = len(feats)
+        raw_top = feats[-1]
+        pyr = self._plan_pyramid(feats, steps, buf, add_conv)
         levels = []
         xx = None
         for i, ex in enumerate(self.extras):           # fpn.py:89-95
@@ -417,6 +497,55 @@ class _FPNNeck:
         return locs, confs
 
 
+class _BiFPNNeck(_FPNNeck):
+    """SSDBiFPN (EfficientDet-style, reference bifpn.py:10-142): 1x1 laterals (no top-down add), then
+    `num_stack` BiFPNModules — relu-normalised scalar weights (host side, bifpn.py:35-38), weighted
+    top-down (nearest up) and bottom-up (2x2 max-pool) fusions, each followed by ConvBNReLU 3x3 — then the
+    same extras and shared towers as SSDFPN."""
+
+    def _build_neck(self, sd, feature_layer):
+        super()._build_neck(sd, feature_layer)
+        dev = self.device
+        self.bifpn = []
+        s_ = 0
+        while f"stack_bifpn.{s_}.w1" in sd:
+            p = f"stack_bifpn.{s_}"
+            w1 = torch.relu(sd[p + ".w1"].float())
+            w1 = w1 / (w1.sum(0) + 1e-6)
+            w2 = torch.relu(sd[p + ".w2"].float())
+            w2 = w2 / (w2.sum(0) + 1e-6)
+            levels = w1.shape[1]
+            mod = {"w1": w1.tolist(), "w2": w2.tolist(), "levels": levels, "td": {}, "bu": {}}
+            for i in range(levels - 1):
+                mod["td"][i] = _Conv(sd[f"{p}.top-down-{i}.0.weight"], _bn(sd, f"{p}.top-down-{i}.1"), None,
+                                     1, 1, True, dev)
+                mod["bu"][i + 1] = _Conv(sd[f"{p}.bottom-up-{i + 1}.0.weight"],
+                                         _bn(sd, f"{p}.bottom-up-{i + 1}.1"), None, 1, 1, True, dev)
+            self.bifpn.append(mod)
+            s_ += 1
+
+    def _plan_pyramid(self, feats, steps, buf, add_conv):
+        xx = [add_conv(self.transforms[i], f) for i, f in enumerate(feats)]      # bifpn.py:127-128
+        for mod in self.bifpn:                                                    # bifpn.py:30-63
+            L, w1, w2 = mod["levels"], mod["w1"], mod["w2"]
+            xs = list(xx)
+            for i in range(L - 1, 0, -1):
+                fused = buf(*xx[i - 1].shape)
+                steps.append(lambda a=xx[i - 1], b=xx[i], o=fused, wa=w1[0][i - 1], wb=w1[1][i - 1]:
+                             K.bifpn_fuse(a, b, wa, wb, mode=0, out=o))
+                xx[i - 1] = add_conv(mod["td"][i - 1], fused)
+            for i in range(0, L - 2):
+                fused = buf(*xx[i + 1].shape)
+                steps.append(lambda a=xx[i + 1], b=xx[i], c=xs[i + 1], o=fused, wa=w2[0][i], wb=w2[1][i],
+                             wc=w2[2][i]: K.bifpn_fuse(a, b, wa, wb, c=c, w2=wc, mode=1, out=o))
+                xx[i + 1] = add_conv(mod["bu"][i + 1], fused)
+            fused = buf(*xx[L - 1].shape)
+            steps.append(lambda a=xx[L - 1], b=xx[L - 2], o=fused, wa=w1[0][L - 1], wb=w1[1][L - 1]:
+                         K.bifpn_fuse(a, b, wa, wb, mode=1, out=o))
+            xx[L - 1] = add_conv(mod["bu"][L - 1], fused)
+        return xx
+
+
 class SSDResNet(_SSDNeck, _ResNetBackbone, _Engine):
     """SSD + ResNet18/34/50/101/152 (reference cfg SSDS='SSD', NETS='ResNet*')."""
 
@@ -429,8 +558,21 @@ class SSDMobileNetV2(_SSDNeck, _MobileNetV2Backbone, _Engine):
     """SSD + MobileNetV2 (reference cfg SSDS='SSD', NETS='MobileNetV2'; BASELINE configs[0]/[2])."""
 
 
+class SSDBiFPNResNet(_BiFPNNeck, _ResNetBackbone, _Engine):
+    """SSDBiFPN + ResNet."""
+
+
+class SSDBiFPNRegNetX(_BiFPNNeck, _RegNetXBackbone, _Engine):
+    """SSDBiFPN + RegNetX (group width 48: RegNetX-3.2GF; BASELINE configs[4])."""
+
+
+class SSDFPNRegNetX(_FPNNeck, _RegNetXBackbone, _Engine):
+    """SSDFPN + RegNetX."""
+
+
 ENGINES = {("SSD", "ResNet"): SSDResNet, ("SSDFPN", "ResNet"): SSDFPNResNet,
-           ("SSD", "MobileNetV2"): SSDMobileNetV2}
+           ("SSD", "MobileNetV2"): SSDMobileNetV2, ("SSDBIFPN", "ResNet"): SSDBiFPNResNet,
+           ("SSDBIFPN", "RegNetX032"): SSDBiFPNRegNetX, ("SSDFPN", "RegNetX032"): SSDFPNRegNetX}
 
 
 def engine_for(ssds, nets):

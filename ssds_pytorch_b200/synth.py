@@ -83,6 +83,77 @@ def mobilenetv2_backbone_shapes():
     return out
 
 
+REGNETX032 = {"ws": [96, 192, 432, 1008], "ds": [2, 6, 15, 2], "gw": 48}
+
+
+def regnetx032_backbone_shapes():
+    """(key, shape) list of the reference RegNetX-3.2GF under `backbone.` (regnet.py:28-282, :388-401)."""
+    out = [("backbone.stem.conv.weight", (32, 3, 3, 3))]
+    _bn_keys(out, "backbone.stem.bn", 32)
+    w_in = 32
+    for si, (w, d) in enumerate(zip(REGNETX032["ws"], REGNETX032["ds"]), start=1):
+        for bi in range(1, d + 1):
+            p = f"backbone.s{si}.b{bi}"
+            stride = 2 if bi == 1 else 1
+            if w_in != w or stride != 1:
+                out.append((p + ".proj.weight", (w, w_in, 1, 1))); _bn_keys(out, p + ".bn", w)
+            out.append((p + ".f.a.weight", (w, w_in, 1, 1))); _bn_keys(out, p + ".f.a_bn", w)
+            out.append((p + ".f.b.weight", (w, REGNETX032["gw"], 3, 3))); _bn_keys(out, p + ".f.b_bn", w)
+            out.append((p + ".f.c.weight", (w, w, 1, 1))); _bn_keys(out, p + ".f.c_bn", w)
+            w_in = w
+    out.append(("backbone.head.fc.weight", (1000, w_in)))
+    out.append(("backbone.head.fc.bias", (1000,)))
+    return out
+
+
+def fpn_neck_shapes(feature_layer, number_box, num_classes, bifpn_stacks=0):
+    """transforms / extras / [stack_bifpn] / shared towers of SSDFPN (fpn.py:103-146) and SSDBiFPN
+    (bifpn.py:144-191)."""
+    out = []
+    ti = 0
+    for layer, depth in zip(feature_layer[0], feature_layer[1]):
+        if isinstance(layer, int):
+            out.append((f"transforms.{ti}.weight", (256, depth, 1, 1)))
+            out.append((f"transforms.{ti}.bias", (256,)))
+            ti += 1
+    for i, (layer, depth) in enumerate(zip(feature_layer[0], feature_layer[1])):
+        cin = 256 if isinstance(layer, int) else depth
+        out.append((f"extras.{i}.0.weight", (256, cin, 3, 3)))
+        _bn_keys(out, f"extras.{i}.1", 256)
+    for s_ in range(bifpn_stacks):
+        p = f"stack_bifpn.{s_}"
+        out.append((p + ".w1", (2, ti)))
+        out.append((p + ".w2", (3, ti - 2)))
+        for i in range(ti - 1, 0, -1):
+            out.append((f"{p}.top-down-{i - 1}.0.weight", (256, 256, 3, 3))); _bn_keys(out, f"{p}.top-down-{i - 1}.1", 256)
+        for i in range(0, ti - 1):
+            out.append((f"{p}.bottom-up-{i + 1}.0.weight", (256, 256, 3, 3))); _bn_keys(out, f"{p}.bottom-up-{i + 1}.1", 256)
+    for tower, cout in (("loc", number_box[0] * 4), ("conf", number_box[0] * num_classes)):
+        for j in range(4):
+            out.append((f"{tower}.{j}.0.weight", (256, 256, 3, 3)))
+            _bn_keys(out, f"{tower}.{j}.1", 256)
+        out.append((f"{tower}.4.weight", (cout, 256, 3, 3)))
+        out.append((f"{tower}.4.bias", (cout,)))
+    return out
+
+
+def model_shapes(ssds, nets, feature_layer, number_box, num_classes):
+    """(key, shape) list of the reference `create_model(cfg).state_dict()` for the supported models."""
+    ssds = ssds.upper()
+    if nets == "MobileNetV2":
+        back = mobilenetv2_backbone_shapes()
+    elif nets == "RegNetX032":
+        back = regnetx032_backbone_shapes()
+    else:
+        back = resnet_backbone_shapes(nets)
+    if ssds == "SSD":
+        return back + ssd_neck_shapes(feature_layer, number_box, num_classes)
+    stacks = 0
+    if ssds == "SSDBIFPN":
+        stacks = 1 if len(feature_layer) == 2 else feature_layer[2]
+    return back + fpn_neck_shapes(feature_layer, number_box, num_classes, stacks)
+
+
 def ssd_neck_shapes(feature_layer, number_box, num_classes):
     out = []
     in_ch, ei = None, 0
@@ -187,12 +258,11 @@ def synthetic_state_dict(nets, feature_layer, number_box, num_classes, seed=0, s
     g = torch.Generator().manual_seed(seed)
     sd = {}
     prior = -math.log((1 - 0.01) / 0.01)
-    shape_fn = (ssd_mobilenetv2_shapes if nets == "MobileNetV2"
-                else (ssdfpn_resnet_shapes if ssds == "SSDFPN" else ssd_resnet_shapes))
-    shapes = shape_fn(nets, feature_layer, number_box, num_classes)
+    shapes = model_shapes(ssds, nets, feature_layer, number_box, num_classes)
     bn_prefixes = {k.rsplit(".", 1)[0] for k, _ in shapes if k.endswith("running_mean")}
+    fpn_like = ssds.upper() != "SSD"
     head_final = {k for k, _ in shapes if k.startswith(("loc.", "conf.")) and
-                  k.rsplit(".", 1)[0] not in bn_prefixes and (ssds != "SSDFPN" or k.split(".")[1] == "4")}
+                  k.rsplit(".", 1)[0] not in bn_prefixes and (not fpn_like or k.split(".")[1] == "4")}
     for key, shape in shapes:
         if key.endswith("num_batches_tracked"):
             sd[key] = torch.tensor(0, dtype=torch.long)
@@ -211,7 +281,9 @@ def synthetic_state_dict(nets, feature_layer, number_box, num_classes, seed=0, s
                 sd[key] = torch.rand(shape, generator=g) * 0.4 + lo
             else:
                 sd[key] = torch.randn(shape, generator=g) * 0.1
-        elif key in head_final or (ssds != "SSDFPN" and key.startswith(("loc.", "conf."))):
+        elif key.endswith((".w1", ".w2")):           # BiFPN fusion weights (init 0.5, bifpn.py:15-16)
+            sd[key] = torch.full(shape, 0.5) if style == "init" else torch.rand(shape, generator=g) + 0.1
+        elif key in head_final or (not fpn_like and key.startswith(("loc.", "conf."))):
             if key.endswith("weight"):
                 sd[key] = torch.randn(shape, generator=g) * 0.01
             else:
@@ -225,9 +297,9 @@ def synthetic_state_dict(nets, feature_layer, number_box, num_classes, seed=0, s
                 sd[key] = (torch.rand(shape, generator=g) * 2 - 1) * a
             else:
                 sd[key] = torch.zeros(shape) if style == "init" else torch.randn(shape, generator=g) * 0.05
-        elif key.startswith(("backbone.fc", "backbone.classifier")):
+        elif key.startswith(("backbone.fc", "backbone.classifier", "backbone.head.fc")):
             sd[key] = torch.zeros(shape)
-        elif key.startswith("extras."):
+        elif key.startswith(("extras.", "stack_bifpn.")):
             fan_in = shape[1] * shape[2] * shape[3]
             fan_out = shape[0] * shape[2] * shape[3]
             a = math.sqrt(6.0 / (fan_in + fan_out))

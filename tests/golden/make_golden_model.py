@@ -34,6 +34,8 @@ tv.models.mobilenet.InvertedResidual = _mv2.InvertedResidual
 tv.models.mobilenet.ConvBNReLU = partial(tv.ops.misc.Conv2dNormActivation, norm_layer=torch.nn.BatchNorm2d,
                                          activation_layer=torch.nn.ReLU6)
 
+from ssds.modeling.nets import regnet as _regnet               # noqa: E402
+_regnet.RegNet.initialize = lambda self: None                 # hard-coded URLs: no network here
 from ssds.core import config as rcfg                          # noqa: E402
 from ssds.modeling import model_builder                       # noqa: E402
 from ssds_pytorch_b200 import synth                           # noqa: E402  (pure python part only)
@@ -60,6 +62,9 @@ def main():
         # BASELINE configs[0]/[2] model: SSD + MobileNetV2 at 300x300 (SURVEY 8a cfg 1b geometry)
         "mbv2": ("SSD", "MobileNetV2", [[5, 7, "Conv:S", "Conv:S", "Conv:S", "Conv:S"],
                                         [96, 320, 512, 256, 256, 128]], [300, 300], 20, 1),
+        # BASELINE configs[4] model: SSDBiFPN + RegNetX-3.2GF (SURVEY 8a cfg 5 geometry), small image
+        "bifpn": ("SSDBiFPN", "RegNetX032", [[2, 3, 4, "Conv:S", "Conv:S"], [192, 432, 1008, 1008, 256]],
+                  [128, 128], 20, 1),
     }
     for tag, (ssds, nets, fl, image, ncls, B) in cases.items():
         L = len(fl[0])
@@ -68,9 +73,7 @@ def main():
         cfg, model = build(nets, fl, [list(s) for s in sizes], ratios, image, ncls, ssds)
         ref_sd = model.state_dict()
         nb = [6] * L
-        shape_fn = (synth.ssd_mobilenetv2_shapes if nets == "MobileNetV2" else
-                    (synth.ssdfpn_resnet_shapes if ssds == "SSDFPN" else synth.ssd_resnet_shapes))
-        shapes = shape_fn(nets, fl, nb, ncls)
+        shapes = synth.model_shapes(ssds, nets, fl, nb, ncls)
         assert [k for k, _ in shapes] == list(ref_sd.keys()), "state_dict key order differs"
         for k, s in shapes:
             assert tuple(ref_sd[k].shape) == tuple(s), (k, ref_sd[k].shape, s)

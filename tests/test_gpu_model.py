@@ -16,6 +16,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 CASES = {
+    "bifpn": ("RegNetX032", [[2, 3, 4, "Conv:S", "Conv:S"], [192, 432, 1008, 1008, 256]], 20, 2, [128, 128]),
     "mbv2": ("MobileNetV2", [[5, 7, "Conv:S", "Conv:S", "Conv:S", "Conv:S"], [96, 320, 512, 256, 256, 128]], 20, 2,
              [300, 300]),
     "fpn50": ("ResNet50", [[3, 4, 5, "Conv:S", "Conv:S"], [512, 1024, 2048, 2048, 256]], 20, 2, [256, 256]),
@@ -40,14 +41,14 @@ def build(tag, S):
     from ssds_pytorch_b200.model import engine_for
     nets, fl, ncls, B, image = CASES[tag]
     L = len(fl[0])
-    ssds = "SSDFPN" if tag.startswith("fpn") else "SSD"
+    ssds = {"fpn50": "SSDFPN", "bifpn": "SSDBiFPN"}.get(tag, "SSD")
     sd = synth.synthetic_state_dict(nets, fl, [6] * L, ncls, seed=11, style="test", ssds=ssds)
     x = torch.rand((B, 3, image[0], image[1]), generator=torch.Generator().manual_seed(1234))
     model = engine_for(ssds, nets)(sd, fl, ncls, [6] * L, device="cuda").eval()
     return sd, fl, x, model, image, ncls
 
 
-@pytest.mark.parametrize("tag", ["r18", "r50", "fpn50", "mbv2"])
+@pytest.mark.parametrize("tag", ["r18", "r50", "fpn50", "mbv2", "bifpn"])
 def test_conv_stack_vs_oracle_bf16_policy(env, tag):
     from oracle import model_oracle as M
     sd, fl, x, model, image, ncls = build(tag, env)
@@ -55,7 +56,8 @@ def test_conv_stack_vs_oracle_bf16_policy(env, tag):
     torch.cuda.synchronize()
     sd_gpu = {k: v.cuda() for k, v in sd.items()}
     with torch.no_grad():
-        fwd = {"fpn50": M.ssdfpn_resnet_forward, "mbv2": M.ssd_mobilenetv2_forward}.get(tag, M.ssd_resnet_forward)
+        fwd = {"fpn50": M.ssdfpn_resnet_forward, "mbv2": M.ssd_mobilenetv2_forward,
+               "bifpn": M.ssdbifpn_forward}.get(tag, M.ssd_resnet_forward)
         rloc, rconf = fwd(sd_gpu, x.cuda(), fl, training=False, policy="bf16")
     worst_l = worst_c = 0.0
     for l, c, rl, rc in zip(loc, conf, rloc, rconf):

@@ -18,23 +18,24 @@ CASES = {
     "r18": ("ResNet18", [[3, 4, 5, "Conv:S"], [128, 256, 512, 256]], 20, 3),
     "fpn50": ("ResNet50", [[3, 4, 5, "Conv:S", "Conv:S"], [512, 1024, 2048, 2048, 256]], 20, 1),
     "mbv2": ("MobileNetV2", [[5, 7, "Conv:S", "Conv:S", "Conv:S", "Conv:S"], [96, 320, 512, 256, 256, 128]], 20, 1),
+    "bifpn": ("RegNetX032", [[2, 3, 4, "Conv:S", "Conv:S"], [192, 432, 1008, 1008, 256]], 20, 1),
 }
+SSDS = {"fpn50": "SSDFPN", "bifpn": "SSDBiFPN"}
 
 FWD = {"r18": M.ssd_resnet_forward, "r50": M.ssd_resnet_forward, "fpn50": M.ssdfpn_resnet_forward,
-       "mbv2": M.ssd_mobilenetv2_forward}
+       "mbv2": M.ssd_mobilenetv2_forward, "bifpn": M.ssdbifpn_forward}
 
 
 def case_inputs(tag, gold):
     nets, fl, ncls, B = CASES[tag]
     L = len(fl[0])
-    sd = synth.synthetic_state_dict(nets, fl, [6] * L, ncls, seed=11, style="test",
-                                    ssds="SSDFPN" if tag.startswith("fpn") else "SSD")
+    sd = synth.synthetic_state_dict(nets, fl, [6] * L, ncls, seed=11, style="test", ssds=SSDS.get(tag, "SSD"))
     image = [int(v) for v in gold[tag + "_image"]]
     x = torch.rand((B, 3, image[0], image[1]), generator=torch.Generator().manual_seed(1234))
     return sd, fl, x, image, ncls
 
 
-@pytest.mark.parametrize("tag", ["r18", "r50", "fpn50", "mbv2"])
+@pytest.mark.parametrize("tag", ["r18", "r50", "fpn50", "mbv2", "bifpn"])
 def test_model_oracle_matches_reference_module(tag):
     gold = np.load(GOLD)
     sd, fl, x, image, ncls = case_inputs(tag, gold)
