@@ -450,8 +450,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int i = 0; i < R; ++i) arm_next();
       // With 4 slots the engine lets two stores stay in flight (waiting for the read of store g right
       // after issuing it would cap the store rate at one 16 KiB sub-tile per smem-read latency)
-      // (not for residual layers: there the re-arm IS the residual prefetch and must run as far ahead
-      // as possible — measured: lag 2 made the conv3 layers 15 % slower)
+      // Residual layers: lag 1 — the re-arm IS the residual prefetch and must run as far ahead as
+      // possible (R-1 chunks) without ever waiting for the store just issued (measured: lag 0 and
+      // lag 2 both make the conv3 layers 12-15 % slower than lag 1).
       const bool lag2 = (R >= 4) && !has_res;
       int g = 0;
       for (int group = blockIdx.x; group < num_groups; group += gridDim.x) {
@@ -470,8 +471,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 tma_store_wait_read<2>(); // store g-2 has been read out of smem -> its slot is free
                 arm_next();               // = chunk g-2+R
               }
+            } else if (has_res) {
+              if (g >= 1) {
+                tma_store_wait_read<1>(); // store g-1 has been read out of smem -> its slot is free
+                arm_next();               // = chunk g-1+R: residual prefetched R-1 chunks ahead
+              }
             } else {
-              tma_store_wait_read<0>();   // store g has been read out of smem -> its slot is free
+              tma_store_wait_read<0>();   // 2 slots: store g must be read before its slot is re-armed
               arm_next();                 // = chunk g+R
             }
           }

@@ -219,9 +219,10 @@ __global__ void __launch_bounds__(DEC_NT)
 decode_finalize(const __grid_constant__ DecodeParams p, void* __restrict__ ws,
                 float* __restrict__ out_scores, float* __restrict__ out_boxes,
                 float* __restrict__ out_classes, int32_t* __restrict__ out_index) {
-  extern __shared__ __align__(16) unsigned long long buf[];  // [p.cap]
+  extern __shared__ __align__(16) unsigned long long buf[];  // [p.cap + p.K]
   __shared__ int s_cnt;
-  __shared__ unsigned long long s_thr;
+  __shared__ unsigned long long s_thr, s_kth;
+  __shared__ int s_scratch[260];
 
   const int l = blockIdx.x, b = blockIdx.y;
   const int L = p.n_levels, K = p.K;
@@ -249,9 +250,12 @@ decode_finalize(const __grid_constant__ DecodeParams p, void* __restrict__ ws,
       take[e] = (i < ncand) && (k[e] > cur);
     }
     const int fill = topk_append<DEC_EPT>(buf, &s_cnt, k, take);
-    if (__syncthreads_or(fill > limit)) topk_prune<DEC_NT>(buf, &s_cnt, &s_thr, K);
+    if (__syncthreads_or(fill > limit))
+      topk_prune_select<DEC_NT>(buf, buf + p.cap, &s_cnt, &s_thr, K, s_scratch, &s_kth);
   }
-  topk_prune<DEC_NT>(buf, &s_cnt, &s_thr, K);
+  __syncthreads();
+  topk_prune_select<DEC_NT>(buf, buf + p.cap, &s_cnt, &s_thr, K, s_scratch, &s_kth);  // -> <= K keys
+  topk_prune<DEC_NT>(buf, &s_cnt, &s_thr, K);                                       // one small sort
   const int nout = min(s_cnt, K);
 
   const int W = lv.W, H = lv.H, C = lv.C;
