@@ -95,6 +95,7 @@ class _Engine(torch.nn.Module):
             N, _, H, W = images.shape
         steps = []          # list of zero-arg callables
         flops = [0]
+        split = [None]
         bf = torch.bfloat16
 
         def buf(n, h, w, c):
@@ -126,6 +127,8 @@ class _Engine(torch.nn.Module):
                 loc = torch.empty((n, h.n_loc, fh, fw), dtype=torch.float32, device=dev)
             if conf is None:
                 conf = torch.empty((n, h.cout - h.n_loc, fh, fw), dtype=torch.float32, device=dev)
+            if split[0] is None:
+                split[0] = len(steps)          # first launch that writes the loc/conf outputs
             steps.append(lambda: K.conv2d_head(f, h.w, h.bias, h.n_loc, not self.training,
                                                loc=loc, conf=conf))
             flops[0] += h.flops_per_pixel * n * fh * fw
@@ -147,7 +150,8 @@ class _Engine(torch.nn.Module):
         feats = self._plan_backbone(packed, H, W, steps, buf, add_conv, add_dw)
         locs, confs = self._plan_neck(feats, steps, buf, add_conv, add_head)
         return {"src": src, "steps": steps, "loc": tuple(locs), "conf": tuple(confs),
-                "flops": flops[0], "graph": None, "launches": len(steps)}
+                "flops": flops[0], "graph": None, "launches": len(steps),
+                "split": split[0] if split[0] is not None else len(steps)}
 
     def plan_for(self, images):
         key = (tuple(images.shape), images.dtype, self.training)
@@ -156,24 +160,36 @@ class _Engine(torch.nn.Module):
             plan = self._plans[key] = self._build_plan(images)
         return plan
 
-    def run_plan(self, plan, use_graph=False):
+    def run_plan(self, plan, use_graph=False, outputs_free=None):
+        """Replay the recorded launches.  `outputs_free` (a CUDA event) is waited for right before the
+        first launch that overwrites the loc/conf outputs, so that a consumer of the PREVIOUS step's
+        outputs (decode/NMS on another stream) can overlap this step's backbone."""
+        k = plan["split"]
         if use_graph:
             if plan["graph"] is None:
                 for s in plan["steps"]:                # warm-up: sets kernel attributes etc.
                     s()
                 torch.cuda.synchronize(self.device)
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    for s in plan["steps"]:
-                        s()
-                plan["graph"] = g
-            plan["graph"].replay()
+                graphs = []
+                for part in (plan["steps"][:k], plan["steps"][k:]):
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        for s in part:
+                            s()
+                    graphs.append(g)
+                plan["graph"] = graphs
+            plan["graph"][0].replay()
+            if outputs_free is not None:
+                torch.cuda.current_stream().wait_event(outputs_free)
+            plan["graph"][1].replay()
         else:
-            for s in plan["steps"]:
+            for i, s in enumerate(plan["steps"]):
+                if i == k and outputs_free is not None:
+                    torch.cuda.current_stream().wait_event(outputs_free)
                 s()
         return plan["loc"], plan["conf"]
 
-    def forward(self, x, use_graph=False):
+    def forward(self, x, use_graph=False, outputs_free=None):
         """x: fp32 NCHW [B,3,H,W] (already `(img-mean)/std`-normalised if mean/std were left at
         0/1) or uint8 NHWC [B,H,W,3].  Returns (tuple loc, tuple conf) like ssd.py:42-74."""
         if not x.is_cuda:
@@ -181,7 +197,7 @@ class _Engine(torch.nn.Module):
         x = x.contiguous()
         plan = self.plan_for(x)
         plan["src"].copy_(x, non_blocking=True)
-        return self.run_plan(plan, use_graph)
+        return self.run_plan(plan, use_graph, outputs_free)
 
     def eval(self):
         self.training = False

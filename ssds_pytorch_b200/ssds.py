@@ -72,14 +72,38 @@ class SSDDetector(object):
         self.use_graph = use_graph
         self._stage = {}
         self._copy_stream = None
+        self._post_stream = None        # decode + NMS of step i overlap the backbone of step i+1
+        self._post_done = None
 
     # -------------------------------------------------------------- device-side entry points
-    def detect_device(self, images):
+    def detect_device(self, images, overlap=False):
         """images already on the GPU: uint8 NHWC [B,H,W,3] (raw pixels) or fp32 NCHW [B,3,H,W] raw
         pixel values; normalisation (x-mean)/std (ssds.py:57) is fused into the first kernel.
-        Returns device tensors (scores [B,D], boxes [B,D,4], classes [B,D])."""
-        loc, conf = self.model(images, use_graph=self.use_graph)
-        return self.decoder(loc, conf, self.anchors)
+        Returns device tensors (scores [B,D], boxes [B,D,4], classes [B,D]).
+
+        overlap=True runs decode + NMS on a side stream so that they overlap the conv stack of the next
+        call (the memory-/latency-bound post-processing hides behind tensor-core work); the results are
+        then produced on that stream — call `join()` (or use `detect_host`) before consuming them."""
+        if not overlap:
+            loc, conf = self.model(images, use_graph=self.use_graph)
+            return self.decoder(loc, conf, self.anchors)
+        if self._post_stream is None:
+            self._post_stream = torch.cuda.Stream(device=self.device)
+        main = torch.cuda.current_stream()
+        loc, conf = self.model(images, use_graph=self.use_graph, outputs_free=self._post_done)
+        heads_done = torch.cuda.Event()
+        heads_done.record(main)
+        with torch.cuda.stream(self._post_stream):
+            self._post_stream.wait_event(heads_done)
+            out = self.decoder(loc, conf, self.anchors)
+            self._post_done = torch.cuda.Event()
+            self._post_done.record(self._post_stream)
+        return out
+
+    def join(self):
+        """Make the current stream wait for the side-stream post-processing of the last call."""
+        if self._post_done is not None:
+            torch.cuda.current_stream().wait_event(self._post_done)
 
     def detect_host(self, imgs, out=None, slot=0, gather=False):
         """Host numpy/torch batch -> pinned staging -> H2D -> detect -> [all-gather] -> packed
@@ -108,19 +132,22 @@ class SSDDetector(object):
             st["dev_in"].copy_(t, non_blocking=True)
             st["copied"].record()
         cur.wait_event(st["copied"])
-        s, b, c = self.detect_device(st["dev_in"])
-        st["consumed"].record()
-        o = st["dev_out"]
-        o[:, :, 0] = s
-        o[:, :, 1:5] = b
-        o[:, :, 5] = c
-        if gather:
-            o = gather_detections(o)
-        if out is None:
-            if st["pin_out"] is None or st["pin_out"].shape != o.shape:
-                st["pin_out"] = torch.empty(o.shape, dtype=torch.float32).pin_memory()
-            out = st["pin_out"]
-        out.copy_(o, non_blocking=True)
+        s, b, c = self.detect_device(st["dev_in"], overlap=True)
+        st["consumed"].record()          # (the plan copied dev_in into its own buffer first)
+        with torch.cuda.stream(self._post_stream):      # packing, all-gather and D2H ride with decode/NMS
+            o = st["dev_out"]
+            o[:, :, 0] = s
+            o[:, :, 1:5] = b
+            o[:, :, 5] = c
+            if gather:
+                o = gather_detections(o)
+            if out is None:
+                if st["pin_out"] is None or st["pin_out"].shape != o.shape:
+                    st["pin_out"] = torch.empty(o.shape, dtype=torch.float32).pin_memory()
+                out = st["pin_out"]
+            out.copy_(o, non_blocking=True)
+            self._post_done = torch.cuda.Event()
+            self._post_done.record(self._post_stream)
         return out
 
     # -------------------------------------------------------------- reference-compatible call
@@ -141,6 +168,7 @@ class SSDDetector(object):
             batch = np.ascontiguousarray(imgs, dtype=np.float32)
         with torch.cuda.device(self.device):
             det = self.detect_host(batch)
+            self.join()
             torch.cuda.current_stream().synchronize()
         det = det.numpy()
         out_scores, out_boxes, out_classes = det[:, :, 0].copy(), det[:, :, 1:5].copy(), det[:, :, 5].copy()
