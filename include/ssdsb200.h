@@ -138,6 +138,29 @@ SSDSB_API int ssdsb_multibox_loss_sum(const float* d_logits /*[B,A,C,H,W]*/,
                                       size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Focal / SmoothL1 / IoU-family losses, forward.  reference: ssds/core/criterion.py
+ * FocalLoss :95-108, SmoothL1Loss :138-151, IOULoss :175-239; masking / summation as the caller does
+ * (pipeline_anchor_basic.py:76-97).
+ *  - ssdsb_focal_loss / ssdsb_loc_loss        drop-in, unreduced outputs.
+ *  - ssdsb_focal_loss_sum / ssdsb_loc_loss_sum fused: per image sum(loss * (depth >= 0)) (cls, class
+ *    taken from depth) and sum(loss * (depth > 0)) (loc); + number of positives.
+ * loc `type`: 0 SmoothL1 (beta), 1 iou, 2 giou, 3 diou, 4 ciou.  pred/target deltas [B,A,4,H,W];
+ * unreduced loc output is [B,A,4,H,W] for SmoothL1 and [B,A,1,H,W] for the IoU family.
+ * ------------------------------------------------------------------------------------------- */
+SSDSB_API size_t ssdsb_loss_sum_workspace_bytes(int B, int A, int H, int W);
+SSDSB_API int ssdsb_focal_loss(const float* d_logits, const float* d_target, int B, int A, int C, int H,
+                               int W, float alpha, float gamma, float* d_out, void* stream);
+SSDSB_API int ssdsb_focal_loss_sum(const float* d_logits, const float* d_depth, int B, int A, int C, int H,
+                                   int W, float alpha, float gamma, float* d_loss_sum /*[B]*/,
+                                   float* d_num_pos /*[B]*/, void* d_workspace, size_t workspace_bytes,
+                                   void* stream);
+SSDSB_API int ssdsb_loc_loss(const float* d_pred, const float* d_target, int B, int A, int H, int W,
+                             int type, float beta, float* d_out, void* stream);
+SSDSB_API int ssdsb_loc_loss_sum(const float* d_pred, const float* d_target, const float* d_depth, int B,
+                                 int A, int H, int W, int type, float beta, float* d_loss_sum /*[B]*/,
+                                 void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Conv stack (tcgen05 / TMA implicit GEMM), bf16 x bf16 -> fp32 accumulate.
  * One call replaces nn.Conv2d -> BatchNorm2d(eval, folded) -> [+ residual] -> [ReLU] of the
  * reference model graph (ssds/modeling/ssds/ssd.py:42-74, nets/resnet.py:41-56, torchvision

@@ -42,7 +42,6 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int UMMA_K = 16;
 constexpr int CONV_NT = 384;          // 4 control warps + 8 epilogue warps
-constexpr int EPI_THREADS = 256;
 
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -120,9 +119,6 @@ __device__ __forceinline__ void tma_store_wait_read() {
 }
 __device__ __forceinline__ void tma_store_wait_all() {
   asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-}
-__device__ __forceinline__ void epi_bar_sync() {   // the 256 epilogue threads only
-  asm volatile("bar.sync 1, 256;" ::: "memory");
 }
 __device__ __forceinline__ void tcgen05_fence_before() {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

@@ -243,7 +243,7 @@ extern "C" int ssdsb_bifpn_fuse_nhwc_bf16(const void* d_a, const void* d_b, cons
   SSDSB_REQUIRE(mode == 0 || mode == 1, "bifpn_fuse: mode=%d (0 top-down, 1 bottom-up)", mode);
   SSDSB_REQUIRE(N >= 1 && H >= 1 && W >= 1 && C >= 8 && C % 8 == 0, "bifpn_fuse: bad shape");
   SSDSB_REQUIRE(mode == 1 || ((H % 2) == 0 && (W % 2) == 0), "bifpn_fuse: top-down needs an even-sized map");
-  SSDSB_REQUIRE(mode == 0 || d_c == nullptr || true, "bifpn_fuse");
+  SSDSB_REQUIRE(mode == 1 || d_c == nullptr, "bifpn_fuse: the third input only exists bottom-up (mode 1)");
   SSDSB_REQUIRE((((uintptr_t)d_a | (uintptr_t)d_b | (uintptr_t)d_c | (uintptr_t)d_out) & 15) == 0,
                 "bifpn_fuse: pointers must be 16-byte aligned");
   const size_t total = (size_t)N * H * W * (C / 8);
