@@ -386,3 +386,101 @@ def multibox_loss_reduced(pred_logits, target, depth, negpos_ratio=3):
     sums = (loss * m).reshape(B, -1).astype(np.float64).sum(axis=1)
     npos = (depth > 0).reshape(B, -1).sum(axis=1)
     return sums, npos
+
+
+# --------------------------------------------------------------------------- #
+# Focal / SmoothL1 / IoU-family losses
+# --------------------------------------------------------------------------- #
+def focal_loss(pred_logits, target, alpha=0.25, gamma=2):
+    """reference criterion.py:95-108 — alpha_t * (1 - p_t)^gamma * BCEWithLogits, unreduced."""
+    x = np.asarray(pred_logits, dtype=f32)
+    t = np.asarray(target, dtype=f32)
+    p = (f32(1) / (f32(1) + np.exp(-x).astype(f32))).astype(f32)
+    ce = bce_with_logits(x, t)
+    a = (t * f32(alpha) + (f32(1) - t) * f32(1 - alpha)).astype(f32)
+    pt = np.where(t == 1, p, f32(1) - p).astype(f32)
+    return (a * (f32(1) - pt) ** f32(gamma) * ce).astype(f32)
+
+
+def smooth_l1_loss(pred, target, beta=0.11):
+    """reference criterion.py:138-151."""
+    x = np.abs(np.asarray(pred, dtype=f32) - np.asarray(target, dtype=f32)).astype(f32)
+    b = f32(beta)
+    return np.where(x >= b, x - f32(0.5) * b, f32(0.5) * x * x / b).astype(f32)
+
+
+def _delta2ltrb(d):
+    """reference criterion.py:233-239: [B,A,4,H,W] (x, y, log w, log h) -> ltrb."""
+    ctr = d[:, :, :2]
+    wh = np.exp(d[:, :, 2:]).astype(f32)
+    return np.concatenate([ctr - f32(0.5) * wh, ctr + f32(0.5) * wh], axis=2).astype(f32)
+
+
+def iou_loss(pred, target, loss_type="iou"):
+    """reference criterion.py:175-231; pred/target [B,A,4,H,W] deltas -> [B,A,1,H,W]."""
+    pred = np.asarray(pred, dtype=f32)
+    target = np.asarray(target, dtype=f32)
+    p, t = _delta2ltrb(pred), _delta2ltrb(target)
+    eps = f32(1e-7)
+
+    def area(lt, rb):
+        en = (lt < rb).all(axis=2).astype(f32)
+        return ((rb - lt).prod(axis=2) * en).astype(f32)
+
+    lt = np.maximum(p[:, :, :2], t[:, :, :2])
+    rb = np.minimum(p[:, :, 2:], t[:, :, 2:])
+    area_i = area(lt, rb)
+    area_a = np.exp(pred[:, :, 2:]).astype(f32).prod(axis=2).astype(f32)       # prod(pred_wh), :188
+    area_b = np.exp(target[:, :, 2:]).astype(f32).prod(axis=2).astype(f32)
+    area_u = (area_a + area_b - area_i).astype(f32)
+    iou = ((area_i + eps) / (area_u + eps)).astype(f32)
+    if loss_type == "iou":
+        return (f32(1) - np.clip(iou, 0, 1))[:, :, None].astype(f32)
+    olt = np.minimum(p[:, :, :2], t[:, :, :2])
+    orb = np.maximum(p[:, :, 2:], t[:, :, 2:])
+    if loss_type == "giou":
+        area_o = (area(olt, orb) + eps).astype(f32)
+        g = (iou - (area_o - area_u) / area_o).astype(f32)
+        return (f32(1) - np.clip(g, -1, 1))[:, :, None].astype(f32)
+    inter_diag = ((pred[:, :, :2] - target[:, :, :2]) ** 2).sum(axis=2).astype(f32)
+    outer_diag = (((orb - olt) ** 2).sum(axis=2) + eps).astype(f32)
+    if loss_type == "diou":
+        d = (iou - inter_diag / outer_diag).astype(f32)
+        return (f32(1) - np.clip(d, -1, 1))[:, :, None].astype(f32)
+    if loss_type == "ciou":
+        pw, ph = np.exp(pred[:, :, 2]).astype(f32), np.exp(pred[:, :, 3]).astype(f32)
+        tw, th = np.exp(target[:, :, 2]).astype(f32), np.exp(target[:, :, 3]).astype(f32)
+        v = (f32(4 / (np.pi ** 2)) * (np.arctan(tw / th).astype(f32) - np.arctan(pw / ph).astype(f32)) ** 2)
+        v = v.astype(f32)
+        S = f32(1) - iou
+        al = (v / (S + v)).astype(f32)
+        c = (iou - (inter_diag / outer_diag + al * v)).astype(f32)
+        return (f32(1) - np.clip(c, -1, 1))[:, :, None].astype(f32)
+    raise ValueError(loss_type)
+
+
+def assert_iou_loss_close(got, ref, pred, target, rtol=1e-5, atol=2e-6, msg=""):
+    """Comparison helper for the IoU family.  For IDENTICAL pred/target boxes the reference's ciou is
+    alpha = v / (1 - iou + v) with v == 0 and 1 - iou either exactly 0 (-> NaN) or one ulp (-> loss ~1e-7),
+    depending on the exp() implementation's last bit: that corner is ill-conditioned in the reference
+    itself, so there each side only has to be NaN or ~0; everywhere else values (and finiteness) must agree."""
+    same = (np.asarray(pred) == np.asarray(target)).all(axis=2, keepdims=True)
+    got, ref = np.asarray(got), np.asarray(ref)
+    assert got.shape == ref.shape == same.shape, (got.shape, ref.shape, same.shape)
+    np.testing.assert_allclose(got[~same], ref[~same], rtol=rtol, atol=atol, err_msg=msg)
+    for v in (got[same], ref[same]):
+        assert (np.isnan(v) | (np.abs(v) < 1e-5)).all(), msg
+
+
+def loc_loss(pred, target, loss_type="smoothl1", beta=0.11):
+    return smooth_l1_loss(pred, target, beta) if loss_type == "smoothl1" else iou_loss(pred, target, loss_type)
+
+
+def masked_loss_sums(cls_loss, loc_loss_v, depth):
+    """Caller-side reduction, pipeline_anchor_basic.py:76-97: per image
+    (sum(cls * (depth >= 0)), sum(loc * (depth > 0)), #fg)."""
+    depth = np.asarray(depth, dtype=f32)
+    B = depth.shape[0]
+    cs = (cls_loss * (depth >= 0)).reshape(B, -1).astype(np.float64).sum(axis=1)
+    ls = (loc_loss_v * (depth > 0)).reshape(B, -1).astype(np.float64).sum(axis=1)
+    return cs, ls, (depth > 0).reshape(B, -1).sum(axis=1)

@@ -6,7 +6,7 @@ from . import _lib                      # noqa: F401  (raises if the CUDA librar
 from .box import (configure_ratio_scale, generate_anchors, anchor_grid, box2delta, delta2box,  # noqa: F401
                   decode, decode_levels, nms, extract_targets)
 from .decoder import Decoder            # noqa: F401
-from .criterion import MultiBoxLoss     # noqa: F401
+from .criterion import MultiBoxLoss, FocalLoss, SmoothL1Loss, IOULoss     # noqa: F401
 from . import _C                        # noqa: F401
 
 __version__ = "0.1.0"

@@ -68,6 +68,10 @@ __device__ __forceinline__ float smooth_l1(float p, float t, float beta) {
   return (x >= beta) ? x - 0.5f * beta : 0.5f * x * x / beta;
 }
 
+// torch.clamp semantics: NaN passes through (fminf/fmaxf would drop it).  The reference's ciou is NaN for
+// identical boxes (v = 0, 1 - iou = 0 -> alpha = 0/0); that is reproduced, not repaired.
+__device__ __forceinline__ float clampf(float x, float lo, float hi) { return x < lo ? lo : (x > hi ? hi : x); }
+
 __device__ __forceinline__ float iou_family(const float (&p)[4], const float (&t)[4], int type) {
   // delta2ltrb (criterion.py:233-239): ctr = d[:2], wh = exp(d[2:])
   const float pw = expf(p[2]), ph = expf(p[3]), tw = expf(t[2]), th = expf(t[3]);
@@ -78,12 +82,12 @@ __device__ __forceinline__ float iou_family(const float (&p)[4], const float (&t
   const float area_a = pw * ph, area_b = tw * th;
   const float area_u = area_a + area_b - area_i;
   const float iou = (area_i + 1e-7f) / (area_u + 1e-7f);
-  if (type == LOC_IOU) return 1.0f - fminf(fmaxf(iou, 0.0f), 1.0f);
+  if (type == LOC_IOU) return 1.0f - clampf(iou, 0.0f, 1.0f);
   const float olx = fminf(plx, tlx), oly = fminf(ply, tly), orx = fmaxf(prx, trx), ory = fmaxf(pry, try_);
   if (type == LOC_GIOU) {
     const float area_o = ((orx - olx) * (ory - oly)) * ((olx < orx && oly < ory) ? 1.0f : 0.0f) + 1e-7f;
     const float g = iou - (area_o - area_u) / area_o;
-    return 1.0f - fminf(fmaxf(g, -1.0f), 1.0f);
+    return 1.0f - clampf(g, -1.0f, 1.0f);
   }
   const float dx = p[0] - t[0], dy = p[1] - t[1];
   const float inter_diag = dx * dx + dy * dy;
@@ -91,14 +95,14 @@ __device__ __forceinline__ float iou_family(const float (&p)[4], const float (&t
   const float outer_diag = (ox * ox + oy * oy) + 1e-7f;
   if (type == LOC_DIOU) {
     const float d = iou - inter_diag / outer_diag;
-    return 1.0f - fminf(fmaxf(d, -1.0f), 1.0f);
+    return 1.0f - clampf(d, -1.0f, 1.0f);
   }
   const float da = atanf(tw / th) - atanf(pw / ph);
   const float v = (float)(4.0 / (3.14159265358979323846 * 3.14159265358979323846)) * (da * da);
   const float S = 1.0f - iou;
   const float al = v / (S + v);
   const float c = iou - (inter_diag / outer_diag + al * v);
-  return 1.0f - fminf(fmaxf(c, -1.0f), 1.0f);
+  return 1.0f - clampf(c, -1.0f, 1.0f);
 }
 
 // REDUCED 0: unreduced output ([B,A,4,H,W] for SmoothL1, [B,A,1,H,W] otherwise);

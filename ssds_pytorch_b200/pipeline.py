@@ -37,3 +37,35 @@ def multibox_cls_loss_step(conf_logits, targets, anchors, num_classes, match=(0.
         fg_total = fg if fg_total is None else fg_total + fg
         parts.append((loss_sum, num_pos, box_t, depth))
     return total / fg_total, parts
+
+
+def detection_loss_step(loc, conf, targets, anchors, num_classes, cls_criterion=None, loc_criterion=None,
+                        match=(0.5, 0.4), center_sampling_radius=0):
+    """Both halves of pipeline_anchor_basic.py:62-97 on the fused reductions.
+
+    loc / conf: per-level raw head outputs [B, A*4, H, W] / [B, A*C, H, W] (model in training mode);
+    cls_criterion: `FocalLoss` (the reference default, config.py:151) or `MultiBoxLoss`;
+    loc_criterion: `SmoothL1Loss` (default, config.py:152) or `IOULoss`.
+    Returns (cls_loss, loc_loss, fg_targets) — the two scalars the reference sums into `loss`.
+    One divergence, on purpose: a NaN produced at an anchor the mask removes (ciou of two identical
+    boxes at depth <= 0) does not reach the sum, whereas `mask * loss` would carry it.
+    """
+    from .criterion import FocalLoss, SmoothL1Loss
+    if center_sampling_radius > 0:
+        raise NotImplementedError("fused sums take the class from depth; ATSS centre sampling decouples "
+                                  "them (box.py:184-191) — use extract_targets + the unreduced criteria")
+    cls_criterion = cls_criterion or FocalLoss()
+    loc_criterion = loc_criterion or SmoothL1Loss()
+    cls_sum, loc_sum, fg = [], [], []
+    for l, c, (stride, anchor) in zip(loc, conf, anchors.items()):
+        B, AC, H, W = c.shape
+        A = anchor.shape[0]
+        _, box_t, depth = extract_targets(targets, anchors, num_classes, stride, (H, W), list(match),
+                                          center_sampling_radius, with_cls_target=False)
+        cs, npos = cls_criterion.forward_sum(c.view(B, A, AC // A, H, W), depth)
+        ls = loc_criterion.forward_sum(l.view(B, A, 4, H, W), box_t, depth)
+        cls_sum.append(cs.sum())
+        loc_sum.append(ls.sum())
+        fg.append(npos.sum().clamp(min=1))
+    fg_targets = torch.stack(fg).sum()
+    return torch.stack(cls_sum).sum() / fg_targets, torch.stack(loc_sum).sum() / fg_targets, fg_targets

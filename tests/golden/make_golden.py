@@ -12,7 +12,8 @@ B200) need neither the reference nor RNG reproducibility.
 Reference functions executed (ssds/modeling/layers/box.py @ b5ec682):
 generate_anchors :46-58, box2delta :61-71, delta2box :74-87, decode :408-477,
 nms :480-546, extract_targets :362-405; decoder.py:25-49 Decoder;
-ssds/core/criterion.py:43-71 MultiBoxLoss (called per image, B=1 slices).
+ssds/core/criterion.py:43-71 MultiBoxLoss (called per image, B=1 slices),
+:95-108 FocalLoss, :138-151 SmoothL1Loss, :175-239 IOULoss (iou/giou/diou/ciou).
 All random inputs are tie-free by construction (distinct float32 scores).
 """
 import os
@@ -29,7 +30,7 @@ warnings.filterwarnings("ignore")
 
 from ssds.modeling.layers import box as rbox            # noqa: E402
 from ssds.modeling.layers.decoder import Decoder        # noqa: E402
-from ssds.core.criterion import MultiBoxLoss            # noqa: E402
+from ssds.core.criterion import MultiBoxLoss, FocalLoss, SmoothL1Loss, IOULoss   # noqa: E402
 
 OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "box_ops.npz")
 G = {}
@@ -231,6 +232,37 @@ def gen_loss(rng):
     G["mbl_n"] = np.int64(len(cases))
 
 
+def gen_loss2():
+    """Focal / SmoothL1 / IoU-family (own RNG so the earlier arrays stay byte-identical)."""
+    rng = np.random.default_rng(20260924)
+    cases = [(2, 3, 5, 8, 8), (2, 6, 80, 5, 5), (1, 9, 4, 10, 10)]
+    for i, (B, A, C, H, W) in enumerate(cases):
+        logits = rng.normal(-2.0, 2.5, (B, A, C, H, W)).astype(np.float32)
+        depth = np.zeros((B, A, 1, H, W), np.float32)
+        u = rng.uniform(size=depth.shape)
+        cls = rng.integers(0, C, depth.shape)
+        depth[u < 0.06] = (cls[u < 0.06] + 1).astype(np.float32)
+        depth[(u >= 0.06) & (u < 0.12)] = -1
+        target = np.zeros_like(logits)
+        for b, a, y, x in zip(*np.nonzero(depth[:, :, 0] > 0)):
+            target[b, a, int(depth[b, a, 0, y, x]) - 1, y, x] = 1
+        # deltas: mostly small (overlapping boxes), some far apart (disjoint), some exactly equal
+        bt = rng.normal(0, 0.6, (B, A, 4, H, W)).astype(np.float32)
+        bp = (bt + rng.normal(0, 0.35, bt.shape)).astype(np.float32)
+        far = rng.uniform(size=(B, A, 1, H, W)) < 0.15
+        bp[:, :, :2] += np.where(far, 6.0, 0.0).astype(np.float32)
+        same = rng.uniform(size=(B, A, 1, H, W)) < 0.05
+        bp = np.where(same, bt, bp).astype(np.float32)
+        p = f"ls{i}_"
+        G[p + "logits"], G[p + "target"], G[p + "depth"] = logits, target, depth
+        G[p + "box_pred"], G[p + "box_target"] = bp, bt
+        G[p + "focal"] = FocalLoss(alpha=0.25, gamma=2)(t(logits), t(target), t(depth)).numpy()
+        G[p + "smoothl1"] = SmoothL1Loss(beta=0.11)(t(bp), t(bt)).numpy()
+        for ty in ("iou", "giou", "diou", "ciou"):
+            G[p + ty] = IOULoss(loss_type=ty)(t(bp), t(bt)).numpy()
+    G["ls_n"] = np.int64(len(cases))
+
+
 def main():
     rng = np.random.default_rng(20260923)
     gen_anchors()
@@ -240,6 +272,7 @@ def main():
     gen_decoder(rng)
     gen_match(rng)
     gen_loss(rng)
+    gen_loss2()
     np.savez_compressed(OUT, **G)
     print("wrote", OUT, os.path.getsize(OUT) // 1024, "KiB,", len(G), "arrays")
 

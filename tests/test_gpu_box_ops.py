@@ -371,3 +371,94 @@ def test_cls_loss_step_like_reference_pipeline(B):
     assert fg > 3
     np.testing.assert_allclose(got.item(), tot / fg, rtol=3e-4)
     np.testing.assert_array_equal(cpu(parts[0][3]), O.extract_targets(tg, anchors, C, 8, (20, 20), [0.5, 0.4])[2])
+
+
+# ----------------------------------------------------------------------------- Focal / SmoothL1 / IoU family
+LOC_TYPES = ("smoothl1", "iou", "giou", "diou", "ciou")
+
+
+def _loc_crit(B, ty):
+    return B.SmoothL1Loss(0.11) if ty == "smoothl1" else B.IOULoss(ty)
+
+
+def test_focal_smoothl1_iou_golden(B, golden):
+    """drop-in unreduced outputs vs the reference's (tests/golden, criterion.py:95-239)."""
+    for i in range(int(golden["ls_n"])):
+        p = f"ls{i}_"
+        out = cpu(B.FocalLoss(0.25, 2)(torch.from_numpy(golden[p + "logits"]), torch.from_numpy(golden[p + "target"]),
+                                       torch.from_numpy(golden[p + "depth"])))
+        np.testing.assert_allclose(out, golden[p + "focal"], rtol=2e-5, atol=1e-7, err_msg=p)
+        for ty in LOC_TYPES:
+            got = cpu(_loc_crit(B, ty)(torch.from_numpy(golden[p + "box_pred"]), torch.from_numpy(golden[p + "box_target"])))
+            if ty == "smoothl1":
+                np.testing.assert_allclose(got, golden[p + ty], rtol=1e-5, atol=2e-6, err_msg=p + ty)
+            else:
+                from oracle import box_oracle as O
+                O.assert_iou_loss_close(got, golden[p + ty], golden[p + "box_pred"], golden[p + "box_target"],
+                                        msg=p + ty)
+
+
+def test_fused_loss_sums_vs_golden_reduction(B, golden):
+    """forward_sum == the caller's mask + sum (pipeline_anchor_basic.py:76-97) of the golden outputs."""
+    from oracle import box_oracle as O
+    for i in range(int(golden["ls_n"])):
+        p = f"ls{i}_"
+        depth = golden[p + "depth"]
+        cs, npos = B.FocalLoss().forward_sum(torch.from_numpy(golden[p + "logits"]), torch.from_numpy(depth))
+        for ty in LOC_TYPES:
+            ecs, els, enpos = O.masked_loss_sums(golden[p + "focal"], np.nan_to_num(golden[p + ty], nan=0.0), depth)
+            ls = _loc_crit(B, ty).forward_sum(torch.from_numpy(golden[p + "box_pred"].reshape(depth.shape[0], -1, *depth.shape[-2:])),
+                                              torch.from_numpy(golden[p + "box_target"]), torch.from_numpy(depth))
+            got = cpu(ls)
+            if ty == "ciou":       # identical boxes: NaN or ~1e-7 (see O.assert_iou_loss_close)
+                same = (golden[p + "box_pred"] == golden[p + "box_target"]).all(axis=2, keepdims=True)
+                poisoned = (same & (depth > 0)).reshape(depth.shape[0], -1).any(axis=1)
+                assert (np.isnan(got) <= poisoned).all()
+                got, els = got[~poisoned], els[~poisoned]
+            np.testing.assert_allclose(got, els, rtol=2e-5, atol=1e-6, err_msg=p + ty)
+        np.testing.assert_allclose(cpu(cs), ecs, rtol=2e-5, atol=1e-6, err_msg=p)
+        np.testing.assert_array_equal(cpu(npos), enpos.astype(np.float32))
+
+
+def test_detection_loss_step_like_reference_pipeline(B):
+    """pipeline_anchor_basic.py:62-97 with the reference's default criteria (FocalLoss + SmoothL1Loss,
+    config.py:151-152) on a 3-level geometry, vs the oracle run the long way."""
+    from collections import OrderedDict
+    from oracle import box_oracle as O
+    from ssds_pytorch_b200.pipeline import detection_loss_step
+    rng = np.random.default_rng(78)
+    Bn, C = 3, 20
+    levels = [(8, 20), (16, 10), (32, 5)]
+    anchors = OrderedDict((s, O.generate_anchors(s, [1, 2, 0.5], [4.0, 5.04, 6.35])) for s, _ in levels)
+    tg = make_targets(rng, Bn, 12, C, 160)
+    conf = [rng.normal(-4.6, 1.0, (Bn, 9 * C, hw, hw)).astype(np.float32) for _, hw in levels]
+    loc = [rng.normal(0, 0.5, (Bn, 9 * 4, hw, hw)).astype(np.float32) for _, hw in levels]
+    tanc = OrderedDict((s, torch.from_numpy(a)) for s, a in anchors.items())
+    for ty in ("smoothl1", "giou"):
+        cl, ll, fg = detection_loss_step([torch.from_numpy(x) for x in loc], [torch.from_numpy(x) for x in conf],
+                                         torch.from_numpy(tg), tanc, C, None, _loc_crit(B, ty))
+        ecs = els = 0.0
+        efg = 0
+        for (s, hw), c, l in zip(levels, conf, loc):
+            cls_t, box_t, dep = O.extract_targets(tg, anchors, C, s, (hw, hw), [0.5, 0.4])
+            f = O.focal_loss(c.reshape(Bn, 9, C, hw, hw), cls_t)
+            lv = O.loc_loss(l.reshape(Bn, 9, 4, hw, hw), box_t, ty)
+            a, b_, n = O.masked_loss_sums(f, lv, dep)
+            ecs += a.sum()
+            els += b_.sum()
+            efg += max(int(n.sum()), 1)
+        assert efg > 3 and fg.item() == efg
+        np.testing.assert_allclose(cl.item(), ecs / efg, rtol=1e-4)
+        np.testing.assert_allclose(ll.item(), els / efg, rtol=1e-4)
+
+
+def test_focal_loss_sum_cfg4_level(B):
+    """cfg 4 level geometry (A=9, C=80, 40x40, B=8): fused sum vs oracle; gamma != 2 takes the powf path."""
+    from oracle import box_oracle as O
+    rng = np.random.default_rng(32)
+    logits, target, depth = synth_loss_inputs(rng, 8, 9, 80, 40, 40)
+    for gamma in (2, 1.5):
+        cs, npos = B.FocalLoss(0.25, gamma).forward_sum(torch.from_numpy(logits), torch.from_numpy(depth))
+        ecs, _, enpos = O.masked_loss_sums(O.focal_loss(logits, target, 0.25, gamma), np.zeros_like(depth), depth)
+        np.testing.assert_allclose(cpu(cs), ecs, rtol=1e-4)
+        np.testing.assert_array_equal(cpu(npos), enpos.astype(np.float32))

@@ -102,3 +102,19 @@ def test_multibox_loss(golden):
         ref = golden[p + "out"]
         np.testing.assert_array_equal(out != 0, ref != 0)      # identical hard-negative selection
         np.testing.assert_allclose(out, ref, rtol=1e-5, atol=1e-6)
+
+
+def test_focal_smoothl1_iou_losses(golden):
+    """oracle restatements of criterion.py:95-108 / :138-151 / :175-239 vs the reference's outputs
+    (NaNs included: ciou of identical boxes is 0/0 in the reference)."""
+    assert int(golden["ls_n"]) >= 3
+    for i in range(int(golden["ls_n"])):
+        p = f"ls{i}_"
+        np.testing.assert_allclose(O.focal_loss(golden[p + "logits"], golden[p + "target"]),
+                                   golden[p + "focal"], rtol=2e-5, atol=1e-7)
+        np.testing.assert_allclose(O.smooth_l1_loss(golden[p + "box_pred"], golden[p + "box_target"]),
+                                   golden[p + "smoothl1"], rtol=1e-6, atol=1e-7)
+        for ty in ("iou", "giou", "diou", "ciou"):
+            O.assert_iou_loss_close(O.iou_loss(golden[p + "box_pred"], golden[p + "box_target"], ty),
+                                    golden[p + ty], golden[p + "box_pred"], golden[p + "box_target"], msg=p + ty)
+    assert np.isnan(golden["ls0_ciou"]).sum() > 0

@@ -15,7 +15,7 @@ import torch
 sys.path.insert(0, __file__.rsplit("/", 2)[0])
 from ssds_pytorch_b200 import synth                      # noqa: E402
 from ssds_pytorch_b200.ssds import SSDDetector           # noqa: E402
-from ssds_pytorch_b200.pipeline import multibox_cls_loss_step  # noqa: E402
+from ssds_pytorch_b200.pipeline import multibox_cls_loss_step, detection_loss_step  # noqa: E402
 import ssds_pytorch_b200 as S                            # noqa: E402
 
 
@@ -57,9 +57,10 @@ def cfg3():
             "launches": plan["launches"] + 3}
 
 
-def cfg4():
+def cfg4(default_losses=False):
     """SSDFPN-ResNet50 640x640 training-step forward: conv stack (train mode: logits) + match +
-    MultiBoxLoss hard-negative mining, 16 images = one rank's shard of 128/8."""
+    MultiBoxLoss hard-negative mining, 16 images = one rank's shard of 128/8.  default_losses: the
+    reference's configured defaults instead (FocalLoss + SmoothL1Loss, config.py:151-152), cls + loc."""
     fl = [[3, 4, 5, "Conv:S", "Conv:S"], [512, 1024, 2048, 2048, 256]]
     det, nb = detector("SSDFPN", "ResNet50", fl, [640, 640], 80, [4.0, 5.04, 6.35], [1, 2, 0.5])
     B = 16
@@ -77,12 +78,17 @@ def cfg4():
 
     def step():
         loc, conf = det.model(x, use_graph=True)
-        out["loss"], _ = multibox_cls_loss_step(conf, tg, det.anchors, 80)
+        if default_losses:
+            out["loss"], out["loc_loss"], _ = detection_loss_step(loc, conf, tg, det.anchors, 80)
+        else:
+            out["loss"], _ = multibox_cls_loss_step(conf, tg, det.anchors, 80)
 
     ms = timed(step)
     ms_fwd = timed(lambda: det.model(x, use_graph=True))
     anchors_per_img = sum(c.shape[1] // 80 * c.shape[2] * c.shape[3] for c in det.model.plan_for(x)["conf"])
-    return {"config": "cfg4 SSDFPN-ResNet50 640x640: forward (logits) + match + MultiBoxLoss, 16 images "
+    what = "match + FocalLoss + SmoothL1Loss" if default_losses else "match + MultiBoxLoss"
+    extra = {"loc_loss": float(out["loc_loss"])} if default_losses else {}
+    return {**extra, "config": f"cfg4 SSDFPN-ResNet50 640x640: forward (logits) + {what}, 16 images "
                       "(per-GPU shard of 128/8)", "ms_per_step": ms, "ms_forward": ms_fwd,
             "ms_match_plus_loss": ms - ms_fwd, "images_per_s_per_gpu": B / ms * 1e3,
             "anchors_per_image": anchors_per_img, "cls_loss": float(out["loss"])}
@@ -121,7 +127,7 @@ def nms_stress():
 
 if __name__ == "__main__":
     which = sys.argv[1:] or ["cfg3", "cfg4", "cfg5", "cfg5stress", "nms_stress"]
-    fns = {"cfg3": cfg3, "cfg4": cfg4, "cfg5": cfg5, "cfg5stress": lambda: cfg5(True), "nms_stress": nms_stress}
+    fns = {"cfg3": cfg3, "cfg4": cfg4, "cfg4focal": lambda: cfg4(True), "cfg5": cfg5, "cfg5stress": lambda: cfg5(True), "nms_stress": nms_stress}
     for w in which:
         t0 = time.time()
         r = fns[w]()
