@@ -208,6 +208,19 @@ SSDSB_API int ssdsb_conv2d_bf16(const ssdsb_conv_desc* desc, const void* d_x, co
                                 const float* d_bias, const void* d_residual, void* d_y, void* d_y2,
                                 void* stream);
 
+/* Two chained pointwise convolutions in one launch (conv_pair.cu):
+ *   y1 = act1(conv1x1(x, w1) + bias1 [+ residual]);   y2 = act2(conv1x1(y1, w2) + bias2)
+ * i.e. a torchvision Bottleneck's conv3+bn3+add+ReLU followed by the NEXT block's conv1+bn1+ReLU
+ * (reference nets/resnet.py:41-56).  Layer 2 reads each y1 tile back from L2 right after the same CTA
+ * stored it, so y1 is written once and never re-read from HBM.  x [N,H,W,Cin], y1/residual
+ * [N,H,W,Cmid], y2 [N,H,W,Cout2], all dense NHWC bf16; w1 [Cmid,Cin], w2 [Cout2,Cmid] bf16 (BN folded);
+ * channel counts multiples of 64 (above 256: of 256); relu: 0 none, 1 ReLU, 2 ReLU6.  Results are
+ * bit-identical to two ssdsb_conv2d_bf16 calls. */
+SSDSB_API int ssdsb_conv1x1_pair_bf16(int N, int H, int W, int Cin, int Cmid, int Cout2, int relu1, int relu2,
+                                      const void* d_x, const void* d_w1, const float* d_bias1,
+                                      const void* d_residual, void* d_y1, const void* d_w2,
+                                      const float* d_bias2, void* d_y2, void* stream);
+
 /* Image pre-processing fused with the layout change the stem needs (SSDDetector.__call__,
  * ssds/ssds.py:48-57: HWC->CHW, (x - mean)/std): packs an image batch into the 2x2
  * space-to-depth NHWC16 bf16 tensor [N, H/2, W/2, 16] (channel (a*2+b)*3+c = pixel (2i+a, 2j+b),

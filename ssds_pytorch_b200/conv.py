@@ -82,6 +82,25 @@ def conv2d(x, w, bias, KH, KW, stride, pad, relu=False, residual=None, out=None,
     return out
 
 
+def conv1x1_pair(x, w1, bias1, relu1, residual, w2, bias2, relu2, out1=None, out2=None):
+    """y1 = act1(conv1x1(x, w1) + bias1 [+ residual]); y2 = act2(conv1x1(y1, w2) + bias2) in ONE launch
+    (a Bottleneck's conv3 + the next block's conv1; y1 is re-read from L2, not HBM).  Dense NHWC bf16;
+    w1 [Cmid, 1, Cin] / w2 [Cout2, 1, Cmid] as `pack_weight` makes them.  Returns (y1, y2)."""
+    N, H, W, Cin = x.shape
+    Cmid, Cout2 = w1.shape[0], w2.shape[0]
+    assert x.is_contiguous() and w1.numel() == Cmid * Cin and w2.numel() == Cout2 * Cmid
+    if out1 is None:
+        out1 = torch.empty((N, H, W, Cmid), dtype=torch.bfloat16, device=x.device)
+    if out2 is None:
+        out2 = torch.empty((N, H, W, Cout2), dtype=torch.bfloat16, device=x.device)
+    assert out1.is_contiguous() and out2.is_contiguous() and (residual is None or residual.is_contiguous())
+    with torch.cuda.device(x.device):
+        check(lib.ssdsb_conv1x1_pair_bf16(N, H, W, Cin, Cmid, Cout2, int(relu1), int(relu2), ptr(x), ptr(w1),
+                                          ptr(bias1), ptr(residual), ptr(out1), ptr(w2), ptr(bias2),
+                                          ptr(out2), stream_ptr()), "conv1x1_pair")
+    return out1, out2
+
+
 def conv2d_head(x, w, bias, n_loc, sigmoid, KH=3, KW=3, stride=1, pad=1, loc=None, conf=None):
     """Fused multibox head: x NHWC bf16 -> (loc fp32 NCHW [N,n_loc,H,W], conf fp32 NCHW [N,Cout-n_loc,H,W]).
     w rows [0,n_loc) are the loc conv, [n_loc,Cout) the conf conv (ssd.py:100-103)."""

@@ -12,6 +12,7 @@ struct ConvKernelParams {
   int KW, taps;
   int stride, pad_w, pad_h;
   int stages, n_staging, tma_store;
+  int store_lag;     // TMA stores the store engine keeps in flight before re-arming a staging slot
   int chunk_cin;     // block-diagonal (grouped) conv: input-channel offset per n-tile (0 = dense)
   int ntile_cout;    // output channels covered by one n-tile (BLOCK_N, or the chunk width)
   int ways;          // M tiles processed together with interleaved MMAs (1, 2 or 4 accumulators)

@@ -14,6 +14,7 @@ launch.  For a fixed input shape the launch sequence is recorded once into stati
 replayed as a CUDA graph (`use_graph=True`).
 """
 import math
+import os
 from collections import OrderedDict
 
 import torch
@@ -254,14 +255,39 @@ class _ResNetBackbone:
         steps.append(lambda: K.maxpool3x3s2(xs, out=pooled))
         x = pooled
         feats = []
-        for li, blocks in enumerate(self.layers):
-            for blk in blocks:
-                identity = add_conv(blk["down"], x) if "down" in blk else x
-                y = x
-                for cv in blk["convs"][:-1]:
-                    y = add_conv(cv, y)
-                x = add_conv(blk["convs"][-1], y, residual=identity, relu=True)
-            if li + 2 in self.outputs:
+        # A bottleneck's conv3 (+bn3 +identity +ReLU) and the NEXT bottleneck's conv1 (+bn1 +ReLU) are both
+        # pointwise: they run as one launch (conv_pair.cu) in which conv1 reads each block-output tile
+        # back from L2 instead of HBM.  SSDSB_NO_PAIR=1 keeps them separate (profiling / A-B runs).
+        use_pair = os.environ.get("SSDSB_NO_PAIR", "0") != "1"
+        flat = [(li, bi, blk) for li, blocks in enumerate(self.layers) for bi, blk in enumerate(blocks)]
+
+        def pairable(c3, c1):
+            chans = (c3.w.shape[-1], c3.cout, c1.cout)
+            return (use_pair and c1.w.shape[-1] == c3.cout and c1.KH == 1 and c1.stride == 1 and
+                    all(c % 64 == 0 and (c <= 256 or c % 256 == 0) for c in chans))
+
+        pre = None                # conv1 output of the current block when the previous launch made it
+        for i, (li, bi, blk) in enumerate(flat):
+            identity = add_conv(blk["down"], x) if "down" in blk else x
+            convs = blk["convs"]
+            if len(convs) == 3:
+                y = pre if pre is not None else add_conv(convs[0], x)
+                y = add_conv(convs[1], y)
+                nxt = flat[i + 1][2]["convs"] if i + 1 < len(flat) else None
+                if nxt is not None and len(nxt) == 3 and pairable(convs[2], nxt[0]):
+                    c3, c1 = convs[2], nxt[0]
+                    n, h, w, _ = y.shape
+                    out1, out2 = buf(n, h, w, c3.cout), buf(n, h, w, c1.cout)
+                    self._add_raw(lambda x=y, r=identity, c3=c3, c1=c1, o1=out1, o2=out2: K.conv1x1_pair(
+                        x, c3.w, c3.bias, True, r, c1.w, c1.bias, c1.relu, out1=o1, out2=o2),
+                        (c3.flops_per_pixel + c1.flops_per_pixel) * n * h * w)
+                    x, pre = out1, out2
+                else:
+                    x, pre = add_conv(convs[2], y, residual=identity, relu=True), None
+            else:
+                y = add_conv(convs[0], x)
+                x = add_conv(convs[1], y, residual=identity, relu=True)
+            if bi == len(self.layers[li]) - 1 and li + 2 in self.outputs:
                 feats.append(x)
         return feats
 

@@ -220,3 +220,39 @@ def test_maxpool(K):
         y = K.maxpool3x3s2(x)
         ref = F.max_pool2d(x.float().permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1)
         assert torch.equal(y.float(), ref)
+
+
+PAIR_CASES = [
+    # N, H, W, Cin, Cmid, Cout2, residual      (conv3 of one bottleneck -> conv1 of the next)
+    (4, 32, 32, 64, 256, 64, True),      # layer1 geometry: 1 K-block, 4 chunks, N2 = 64
+    (2, 32, 32, 128, 512, 128, True),    # layer2: two 256-wide n-tiles for y1
+    (2, 16, 16, 256, 1024, 256, True),   # layer3
+    (2, 16, 16, 512, 2048, 512, True),   # layer4: Cout2 = 512 -> two n-tiles for y2 as well
+    (3, 32, 32, 64, 256, 128, True),     # stage transition: next block is twice as wide
+    (1, 16, 8, 64, 64, 64, False),       # ONE tile per CTA, one chunk per tile (flush path), no residual
+    (2, 19, 19, 64, 128, 64, True),      # ragged tile rows
+    (40, 16, 16, 64, 256, 64, True),     # 320 tiles on 148 CTAs: CTAs with 2 and 3 tiles
+]
+
+
+@pytest.mark.parametrize("case", PAIR_CASES)
+def test_conv1x1_pair_bit_identical_to_two_launches(K, case):
+    """conv_pair.cu: conv3(+residual+ReLU) and the next conv1(+ReLU) fused; y1 and y2 must be the very
+    same bf16 values two separate launches produce (same K-block order, y1 round-trips through bf16)."""
+    N, H, W, Cin, Cmid, Cout2, use_res = case
+    g = torch.Generator().manual_seed(hash(case) % (2 ** 31))
+    x = torch.randn((N, H, W, Cin), generator=g).to(torch.bfloat16).cuda()
+    w1 = K.pack_weight(torch.randn((Cmid, Cin, 1, 1), generator=g) / np.sqrt(Cin)).cuda()
+    w2 = K.pack_weight(torch.randn((Cout2, Cmid, 1, 1), generator=g) / np.sqrt(Cmid)).cuda()
+    b1 = torch.randn((Cmid,), generator=g).cuda()
+    b2 = torch.randn((Cout2,), generator=g).cuda()
+    res = torch.randn((N, H, W, Cmid), generator=g).to(torch.bfloat16).cuda() if use_res else None
+    r1 = K.conv2d(x, w1, b1, 1, 1, 1, 0, True, res)
+    r2 = K.conv2d(r1, w2, b2, 1, 1, 1, 0, True)
+    for _ in range(3):                      # repeated: a stale-read race would show up as flakiness
+        y1 = torch.full_like(r1, float("nan"))
+        y2 = torch.full_like(r2, float("nan"))
+        K.conv1x1_pair(x, w1, b1, True, res, w2, b2, True, out1=y1, out2=y2)
+        torch.cuda.synchronize()
+        assert torch.equal(y1, r1)
+        assert torch.equal(y2, r2)

@@ -16,6 +16,7 @@ CFG = {
     "l1_conv1": (128, 128, 256, 64, 1, 1, 0, True, False, False),
     "l1_conv2": (128, 128, 64, 64, 3, 1, 1, True, False, False),
     "l1_conv3": (128, 128, 64, 256, 1, 1, 0, True, True, False),
+    "l1_down": (128, 128, 64, 256, 1, 1, 0, False, False, False),
     "l2_conv1": (64, 64, 512, 128, 1, 1, 0, True, False, False),
     "l2_conv2": (64, 64, 128, 128, 3, 1, 1, True, False, False),
     "l2_conv3": (64, 64, 128, 512, 1, 1, 0, True, True, False),
@@ -29,7 +30,11 @@ CFG = {
 
 
 def main():
-    name = sys.argv[1]
+    for name in sys.argv[1:]:
+        one(name)
+
+
+def one(name):
     B = 64
     g = torch.Generator().manual_seed(0)
     if name == "stem":
