@@ -82,6 +82,10 @@ def conv2d(x, w, bias, KH, KW, stride, pad, relu=False, residual=None, out=None,
     return out
 
 
+def sm_count():
+    return torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+
+
 def conv1x1_pair(x, w1, bias1, relu1, residual, w2, bias2, relu2, out1=None, out2=None):
     """y1 = act1(conv1x1(x, w1) + bias1 [+ residual]); y2 = act2(conv1x1(y1, w2) + bias2) in ONE launch
     (a Bottleneck's conv3 + the next block's conv1; y1 is re-read from L2, not HBM).  Dense NHWC bf16;

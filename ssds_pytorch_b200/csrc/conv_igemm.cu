@@ -280,12 +280,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (lane == 0 && p.tma_store) {
       const int R = p.n_staging;
       const bool has_res = (p.residual != nullptr);
-      int a_group = blockIdx.x, a_way = 0, a_chunk = 0, armed = 0;       // arming iterator
+      int a_group = blockIdx.x, a_way = 0, a_chunk = 0, a_slot = 0;      // arming iterator
       auto arm_next = [&]() {
         if (a_group >= num_groups) return;
         const int a_m0 = (a_group / p.n_tiles) * WAYS;
         const TileCoord ta = tile_coord(p, a_m0 + a_way, a_group % p.n_tiles);
-        const int slot = armed % R;
+        const int slot = a_slot;
+        if (++a_slot == R) a_slot = 0;
         if (has_res) {
           mbar_expect_tx(&slot_ready[slot], (uint32_t)rows * 128u);
           tma_load_4d(staging + slot * STAGING_BYTES, &tmR, &slot_ready[slot],
@@ -293,7 +294,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         } else {
           mbar_arrive(&slot_ready[slot]);
         }
-        ++armed;
         const int nch = min(BLOCK_N, p.Cout - ta.n_tile * BLOCK_N) >> 6;
         if (++a_chunk == nch) {
           a_chunk = 0;
@@ -310,17 +310,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       // are in flight R - store_lag chunks ahead.
       const int lag = p.store_lag;
       int g = 0;
+      SlotRing sring = {0, 0u};
       for (int group = blockIdx.x; group < num_groups; group += gridDim.x) {
         const int m0 = (group / p.n_tiles) * WAYS;
         for (int w = 0; w < WAYS; ++w) {
           const TileCoord t = tile_coord(p, m0 + w, group % p.n_tiles);
           const int nch = min(BLOCK_N, p.Cout - t.n_tile * BLOCK_N) >> 6;
           for (int c = 0; c < nch; ++c, ++g) {
-            const int slot = g % R;
-            mbar_wait(&slot_full[slot], (uint32_t)(g / R) & 1u);
-            tma_store_4d(&tmY, staging + slot * STAGING_BYTES, t.n_tile * BLOCK_N + c * 64, t.w0, t.h0,
+            mbar_wait(&slot_full[sring.slot], sring.phase);
+            tma_store_4d(&tmY, staging + sring.slot * STAGING_BYTES, t.n_tile * BLOCK_N + c * 64, t.w0, t.h0,
                          t.n0);
             tma_store_commit();
+            sring.advance(R);
             if (g >= lag) {
               tma_store_wait_read_n(lag);   // store g-lag has been read out of smem -> its slot is free
               arm_next();                   // = chunk g-lag+R
@@ -339,8 +340,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint32_t acc_phase = 0;
     // staging ring state (TMA-store path)
     const int R = p.n_staging;
-    int g = 0;                                // chunks processed so far (all epilogue threads)
+    SlotRing ring = {0, 0u};
     const bool has_res = (p.residual != nullptr);
+    const bool staged = (p.mode == CONV_OUT_NHWC_BF16) && p.tma_store;
+    const uint32_t staging_addr = smem_u32(staging);
     // row r -> (bn, bh, bw) in TMA box order (w fastest); constant across tiles
     const int bw = r % p.BW;
     const int bh = (r / p.BW) % p.BH;
@@ -350,73 +353,22 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
      const int m0 = (group / p.n_tiles) * WAYS;
      mbar_wait(&tmem_full[acc], acc_phase);
      tcgen05_fence_after();
+     const int n_tile = group % p.n_tiles;
      for (int way = 0; way < WAYS; ++way) {
-      const TileCoord t = tile_coord(p, m0 + way, group % p.n_tiles);
-      const int w = t.w0 + bw, h = t.h0 + bh, n = t.n0 + bn;
-      const bool row_ok = (r < rows) && (w < p.Wo) && (h < p.Ho) && (n < p.N);
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) +
                              (uint32_t)((acc * WAYS + way) * BLOCK_N);
-
-      if (p.mode == CONV_OUT_NHWC_BF16 && p.tma_store) {
+      if (staged) {
         // ---------- staged path: 64-column chunks through swizzled smem + TMA store ----------
-        const int ncols = min(BLOCK_N, p.Cout - t.n_tile * BLOCK_N);
-        const int nchunks = ncols >> 6;
-        for (int c = 0; c < nchunks; ++c, ++g) {
-          const int slot = g % R;
-          unsigned char* sbuf = staging + slot * STAGING_BYTES;
-          const int col0 = t.n_tile * BLOCK_N + c * 64;
-          mbar_wait(&slot_ready[slot], (uint32_t)(g / R) & 1u);   // slot free (+ residual landed)
-          {
-            uint32_t v[32];
-            tmem_ld32(t_row + (uint32_t)(c * 64 + half * 32), v);
-            const float4* bp = reinterpret_cast<const float4*>(p.bias + col0 + half * 32);
-            float4 bv[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) bv[e] = __ldg(bp + e);
-            tmem_ld_wait();
-#pragma unroll
-            for (int gq = 0; gq < 4; ++gq) {
-              const int chunk16 = half * 4 + gq;                     // 16-byte piece of the 128B row
-              uint4* sp = reinterpret_cast<uint4*>(sbuf + r * 128 + ((chunk16 ^ (r & 7)) << 4));
-              float f[8];
-              f[0] = __uint_as_float(v[gq * 8 + 0]) + bv[gq * 2].x;
-              f[1] = __uint_as_float(v[gq * 8 + 1]) + bv[gq * 2].y;
-              f[2] = __uint_as_float(v[gq * 8 + 2]) + bv[gq * 2].z;
-              f[3] = __uint_as_float(v[gq * 8 + 3]) + bv[gq * 2].w;
-              f[4] = __uint_as_float(v[gq * 8 + 4]) + bv[gq * 2 + 1].x;
-              f[5] = __uint_as_float(v[gq * 8 + 5]) + bv[gq * 2 + 1].y;
-              f[6] = __uint_as_float(v[gq * 8 + 6]) + bv[gq * 2 + 1].z;
-              f[7] = __uint_as_float(v[gq * 8 + 7]) + bv[gq * 2 + 1].w;
-              if (has_res) {
-                const uint4 rv = *sp;
-                const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {      // bf16 -> fp32 is a 16-bit shift
-                  f[e * 2 + 0] += __uint_as_float(rw[e] << 16);
-                  f[e * 2 + 1] += __uint_as_float(rw[e] & 0xffff0000u);
-                }
-              }
-              if (p.relu) {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.0f);
-                if (p.relu == 2) {             // ReLU6 (MobileNetV2)
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) f[e] = fminf(f[e], 6.0f);
-                }
-              }
-              uint4 o;
-              o.x = pack_bf16(f[0], f[1]);
-              o.y = pack_bf16(f[2], f[3]);
-              o.z = pack_bf16(f[4], f[5]);
-              o.w = pack_bf16(f[6], f[7]);
-              *sp = o;
-            }
-          }
-          fence_proxy_async();                 // generic-proxy smem writes -> visible to TMA
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&slot_full[slot]);
-        }
-      } else {
+        const int nchunks = min(BLOCK_N, p.Cout - n_tile * BLOCK_N) >> 6;
+        staged_epilogue_item(t_row, nchunks, p.bias + n_tile * BLOCK_N + half * 32, staging_addr,
+                             STAGING_BYTES, R, ring, slot_ready, slot_full,
+                             way == WAYS - 1 ? &tmem_empty[acc] : nullptr, has_res, p.relu, r, half, lane);
+        continue;
+      }
+      const TileCoord t = tile_coord(p, m0 + way, n_tile);
+      const int w = t.w0 + bw, h = t.h0 + bh, n = t.n0 + bn;
+      const bool row_ok = (r < rows) && (w < p.Wo) && (h < p.Ho) && (n < p.N);
+      {
 #pragma unroll 1
         for (int c0 = half * 32; c0 < p.ntile_cout; c0 += 64) {
           const int col0 = t.n_tile * p.ntile_cout + c0;
@@ -512,9 +464,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
       }
      }  // ways
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (!staged) {
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      }
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;

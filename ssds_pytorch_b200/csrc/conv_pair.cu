@@ -31,7 +31,7 @@ namespace {
 constexpr int P_BLOCK_N = 256;
 constexpr int P_BLOCK_K = 64;
 constexpr int P_MAX_STAGES = 8;
-constexpr int P_STAGING = 4;
+constexpr int P_MAX_STAGING = 8;
 constexpr int P_STAGING_BYTES = BLOCK_M * 128;
 constexpr int P_A_BYTES = BLOCK_M * 128;
 constexpr int P_B_BYTES = P_BLOCK_N * 128;
@@ -51,6 +51,8 @@ struct PairParams {
   PairLayer L[2];
   int has_res;        // layer 1 adds a residual (TMA-prefetched into the staging slot)
   int stages;
+  int n_staging;      // staging slots (16 KiB each)
+  int store_lag;      // TMA stores kept in flight before a slot is re-armed
   int lag;            // layer 2 runs this many of the CTA's tiles behind layer 1
   int BW, BH, BN, tiles_w, tiles_h, tiles_n;
   int Ho, Wo, N;
@@ -116,14 +118,14 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
       (reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
   const int STAGES = p.stages;
   unsigned char* staging = smem + STAGES * P_STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + P_STAGING * P_STAGING_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + p.n_staging * P_STAGING_BYTES);
   uint64_t* full_bar = bars;                              // [P_MAX_STAGES]
   uint64_t* empty_bar = bars + P_MAX_STAGES;              // [P_MAX_STAGES]
   uint64_t* tmem_full = bars + 2 * P_MAX_STAGES;          // [2]
   uint64_t* tmem_empty = bars + 2 * P_MAX_STAGES + 2;     // [2]
-  uint64_t* slot_ready = bars + 2 * P_MAX_STAGES + 4;               // [P_STAGING]
-  uint64_t* slot_full = bars + 2 * P_MAX_STAGES + 4 + P_STAGING;    // [P_STAGING]
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * P_MAX_STAGES + 4 + 2 * P_STAGING);
+  uint64_t* slot_ready = bars + 2 * P_MAX_STAGES + 4;                   // [P_MAX_STAGING]
+  uint64_t* slot_full = bars + 2 * P_MAX_STAGES + 4 + P_MAX_STAGING;    // [P_MAX_STAGING]
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * P_MAX_STAGES + 4 + 2 * P_MAX_STAGING);
   uint32_t* y1_done = tmem_holder + 1;      // number of this CTA's tiles whose y1 is complete in global
 
   const int warp = threadIdx.x >> 5;
@@ -147,7 +149,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
       mbar_init(&tmem_full[a], 1);
       mbar_init(&tmem_empty[a], 8);
     }
-    for (int r = 0; r < P_STAGING; ++r) {
+    for (int r = 0; r < P_MAX_STAGING; ++r) {
       mbar_init(&slot_ready[r], 1);
       mbar_init(&slot_full[r], 8);
     }
@@ -243,10 +245,10 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
   } else if (warp == 3) {
     // ======================= store / residual engine =======================
     if (lane == 0) {
-      constexpr int R = P_STAGING;
+      const int R = p.n_staging;
       // arming iterator: runs R chunks ahead of the stores
       ItemIter ait(n_my, p.lag, n1, n2);
-      int a_layer = 0, a_seq = 0, a_nt = 0, a_chunk = 0, a_nch = 0, armed = 0;
+      int a_layer = 0, a_seq = 0, a_nt = 0, a_chunk = 0, a_nch = 0, a_slot = 0;
       bool a_valid = false;
       auto arm_next = [&]() {
         if (!a_valid || a_chunk == a_nch) {
@@ -255,7 +257,8 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
           a_chunk = 0;
           a_nch = min(P_BLOCK_N, p.L[a_layer].Cout - a_nt * P_BLOCK_N) >> 6;
         }
-        const int slot = armed % R;
+        const int slot = a_slot;
+        if (++a_slot == R) a_slot = 0;
         if (a_layer == 0 && p.has_res) {
           const PTile ta = ptile(p, (int)blockIdx.x + a_seq * (int)gridDim.x);
           mbar_expect_tx(&slot_ready[slot], (uint32_t)rows * 128u);
@@ -264,7 +267,6 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
         } else {
           mbar_arrive(&slot_ready[slot]);
         }
-        ++armed;
         ++a_chunk;
       };
       for (int i = 0; i < R; ++i) arm_next();
@@ -273,6 +275,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
       uint32_t pending = 0;     // tiles whose last y1 store has been issued
       int since = 0;            // stores issued since `pending` last grew
       int g = 0;
+      SlotRing sring = {0, 0u};
       ItemIter it(n_my, p.lag, n1, n2);
       int layer, seq, nt;
       while (it.next(layer, seq, nt)) {
@@ -288,13 +291,13 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
           published = pending;
         }
         for (int c = 0; c < nch; ++c, ++g) {
-          const int slot = g % R;
-          mbar_wait(&slot_full[slot], (uint32_t)(g / R) & 1u);
-          tma_store_4d(my, staging + slot * P_STAGING_BYTES, nt * P_BLOCK_N + c * 64, t.w0, t.h0, t.n0);
+          mbar_wait(&slot_full[sring.slot], sring.phase);
+          tma_store_4d(my, staging + sring.slot * P_STAGING_BYTES, nt * P_BLOCK_N + c * 64, t.w0, t.h0, t.n0);
           tma_store_commit();
+          sring.advance(R);
           ++since;
-          if (g >= 1) {
-            tma_store_wait_read<1>();     // store g-1 has left smem -> re-arm its slot (residual prefetch)
+          if (g >= p.store_lag) {
+            tma_store_wait_read_n(p.store_lag);   // store g-lag has left smem -> re-arm its slot (residual prefetch)
             arm_next();
           }
           if (layer == 0 && nt == n1 - 1 && c == nch - 1) {
@@ -318,74 +321,20 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
     const int r = q * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
-    constexpr int R = P_STAGING;
-    int g = 0;
+    const int R = p.n_staging;
+    SlotRing ring = {0, 0u};
+    const uint32_t staging_addr = smem_u32(staging);
     ItemIter it(n_my, p.lag, n1, n2);
     int layer, seq, nt;
     while (it.next(layer, seq, nt)) {
       const PairLayer& Lr = p.L[layer];
-      const bool has_res = (layer == 0) && p.has_res;
-      const int relu = Lr.relu;
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * P_BLOCK_N);
       const int nchunks = min(P_BLOCK_N, Lr.Cout - nt * P_BLOCK_N) >> 6;
-      for (int c = 0; c < nchunks; ++c, ++g) {
-        const int slot = g % R;
-        unsigned char* sbuf = staging + slot * P_STAGING_BYTES;
-        const int col0 = nt * P_BLOCK_N + c * 64;
-        mbar_wait(&slot_ready[slot], (uint32_t)(g / R) & 1u);
-        uint32_t v[32];
-        tmem_ld32(t_row + (uint32_t)(c * 64 + half * 32), v);
-        const float4* bp = reinterpret_cast<const float4*>(Lr.bias + col0 + half * 32);
-        float4 bv[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) bv[e] = __ldg(bp + e);
-        tmem_ld_wait();
-#pragma unroll
-        for (int gq = 0; gq < 4; ++gq) {
-          const int chunk16 = half * 4 + gq;
-          uint4* sp = reinterpret_cast<uint4*>(sbuf + r * 128 + ((chunk16 ^ (r & 7)) << 4));
-          float f[8];
-          f[0] = __uint_as_float(v[gq * 8 + 0]) + bv[gq * 2].x;
-          f[1] = __uint_as_float(v[gq * 8 + 1]) + bv[gq * 2].y;
-          f[2] = __uint_as_float(v[gq * 8 + 2]) + bv[gq * 2].z;
-          f[3] = __uint_as_float(v[gq * 8 + 3]) + bv[gq * 2].w;
-          f[4] = __uint_as_float(v[gq * 8 + 4]) + bv[gq * 2 + 1].x;
-          f[5] = __uint_as_float(v[gq * 8 + 5]) + bv[gq * 2 + 1].y;
-          f[6] = __uint_as_float(v[gq * 8 + 6]) + bv[gq * 2 + 1].z;
-          f[7] = __uint_as_float(v[gq * 8 + 7]) + bv[gq * 2 + 1].w;
-          if (has_res) {
-            const uint4 rv = *sp;
-            const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              f[e * 2 + 0] += __uint_as_float(rw[e] << 16);
-              f[e * 2 + 1] += __uint_as_float(rw[e] & 0xffff0000u);
-            }
-          }
-          if (relu) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.0f);
-            if (relu == 2) {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) f[e] = fminf(f[e], 6.0f);
-            }
-          }
-          uint4 o;
-          o.x = pack_bf16(f[0], f[1]);
-          o.y = pack_bf16(f[2], f[3]);
-          o.z = pack_bf16(f[4], f[5]);
-          o.w = pack_bf16(f[6], f[7]);
-          *sp = o;
-        }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&slot_full[slot]);
-      }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      staged_epilogue_item(t_row, nchunks, Lr.bias + nt * P_BLOCK_N + half * 32, staging_addr, P_STAGING_BYTES,
+                           R, ring, slot_ready, slot_full, &tmem_empty[acc], (layer == 0) && p.has_res,
+                           Lr.relu, r, half, lane);
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;
@@ -480,7 +429,20 @@ extern "C" int ssdsb_conv1x1_pair_bf16(int N, int H, int W, int Cin, int Cmid, i
     const int v = atoi(e);
     if (v >= 1 && v <= 8) kp.lag = v;
   }
-  kp.stages = (P_MAX_SMEM - 1024 - P_BAR_BYTES - P_STAGING * P_STAGING_BYTES) / P_STAGE_BYTES;
+  // residual prefetch distance (slots - store_lag) = 4 sub-tiles as in conv_igemm.cu, and 3 operand
+  // stages (r1l sweep: 6 slots / 2 stages is 10 % slower on the 64x64 stage, 4 slots 5 % slower on 128x128)
+  kp.n_staging = 5;
+  kp.store_lag = 1;
+  if (const char* e = getenv("SSDSB_PAIR_STAGING")) {      // experiment knobs (profiling only)
+    const int v = atoi(e);
+    if (v >= 2 && v <= P_MAX_STAGING) kp.n_staging = v;
+  }
+  if (const char* e = getenv("SSDSB_PAIR_STORE_LAG")) {
+    const int v = atoi(e);
+    if (v >= 0 && v <= 6) kp.store_lag = v;
+  }
+  if (kp.store_lag > kp.n_staging - 1) kp.store_lag = kp.n_staging - 1;
+  kp.stages = (P_MAX_SMEM - 1024 - P_BAR_BYTES - kp.n_staging * P_STAGING_BYTES) / P_STAGE_BYTES;
   if (kp.stages > P_MAX_STAGES) kp.stages = P_MAX_STAGES;
 
   alignas(64) CUtensorMap tmA1, tmB1, tmY1, tmR1, tmB2, tmY2;
@@ -512,7 +474,7 @@ extern "C" int ssdsb_conv1x1_pair_bf16(int N, int H, int W, int Cin, int Cmid, i
   }
   const int m_tiles = kp.tiles_w * kp.tiles_h * kp.tiles_n;
   const int grid = m_tiles < sms ? m_tiles : sms;
-  const int smem = kp.stages * P_STAGE_BYTES + P_STAGING * P_STAGING_BYTES + 1024 + P_BAR_BYTES;
+  const int smem = kp.stages * P_STAGE_BYTES + kp.n_staging * P_STAGING_BYTES + 1024 + P_BAR_BYTES;
   conv_pair_kernel<<<grid, CONV_NT, smem, (cudaStream_t)stream>>>(tmA1, tmB1, tmY1, tmR1, tmB2, tmY2, kp);
   SSDSB_LAUNCH_CHECK("conv_pair_kernel");
   return SSDSB_OK;

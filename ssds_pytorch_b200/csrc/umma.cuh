@@ -141,6 +141,39 @@ __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// tcgen05.wait::ld with the destination registers as in/out operands: the compiler cannot move any
+// use of v[] above the wait (the asynchronous tcgen05.ld "writes" them only when this returns)
+__device__ __forceinline__ void tmem_ld_wait_dep(uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.wait::ld.sync.aligned;"
+      : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+        "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]),
+        "+r"(v[15]), "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]),
+        "+r"(v[22]), "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]),
+        "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+      :
+      : "memory");
+}
+__device__ __forceinline__ float4 ldg_nc_f4(const float* p) {      // volatile: stays where it is issued
+  float4 o;
+  asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w)
+               : "l"(p));
+  return o;
+}
+__device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
+  uint4 o;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(o.x), "=r"(o.y), "=r"(o.z), "=r"(o.w)
+               : "r"(addr)
+               : "memory");
+  return o;
+}
+__device__ __forceinline__ void sts_u4(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+
 // K-major swizzled operand tile: rows of ROW_BYTES (= swizzle span: 128, 64 or 32), 8-row groups
 // 8*ROW_BYTES apart; one swizzle atom along K, so the leading-dimension offset is unused.
 template <int ROW_BYTES>
@@ -161,6 +194,112 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Staged NHWC epilogue of one work item (one accumulator = up to 256 columns), one of the 8 epilogue
+// warps: per 64-column chunk  TMEM -> +bias [+ residual already TMA-loaded into the slot] -> act -> bf16
+// -> 128B-swizzled staging slot -> slot_full (the store engine then issues the TMA store).
+// Latency matters more than instruction count here (2 warps per scheduler, one chunk at a time):
+//   * the tcgen05.ld of chunk c+1 is issued as soon as chunk c sits in registers, and the accumulator is
+//     handed back to the MMA warp right after the LAST chunk has been read, not after it has been stored;
+//   * the 8 bias loads are volatile (issued together, before the TMEM wait), slot index / phase are
+//     carried incrementally (no division by the runtime slot count), staging accesses use 32-bit
+//     shared-space addresses.
+// ---------------------------------------------------------------------------------------------
+struct SlotRing {
+  int slot;
+  uint32_t phase;
+  __device__ __forceinline__ void advance(int R) {
+    if (++slot == R) {
+      slot = 0;
+      phase ^= 1u;
+    }
+  }
+};
+
+template <bool HAS_RES>
+__device__ __forceinline__ void staged_epilogue_item_t(uint32_t t_row, int nchunks, const float* bias_half,
+                                                       uint32_t staging_addr, int slot_bytes, int R,
+                                                       SlotRing& ring, uint64_t* slot_ready,
+                                                       uint64_t* slot_full, uint64_t* tmem_empty_bar,
+                                                       int relu, int r, int half, int lane) {
+  // ReLU / ReLU6 as one clamp: no branches inside the element loops
+  const float hi = (relu == 2) ? 6.0f : __int_as_float(0x7f800000);
+  uint32_t v[32];
+  float4 bv[8];
+  tmem_ld32(t_row + (uint32_t)(half * 32), v);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) bv[e] = ldg_nc_f4(bias_half + e * 4);
+  for (int c = 0; c < nchunks; ++c) {
+    tmem_ld_wait_dep(v);
+    float f[32];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      f[e * 4 + 0] = __uint_as_float(v[e * 4 + 0]) + bv[e].x;
+      f[e * 4 + 1] = __uint_as_float(v[e * 4 + 1]) + bv[e].y;
+      f[e * 4 + 2] = __uint_as_float(v[e * 4 + 2]) + bv[e].z;
+      f[e * 4 + 3] = __uint_as_float(v[e * 4 + 3]) + bv[e].w;
+    }
+    if (c + 1 < nchunks) {               // next chunk's accumulator columns and bias: in flight from here on
+      tmem_ld32(t_row + (uint32_t)((c + 1) * 64 + half * 32), v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) bv[e] = ldg_nc_f4(bias_half + (c + 1) * 64 + e * 4);
+    } else if (tmem_empty_bar) {         // (null: more tiles of this accumulator group follow)
+      tcgen05_fence_before();            // accumulator fully read: the MMA warp may overwrite it
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty_bar);
+    }
+    const uint32_t row_addr = staging_addr + (uint32_t)(ring.slot * slot_bytes + r * 128);
+    uint32_t a[4];
+#pragma unroll
+    for (int gq = 0; gq < 4; ++gq) a[gq] = row_addr + (uint32_t)((((half * 4 + gq) ^ (r & 7))) << 4);
+    mbar_wait(&slot_ready[ring.slot], ring.phase);   // slot free (+ residual landed)
+    if (HAS_RES) {
+      uint4 rv[4];
+#pragma unroll
+      for (int gq = 0; gq < 4; ++gq) rv[gq] = lds_u4(a[gq]);     // all four 16-byte pieces in flight together
+#pragma unroll
+      for (int gq = 0; gq < 4; ++gq) {
+        const uint32_t rw[4] = {rv[gq].x, rv[gq].y, rv[gq].z, rv[gq].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {    // bf16 -> fp32 is a 16-bit shift
+          f[gq * 8 + e * 2 + 0] += __uint_as_float(rw[e] << 16);
+          f[gq * 8 + e * 2 + 1] += __uint_as_float(rw[e] & 0xffff0000u);
+        }
+      }
+    }
+    if (relu) {
+#pragma unroll
+      for (int e = 0; e < 32; ++e) f[e] = fminf(fmaxf(f[e], 0.0f), hi);
+    }
+#pragma unroll
+    for (int gq = 0; gq < 4; ++gq) {
+      uint4 o;
+      o.x = pack_bf16(f[gq * 8 + 0], f[gq * 8 + 1]);
+      o.y = pack_bf16(f[gq * 8 + 2], f[gq * 8 + 3]);
+      o.z = pack_bf16(f[gq * 8 + 4], f[gq * 8 + 5]);
+      o.w = pack_bf16(f[gq * 8 + 6], f[gq * 8 + 7]);
+      sts_u4(a[gq], o);
+    }
+    fence_proxy_async();                 // generic-proxy smem writes -> visible to TMA
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&slot_full[ring.slot]);
+    ring.advance(R);
+  }
+}
+
+__device__ __forceinline__ void staged_epilogue_item(uint32_t t_row, int nchunks, const float* bias_half,
+                                                     uint32_t staging_addr, int slot_bytes, int R,
+                                                     SlotRing& ring, uint64_t* slot_ready, uint64_t* slot_full,
+                                                     uint64_t* tmem_empty_bar, bool has_res, int relu, int r,
+                                                     int half, int lane) {
+  if (has_res)
+    staged_epilogue_item_t<true>(t_row, nchunks, bias_half, staging_addr, slot_bytes, R, ring, slot_ready,
+                                 slot_full, tmem_empty_bar, relu, r, half, lane);
+  else
+    staged_epilogue_item_t<false>(t_row, nchunks, bias_half, staging_addr, slot_bytes, R, ring, slot_ready,
+                                  slot_full, tmem_empty_bar, relu, r, half, lane);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -261,9 +261,12 @@ class _ResNetBackbone:
         use_pair = os.environ.get("SSDSB_NO_PAIR", "0") != "1"
         flat = [(li, bi, blk) for li, blocks in enumerate(self.layers) for bi, blk in enumerate(blocks)]
 
-        def pairable(c3, c1):
+        def pairable(c3, c1, n, h, w):
+            # M-tiles are the scheduling unit of the fused kernel: below ~8 tiles per SM the tail
+            # quantisation costs more than the saved HBM read (measured: 32x32 and 16x16 stages at B=64)
             chans = (c3.w.shape[-1], c3.cout, c1.cout)
             return (use_pair and c1.w.shape[-1] == c3.cout and c1.KH == 1 and c1.stride == 1 and
+                    n * h * w >= 128 * 8 * K.sm_count() and
                     all(c % 64 == 0 and (c <= 256 or c % 256 == 0) for c in chans))
 
         pre = None                # conv1 output of the current block when the previous launch made it
@@ -274,9 +277,9 @@ class _ResNetBackbone:
                 y = pre if pre is not None else add_conv(convs[0], x)
                 y = add_conv(convs[1], y)
                 nxt = flat[i + 1][2]["convs"] if i + 1 < len(flat) else None
-                if nxt is not None and len(nxt) == 3 and pairable(convs[2], nxt[0]):
+                n, h, w, _ = y.shape
+                if nxt is not None and len(nxt) == 3 and pairable(convs[2], nxt[0], n, h, w):
                     c3, c1 = convs[2], nxt[0]
-                    n, h, w, _ = y.shape
                     out1, out2 = buf(n, h, w, c3.cout), buf(n, h, w, c1.cout)
                     self._add_raw(lambda x=y, r=identity, c3=c3, c1=c1, o1=out1, o2=out2: K.conv1x1_pair(
                         x, c3.w, c3.bias, True, r, c1.w, c1.bias, c1.relu, out1=o1, out2=o2),
