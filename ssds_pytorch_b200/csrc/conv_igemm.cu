@@ -154,6 +154,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  pdl_wait();       // everything above overlapped the previous kernel's tail; its outputs are needed from here
+  pdl_trigger();
 
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
   const int m_groups = (m_tiles + WAYS - 1) / WAYS;
@@ -506,7 +508,7 @@ int launch_ways(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, S::MAX_BYTES));
     configured = true;
   }
-  conv_igemm_kernel<BLOCK_N, BLOCK_K, WAYS><<<grid, CONV_NT, smem, st>>>(tmA, tmB, tmY, tmR, kp);
+  SSDSB_CUDA(launch_pdl(conv_igemm_kernel<BLOCK_N, BLOCK_K, WAYS>, grid, CONV_NT, smem, st, tmA, tmB, tmY, tmR, kp));
   SSDSB_LAUNCH_CHECK("conv_igemm_kernel");
   return SSDSB_OK;
 }

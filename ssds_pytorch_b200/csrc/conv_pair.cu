@@ -167,6 +167,8 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  pdl_wait();
+  pdl_trigger();
 
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
   const int n_my = ((int)blockIdx.x < m_tiles) ? (m_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
@@ -475,7 +477,8 @@ extern "C" int ssdsb_conv1x1_pair_bf16(int N, int H, int W, int Cin, int Cmid, i
   const int m_tiles = kp.tiles_w * kp.tiles_h * kp.tiles_n;
   const int grid = m_tiles < sms ? m_tiles : sms;
   const int smem = kp.stages * P_STAGE_BYTES + kp.n_staging * P_STAGING_BYTES + 1024 + P_BAR_BYTES;
-  conv_pair_kernel<<<grid, CONV_NT, smem, (cudaStream_t)stream>>>(tmA1, tmB1, tmY1, tmR1, tmB2, tmY2, kp);
+  SSDSB_CUDA(launch_pdl(conv_pair_kernel, grid, CONV_NT, smem, (cudaStream_t)stream, tmA1, tmB1, tmY1, tmR1, tmB2,
+                        tmY2, kp));
   SSDSB_LAUNCH_CHECK("conv_pair_kernel");
   return SSDSB_OK;
 }

@@ -4,6 +4,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -174,6 +175,13 @@ __device__ __forceinline__ void sts_u4(uint32_t addr, const uint4& v) {
                : "memory");
 }
 
+// Programmatic dependent launch: a kernel launched with the programmatic-stream-serialization attribute
+// may start (prologue: barrier init, TMEM allocation, descriptor prefetch) while its predecessor in the
+// stream is still draining; pdl_wait() blocks until the predecessor has completed and flushed (no-op
+// without the attribute), pdl_trigger() lets the successor be scheduled as SMs free up.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // K-major swizzled operand tile: rows of ROW_BYTES (= swizzle span: 128, 64 or 32), 8-row groups
 // 8*ROW_BYTES apart; one swizzle atom along K, so the leading-dimension offset is unused.
 template <int ROW_BYTES>
@@ -300,6 +308,35 @@ __device__ __forceinline__ void staged_epilogue_item(uint32_t t_row, int nchunks
   else
     staged_epilogue_item_t<false>(t_row, nchunks, bias_half, staging_addr, slot_bytes, R, ring, slot_ready,
                                   slot_full, tmem_empty_bar, relu, r, half, lane);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host: launch with (optional) programmatic dependent launch.  Measured r1l (bench A/B on one box): no
+// difference within noise (9500/9558 vs 9518/9479 img/s) — the persistent CTAs hold the whole SM until
+// they exit, so only the ~2 us prologue can overlap — hence OFF by default; SSDSB_PDL=1 enables it.
+// ---------------------------------------------------------------------------------------------
+inline bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SSDSB_PDL");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v != 0;
+}
+
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, int smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)block);
+  cfg.dynamicSmemBytes = (size_t)smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
 // ---------------------------------------------------------------------------------------------
