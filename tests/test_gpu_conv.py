@@ -215,7 +215,7 @@ def test_upsample2x_add(K):
 
 def test_maxpool(K):
     g = torch.Generator().manual_seed(9)
-    for (N, H, W, Cc) in [(2, 32, 32, 64), (1, 15, 17, 8)]:
+    for (N, H, W, Cc) in [(2, 32, 32, 64), (1, 15, 17, 8), (2, 7, 9, 16), (1, 2, 2, 8), (3, 33, 20, 24), (1, 1, 1, 8)]:
         x = torch.randn((N, H, W, Cc), generator=g).to(torch.bfloat16).cuda()
         y = K.maxpool3x3s2(x)
         ref = F.max_pool2d(x.float().permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1)
