@@ -54,6 +54,7 @@ struct PairParams {
   int n_staging;      // staging slots (16 KiB each)
   int store_lag;      // TMA stores kept in flight before a slot is re-armed
   int lag;            // layer 2 runs this many of the CTA's tiles behind layer 1
+  int done_lag;       // y1 completion of a tile is checked this many stores after its last store (<= 8)
   int BW, BH, BN, tiles_w, tiles_h, tiles_n;
   int Ho, Wo, N;
 };
@@ -106,6 +107,19 @@ __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
 template <int N>
 __device__ __forceinline__ void tma_store_wait_done() {     // completion, not just the smem read
   asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_done_n(int n) {   // all but the n newest groups complete
+  switch (n) {
+    case 0: tma_store_wait_done<0>(); break;
+    case 1: tma_store_wait_done<1>(); break;
+    case 2: tma_store_wait_done<2>(); break;
+    case 3: tma_store_wait_done<3>(); break;
+    case 4: tma_store_wait_done<4>(); break;
+    case 5: tma_store_wait_done<5>(); break;
+    case 6: tma_store_wait_done<6>(); break;
+    case 7: tma_store_wait_done<7>(); break;
+    default: tma_store_wait_done<8>(); break;
+  }
 }
 
 __global__ void __launch_bounds__(CONV_NT, 1)
@@ -305,9 +319,10 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
           if (layer == 0 && nt == n1 - 1 && c == nch - 1) {
             pending = (uint32_t)seq + 1u;
             since = 0;
-          } else if (pending > published && since >= 2) {
-            // y1 of tile `pending-1`: every store but the two newest has completed
-            tma_store_wait_done<2>();
+          } else if (pending > published && since >= p.done_lag) {
+            // y1 of tile `pending-1`: every store but the `done_lag` newest has completed; checking
+            // late keeps this thread (which also issues the stores and re-arms the slots) from waiting
+            tma_store_wait_done_n(p.done_lag);
             fence_proxy_async_all();
             st_release_u32(y1_done, pending);
             published = pending;
@@ -427,9 +442,14 @@ extern "C" int ssdsb_conv1x1_pair_bf16(int N, int H, int W, int Cin, int Cmid, i
   kp.L[1].bias = bias2;
   kp.has_res = residual ? 1 : 0;
   kp.lag = 2;
-  if (const char* e = getenv("SSDSB_PAIR_LAG")) {          // experiment knob (profiling only)
+  kp.done_lag = 2;
+  if (const char* e = getenv("SSDSB_PAIR_LAG")) {          // experiment knobs (profiling only)
     const int v = atoi(e);
     if (v >= 1 && v <= 8) kp.lag = v;
+  }
+  if (const char* e = getenv("SSDSB_PAIR_DONE_LAG")) {
+    const int v = atoi(e);
+    if (v >= 0 && v <= 8) kp.done_lag = v;
   }
   // residual prefetch distance (slots - store_lag) = 4 sub-tiles as in conv_igemm.cu, and 3 operand
   // stages (r1l sweep: 6 slots / 2 stages is 10 % slower on the 64x64 stage, 4 slots 5 % slower on 128x128)
