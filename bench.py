@@ -275,7 +275,7 @@ def run_b200(args):
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / K,
                     "api": "SSDDetector.detect_host(uint8 NHWC pinned batch)"},
             "gpu_launches": launches_step * K,
-            "roofline": {"bound": "tensor", "kernel": "conv_igemm_kernel (all conv launches of a step)",
+            "roofline": {"bound": "tensor", "kernel": "conv_igemm_kernel + conv_pair_kernel (all conv launches of a step)",
                          "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
                          "peak_source": f"{src} bf16 sustained", "traffic": measured_conv_traffic(),
                          "traffic_unit": "DRAM bytes per step over the conv launches (ncu, profiles/r1_conv_traffic.json)",
