@@ -23,6 +23,9 @@ from . import conv as K
 from .box import configure_ratio_scale, generate_anchors
 
 BN_EPS = 1e-5
+# conv3 -> next conv1 pair launches (conv_pair.cu) are used from this many M-tiles per SM upwards
+# (tests lower it to exercise the pairing on small inputs)
+PAIR_MIN_TILES_PER_SM = 8
 
 
 def _bn(sd, prefix):
@@ -266,7 +269,7 @@ class _ResNetBackbone:
             # quantisation costs more than the saved HBM read (measured: 32x32 and 16x16 stages at B=64)
             chans = (c3.w.shape[-1], c3.cout, c1.cout)
             return (use_pair and c1.w.shape[-1] == c3.cout and c1.KH == 1 and c1.stride == 1 and
-                    n * h * w >= 128 * 8 * K.sm_count() and
+                    n * h * w >= 128 * PAIR_MIN_TILES_PER_SM * K.sm_count() and
                     all(c % 64 == 0 and (c <= 256 or c % 256 == 0) for c in chans))
 
         pre = None                # conv1 output of the current block when the previous launch made it

@@ -126,3 +126,25 @@ def test_detector_end_to_end_vs_reference_golden(env):
     out = det(x.numpy())
     assert out[0].shape == (B, 100) and out[1].dtype.kind == "i" and out[2].dtype.kind == "i"
     np.testing.assert_allclose(out[0], s, rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("tag", ["r50", "fpn50"])
+def test_pair_launch_plan_is_bit_identical_to_separate_launches(env, tag, monkeypatch):
+    """The ResNet50 plan with every eligible conv3 -> next conv1 fused into one conv_pair launch (threshold
+    lowered so that it applies to this small input: all four stages, stage transitions included) must
+    give exactly the tensors of the plan that launches them separately."""
+    from ssds_pytorch_b200 import model as MD
+    sd, fl, x, _, image, ncls = build(tag, env)
+    L = len(fl[0])
+    ssds = "SSDFPN" if tag == "fpn50" else "SSD"
+    outs = []
+    for pair in (False, True):
+        monkeypatch.setattr(MD, "PAIR_MIN_TILES_PER_SM", 0 if pair else 10 ** 9)
+        m = MD.engine_for(ssds, "ResNet50")(sd, fl, ncls, [6] * L, device="cuda").eval()
+        plan = m.plan_for(x.cuda())
+        loc, conf = m(x.cuda())
+        torch.cuda.synchronize()
+        outs.append((plan["launches"], [t.clone() for t in loc], [t.clone() for t in conf]))
+    assert outs[1][0] == outs[0][0] - 15          # 15 of ResNet50's 16 bottlenecks have a successor
+    for a, b in zip(outs[0][1] + outs[0][2], outs[1][1] + outs[1][2]):
+        assert torch.equal(a, b)
