@@ -54,7 +54,6 @@ struct ConvSmem {
   static constexpr int A_STAGE_BYTES = BLOCK_M * ROW_BYTES;
   static constexpr int B_STAGE_BYTES = BLOCK_N * ROW_BYTES;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int TMEM_COLS = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;
   static constexpr int BAR_BYTES = 512;
   static constexpr int MAX_BYTES = 232448;  // 227 KiB opt-in limit per CTA
   static_assert(STAGE_BYTES % 1024 == 0, "stage bases must stay 1024-byte aligned");
