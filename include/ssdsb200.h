@@ -160,6 +160,23 @@ SSDSB_API int ssdsb_loc_loss_sum(const float* d_pred, const float* d_target, con
                                  int A, int H, int W, int type, float beta, float* d_loss_sum /*[B]*/,
                                  void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* Backward of the fused per-image sums ("plus backward so the training step is
+ * usable"): gradients of  sum_b scale[b] * loss_sum[b]  w.r.t. the logits / predicted deltas, where
+ * loss_sum is what ssdsb_{multibox,focal,loc}_loss_sum return; the caller folds 1/fg_targets and the
+ * upstream gradient into d_scale [B].  Same values autograd gives on the reference modules
+ * (criterion.py:43-239 under pipeline_anchor_basic.py:76-97); the mined hard-negative mask and ciou's
+ * alpha are constants there too.  Outputs have the shape of the differentiated input. */
+SSDSB_API int ssdsb_multibox_loss_sum_backward(const float* d_logits, const float* d_depth, int B, int A,
+                                               int C, int H, int W, int negpos_ratio, const float* d_scale,
+                                               float* d_grad_logits, void* d_workspace,
+                                               size_t workspace_bytes, void* stream);
+SSDSB_API int ssdsb_focal_loss_sum_backward(const float* d_logits, const float* d_depth, int B, int A, int C,
+                                            int H, int W, float alpha, float gamma, const float* d_scale,
+                                            float* d_grad_logits, void* stream);
+SSDSB_API int ssdsb_loc_loss_sum_backward(const float* d_pred, const float* d_target, const float* d_depth,
+                                          int B, int A, int H, int W, int type, float beta,
+                                          const float* d_scale, float* d_grad_pred, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Conv stack (tcgen05 / TMA implicit GEMM), bf16 x bf16 -> fp32 accumulate.
  * One call replaces nn.Conv2d -> BatchNorm2d(eval, folded) -> [+ residual] -> [ReLU] of the

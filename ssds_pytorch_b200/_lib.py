@@ -65,6 +65,9 @@ def _load():
         "ssdsb_focal_loss_sum": (i, [vp, vp, i, i, i, i, i, f, f, vp, vp, vp, sz, vp]),
         "ssdsb_loc_loss": (i, [vp, vp, i, i, i, i, i, f, vp, vp]),
         "ssdsb_loc_loss_sum": (i, [vp, vp, vp, i, i, i, i, i, f, vp, vp, sz, vp]),
+        "ssdsb_multibox_loss_sum_backward": (i, [vp, vp, i, i, i, i, i, i, vp, vp, vp, sz, vp]),
+        "ssdsb_focal_loss_sum_backward": (i, [vp, vp, i, i, i, i, i, f, f, vp, vp, vp]),
+        "ssdsb_loc_loss_sum_backward": (i, [vp, vp, vp, i, i, i, i, i, f, vp, vp, vp]),
         "ssdsb_conv1x1_pair_bf16": (i, [i, i, i, i, i, i, i, i, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
         "ssdsb_conv2d_bf16": (i, [C.POINTER(ConvDesc), vp, vp, vp, vp, vp, vp, vp]),
         "ssdsb_pack_image_s2d": (i, [vp, i, i, i, i, f, f, i, i, vp, vp]),

@@ -193,6 +193,35 @@ mbl_sum(const float* __restrict__ depth, const uint32_t* __restrict__ mce,
   }
 }
 
+// backward of sum_b scale[b] * sum(ce * selected * (depth >= 0)):  (sigmoid(x) - t) * scale[b] on the
+// selected anchors, 0 elsewhere (the mined mask is a constant for autograd, as in the reference where it
+// comes out of sort indices)
+__global__ void __launch_bounds__(MBL_NT)
+mbl_grad(const float* __restrict__ logits, const float* __restrict__ depth, const uint32_t* __restrict__ mce,
+         const uint2* __restrict__ sel, const float* __restrict__ scale, int A, int C, int HW,
+         float* __restrict__ grad) {
+  const int b = blockIdx.y;
+  const int N = A * HW;
+  const int i = blockIdx.x * MBL_NT + threadIdx.x;
+  if (i >= N) return;
+  const float d = __ldg(depth + (size_t)b * N + i);
+  const bool keep = (d >= 0.0f) && ((d > 0.0f) || is_neg(__ldg(mce + (size_t)b * N + i), i, sel[b]));
+  const int a = i / HW, yx = i % HW;
+  const size_t off = ((size_t)b * A + a) * C * HW + yx;
+  const int cpos = (d > 0.0f) ? (int)d - 1 : -1;
+  const float sc = __ldg(scale + b);
+#pragma unroll 4
+  for (int c = 0; c < C; ++c) {
+    float g = 0.0f;
+    if (keep) {
+      const float x = __ldcs(logits + off + (size_t)c * HW);
+      const float p = 1.0f / (1.0f + expf(-x));
+      g = (p - ((c == cpos) ? 1.0f : 0.0f)) * sc;
+    }
+    __stcs(grad + off + (size_t)c * HW, g);
+  }
+}
+
 struct MblWs {
   uint32_t* mce;
   float* sce;
@@ -286,5 +315,28 @@ extern "C" int ssdsb_multibox_loss_sum(const float* d_logits, const float* d_dep
   SSDSB_LAUNCH_CHECK("mbl_select");
   mbl_sum<<<B, SEL_NT, 0, st>>>(d_depth, w.mce, w.sce, w.sel, w.npos, N, d_loss_sum, d_num_pos);
   SSDSB_LAUNCH_CHECK("mbl_sum");
+  return SSDSB_OK;
+}
+
+extern "C" int ssdsb_multibox_loss_sum_backward(const float* d_logits, const float* d_depth, int B, int A,
+                                                int C, int H, int W, int negpos_ratio, const float* d_scale,
+                                                float* d_grad_logits, void* d_workspace,
+                                                size_t workspace_bytes, void* stream) {
+  int rc = mbl_check(B, A, C, H, W, negpos_ratio, d_workspace, workspace_bytes);
+  if (rc != SSDSB_OK) return rc;
+  if (B == 0) return SSDSB_OK;
+  SSDSB_REQUIRE(d_logits && d_depth && d_scale && d_grad_logits, "multibox_loss_sum_backward: NULL argument");
+  const int HW = H * W, N = A * HW;
+  MblWs w = mbl_carve(d_workspace, B, N);
+  cudaStream_t st = (cudaStream_t)stream;
+  SSDSB_CUDA(cudaMemsetAsync(d_workspace, 0, w.head, st));
+  dim3 grid((N + MBL_NT - 1) / MBL_NT, B);
+  // the selection is recomputed (same kernels as the forward => same mask) rather than stored
+  mbl_ce<1><<<grid, MBL_NT, 0, st>>>(d_logits, nullptr, d_depth, A, C, HW, nullptr, w.mce, w.sce, w.npos);
+  SSDSB_LAUNCH_CHECK("mbl_ce<1>");
+  mbl_select<<<B, SEL_NT, 0, st>>>(w.mce, N, w.npos, negpos_ratio, w.sel);
+  SSDSB_LAUNCH_CHECK("mbl_select");
+  mbl_grad<<<grid, MBL_NT, 0, st>>>(d_logits, d_depth, w.mce, w.sel, d_scale, A, C, HW, d_grad_logits);
+  SSDSB_LAUNCH_CHECK("mbl_grad");
   return SSDSB_OK;
 }

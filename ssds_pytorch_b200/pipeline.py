@@ -1,7 +1,8 @@
 """The loss half of the training step, as the reference sequences it
 (ssds/pipeline/pipeline_anchor_basic.py:62-97, same body in pipeline_anchor_apex.py:37-72), on the
 fused kernels: per level `extract_targets` (match + encode + depth, no one-hot target) followed by the
-fused `MultiBoxLoss` reduction.  Forward only (timing / inference-side scope of this round).
+fused `MultiBoxLoss` reduction.  The returned losses are differentiable w.r.t. the head outputs passed
+in (dL/dlogits, dL/dloc through the backward kernels); the conv stack itself has no backward yet.
 
     cls_loss, parts = multibox_cls_loss_step(conf_logits, targets, anchors, num_classes)
 

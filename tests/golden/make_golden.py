@@ -263,6 +263,37 @@ def gen_loss2():
     G["ls_n"] = np.int64(len(cases))
 
 
+def gen_loss_grads():
+    """Gradients autograd gives on the reference modules for the masked, normalised sums of
+    pipeline_anchor_basic.py:76-97 (inputs: the ls*/mbl* arrays generated above)."""
+    for i in range(int(G["ls_n"])):
+        p = f"ls{i}_"
+        depth = t(G[p + "depth"])
+        fg = (depth > 0).sum().float().clamp(min=1)
+        G[p + "fg"] = np.float32(fg.item())
+        x = t(G[p + "logits"]).requires_grad_(True)
+        loss = FocalLoss(alpha=0.25, gamma=2)(x, t(G[p + "target"]), depth)
+        ((loss * (depth >= 0).expand_as(loss).float()).sum() / fg).backward()
+        G[p + "g_focal"] = x.grad.numpy().copy()
+        for ty in ("smoothl1", "iou", "giou", "diou", "ciou"):
+            bp = t(G[p + "box_pred"]).requires_grad_(True)
+            crit = SmoothL1Loss(beta=0.11) if ty == "smoothl1" else IOULoss(loss_type=ty)
+            l = crit(bp, t(G[p + "box_target"]))
+            ((l * (depth > 0).expand_as(l).float()).sum() / fg).backward()
+            G[p + "g_" + ty] = bp.grad.numpy().copy()
+    crit = MultiBoxLoss(negpos_ratio=3)
+    for i in range(int(G["mbl_n"])):
+        p = f"mbl{i}_"
+        grads = []
+        for b in range(G[p + "logits"].shape[0]):                    # B=1 slices (SURVEY 8a-7)
+            x = t(G[p + "logits"][b:b + 1]).requires_grad_(True)
+            d = t(G[p + "depth"][b:b + 1])
+            out = crit(x, t(G[p + "target"][b:b + 1]), d)
+            (out * (d >= 0).expand_as(out).float()).sum().backward()
+            grads.append(x.grad.numpy().copy())
+        G[p + "grad"] = np.concatenate(grads, 0)
+
+
 def main():
     rng = np.random.default_rng(20260923)
     gen_anchors()
@@ -273,6 +304,7 @@ def main():
     gen_match(rng)
     gen_loss(rng)
     gen_loss2()
+    gen_loss_grads()
     np.savez_compressed(OUT, **G)
     print("wrote", OUT, os.path.getsize(OUT) // 1024, "KiB,", len(G), "arrays")
 

@@ -462,3 +462,62 @@ def test_focal_loss_sum_cfg4_level(B):
         ecs, _, enpos = O.masked_loss_sums(O.focal_loss(logits, target, 0.25, gamma), np.zeros_like(depth), depth)
         np.testing.assert_allclose(cpu(cs), ecs, rtol=1e-4)
         np.testing.assert_array_equal(cpu(npos), enpos.astype(np.float32))
+
+
+# ----------------------------------------------------------------------------- loss backward (8f rank 1)
+def test_loss_backward_vs_reference_autograd_golden(B, golden):
+    """forward_sum(...) is differentiable: dL/dlogits, dL/dloc from the backward kernels vs the gradients
+    autograd gives on the REFERENCE modules (tests/golden: ls*_g_*, mbl*_grad)."""
+    for i in range(int(golden["ls_n"])):
+        p = f"ls{i}_"
+        depth = torch.from_numpy(golden[p + "depth"]).cuda()
+        fg = float(golden[p + "fg"])
+        x = torch.from_numpy(golden[p + "logits"]).cuda().requires_grad_(True)
+        ls, npos = B.FocalLoss(0.25, 2).forward_sum(x, depth)
+        assert not npos.requires_grad
+        (ls.sum() / fg).backward()
+        np.testing.assert_allclose(cpu(x.grad), golden[p + "g_focal"], rtol=2e-5, atol=1e-8, err_msg=p)
+        same = (golden[p + "box_pred"] == golden[p + "box_target"]).all(axis=2, keepdims=True)
+        for ty in LOC_TYPES:
+            bp = torch.from_numpy(golden[p + "box_pred"]).cuda().requires_grad_(True)
+            l = _loc_crit(B, ty).forward_sum(bp, torch.from_numpy(golden[p + "box_target"]), depth)
+            (l.sum() / fg).backward()
+            ref = golden[p + "g_" + ty]
+            ok = ~np.broadcast_to(same, ref.shape) if ty == "ciou" else np.ones(ref.shape, bool)
+            np.testing.assert_allclose(cpu(bp.grad)[ok], ref[ok], rtol=5e-5, atol=2e-8, err_msg=p + ty)
+    for i in range(int(golden["mbl_n"])):
+        p = f"mbl{i}_"
+        x = torch.from_numpy(golden[p + "logits"]).cuda().requires_grad_(True)
+        ls, _ = B.MultiBoxLoss(3).forward_sum(x, torch.from_numpy(golden[p + "depth"]))
+        ls.sum().backward()
+        np.testing.assert_allclose(cpu(x.grad), golden[p + "grad"], rtol=2e-5, atol=1e-7, err_msg=p)
+
+
+def test_detection_loss_step_backward_vs_oracle(B):
+    """the whole loss step (match + FocalLoss + SmoothL1 / GIoU, masks, 1/fg) differentiated w.r.t. the raw
+    head outputs, vs the oracle (torch restatement + autograd, pinned by test_oracle_golden.py)."""
+    from collections import OrderedDict
+    from oracle import box_oracle as O
+    from oracle import loss_grad_oracle as LG
+    from ssds_pytorch_b200.pipeline import detection_loss_step
+    rng = np.random.default_rng(79)
+    Bn, C = 2, 20
+    levels = [(8, 20), (16, 10)]
+    anchors = OrderedDict((s, O.generate_anchors(s, [1, 2, 0.5], [4.0, 5.04, 6.35])) for s, _ in levels)
+    tg = make_targets(rng, Bn, 10, C, 160)
+    conf = [rng.normal(-3.0, 1.5, (Bn, 9 * C, hw, hw)).astype(np.float32) for _, hw in levels]
+    loc = [rng.normal(0, 0.5, (Bn, 9 * 4, hw, hw)).astype(np.float32) for _, hw in levels]
+    tanc = OrderedDict((s, torch.from_numpy(a)) for s, a in anchors.items())
+    for ty in ("smoothl1", "giou"):
+        tc = [torch.from_numpy(x).cuda().requires_grad_(True) for x in conf]
+        tl = [torch.from_numpy(x).cuda().requires_grad_(True) for x in loc]
+        cl, ll, fg = detection_loss_step(tl, tc, torch.from_numpy(tg), tanc, C, None, _loc_crit(B, ty))
+        (cl + ll).backward()
+        scale = np.full((Bn,), 1.0 / fg.item(), np.float32)
+        for (s, hw), c, l, gc, gl in zip(levels, conf, loc, tc, tl):
+            cls_t, box_t, dep = O.extract_targets(tg, anchors, C, s, (hw, hw), [0.5, 0.4])
+            eg = LG.focal_sum_grad(c.reshape(Bn, 9, C, hw, hw), cls_t, dep, scale)
+            np.testing.assert_allclose(cpu(gc.grad).reshape(eg.shape), eg, rtol=1e-4, atol=1e-8)
+            el = LG.loc_sum_grad(l.reshape(Bn, 9, 4, hw, hw), box_t, dep, scale, ty)
+            np.testing.assert_allclose(cpu(gl.grad).reshape(el.shape), el, rtol=1e-4, atol=2e-8)
+            assert np.abs(el).max() > 0

@@ -118,3 +118,27 @@ def test_focal_smoothl1_iou_losses(golden):
             O.assert_iou_loss_close(O.iou_loss(golden[p + "box_pred"], golden[p + "box_target"], ty),
                                     golden[p + ty], golden[p + "box_pred"], golden[p + "box_target"], msg=p + ty)
     assert np.isnan(golden["ls0_ciou"]).sum() > 0
+
+
+def test_loss_gradients(golden):
+    """oracle backward (torch restatement + autograd) vs autograd on the reference modules."""
+    from oracle import loss_grad_oracle as LG
+    for i in range(int(golden["ls_n"])):
+        p = f"ls{i}_"
+        depth = golden[p + "depth"]
+        B = depth.shape[0]
+        scale = np.full((B,), 1.0 / float(golden[p + "fg"]), np.float32)
+        np.testing.assert_allclose(LG.focal_sum_grad(golden[p + "logits"], golden[p + "target"], depth, scale),
+                                   golden[p + "g_focal"], rtol=1e-5, atol=1e-9)
+        same = (golden[p + "box_pred"] == golden[p + "box_target"]).all(axis=2, keepdims=True)
+        for ty in ("smoothl1", "iou", "giou", "diou", "ciou"):
+            g = LG.loc_sum_grad(golden[p + "box_pred"], golden[p + "box_target"], depth, scale, ty)
+            ref = golden[p + "g_" + ty]
+            ok = ~np.broadcast_to(same, ref.shape) if ty == "ciou" else np.ones(ref.shape, bool)
+            np.testing.assert_allclose(g[ok], ref[ok], rtol=1e-5, atol=1e-8, err_msg=p + ty)
+    for i in range(int(golden["mbl_n"])):
+        p = f"mbl{i}_"
+        B = golden[p + "depth"].shape[0]
+        g = LG.multibox_sum_grad(golden[p + "logits"], golden[p + "target"], golden[p + "depth"],
+                                 np.ones((B,), np.float32))
+        np.testing.assert_allclose(g, golden[p + "grad"], rtol=1e-5, atol=1e-7, err_msg=p)
