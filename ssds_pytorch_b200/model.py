@@ -98,6 +98,7 @@ class _Engine(torch.nn.Module):
         else:
             N, _, H, W = images.shape
         steps = []          # list of zero-arg callables
+        info = {}           # step index -> {kind, flops, bytes}: algorithmic work of that launch (profiling tools)
         flops = [0]
         split = [None]
         bf = torch.bfloat16
@@ -122,6 +123,11 @@ class _Engine(torch.nn.Module):
                                           residual, out=y, Ho=ho, Wo=wo, x_kind=x_kind,
                                           x_width=x_width))
             flops[0] += cv.flops_per_pixel * n * ho * wo
+            info[len(steps) - 1] = {"kind": f"conv{cv.KH}x{cv.KW}s{cv.stride} {x.shape[3]}->{cv.cout} @{ho}x{wo}",
+                                    "flops": cv.flops_per_pixel * n * ho * wo,
+                                    # a strided 1x1 only touches every stride-th pixel of x
+                                    "bytes": 2 * (x.numel() // (cv.stride ** 2 if cv.KH == 1 else 1) + cv.w.numel() +
+                                                  y.numel() + (residual.numel() if residual is not None else 0))}
             return y
 
         def add_head(f, h, loc=None, conf=None):
@@ -136,6 +142,9 @@ class _Engine(torch.nn.Module):
             steps.append(lambda: K.conv2d_head(f, h.w, h.bias, h.n_loc, not self.training,
                                                loc=loc, conf=conf))
             flops[0] += h.flops_per_pixel * n * fh * fw
+            info[len(steps) - 1] = {"kind": f"head3x3 {f.shape[3]}->{h.cout} @{fh}x{fw}",
+                                    "flops": h.flops_per_pixel * n * fh * fw,
+                                    "bytes": 2 * (f.numel() + h.w.numel()) + 4 * (loc.numel() + conf.numel())}
             return loc, conf
 
         def add_dw(dw, x):
@@ -146,15 +155,16 @@ class _Engine(torch.nn.Module):
             flops[0] += dw.flops_per_pixel * n * ho * wo
             return y
 
-        def add_raw(fn, nflops):
+        def add_raw(fn, nflops, kind="raw", nbytes=0):
             steps.append(fn)
             flops[0] += nflops
+            info[len(steps) - 1] = {"kind": kind, "flops": nflops, "bytes": nbytes}
 
         self._add_raw = add_raw
         feats = self._plan_backbone(packed, H, W, steps, buf, add_conv, add_dw)
         locs, confs = self._plan_neck(feats, steps, buf, add_conv, add_head)
         return {"src": src, "steps": steps, "loc": tuple(locs), "conf": tuple(confs),
-                "flops": flops[0], "graph": None, "launches": len(steps),
+                "flops": flops[0], "graph": None, "launches": len(steps), "info": info,
                 "split": split[0] if split[0] is not None else len(steps)}
 
     def plan_for(self, images):
@@ -286,7 +296,10 @@ class _ResNetBackbone:
                     out1, out2 = buf(n, h, w, c3.cout), buf(n, h, w, c1.cout)
                     self._add_raw(lambda x=y, r=identity, c3=c3, c1=c1, o1=out1, o2=out2: K.conv1x1_pair(
                         x, c3.w, c3.bias, True, r, c1.w, c1.bias, c1.relu, out1=o1, out2=o2),
-                        (c3.flops_per_pixel + c1.flops_per_pixel) * n * h * w)
+                        (c3.flops_per_pixel + c1.flops_per_pixel) * n * h * w,
+                        kind=f"pair1x1 {y.shape[3]}->{c3.cout}->{c1.cout} @{h}x{w}",
+                        nbytes=2 * (y.numel() + identity.numel() + out1.numel() + out2.numel() + c3.w.numel() +
+                                    c1.w.numel()))
                     x, pre = out1, out2
                 else:
                     x, pre = add_conv(convs[2], y, residual=identity, relu=True), None
