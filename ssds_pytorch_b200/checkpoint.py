@@ -17,6 +17,7 @@ prints the import report; without --dry-run it also builds the detector on the c
 """
 import argparse
 import os
+import re
 import sys
 from collections import OrderedDict
 
@@ -33,12 +34,13 @@ def find_previous_checkpoint(output_dir):
     if not os.path.exists(index):
         return False
     epochs, files = [], []
+    entry = re.compile(r"epoch\s+(\d+):\s(.*)$")          # "epoch {n}: {path}" as save_checkpoints writes it
     with open(index) as f:
         for line in f:
-            if "epoch " not in line or ":" not in line:
-                continue
-            epochs.append(int(line[line.find("epoch ") + len("epoch "):line.find(":")]))
-            files.append(line[line.find(":") + 2:].rstrip("\n"))
+            m = entry.search(line.rstrip("\n"))
+            if m:
+                epochs.append(int(m.group(1)))
+                files.append(m.group(2))
     return epochs, files
 
 
@@ -46,7 +48,7 @@ def strip_module_prefix(state):
     """checkpoint.py:87-91: a (Distributed)DataParallel checkpoint carries `module.` on every key; the
     reference decides by looking at the FIRST key only and then drops the first dotted component of all."""
     if state and "module." in next(iter(state)):
-        return OrderedDict((".".join(k.split(".")[1:]), v) for k, v in state.items())
+        return OrderedDict((k.partition(".")[2], v) for k, v in state.items())
     return state
 
 
