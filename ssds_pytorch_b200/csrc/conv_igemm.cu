@@ -57,15 +57,19 @@ struct ConvSmem {
   static constexpr int BAR_BYTES = 512;
   static constexpr int MAX_BYTES = 232448;  // 227 KiB opt-in limit per CTA
   static_assert(STAGE_BYTES % 1024 == 0, "stage bases must stay 1024-byte aligned");
-  static int stage_bytes(bool b_resident) { return b_resident ? A_STAGE_BYTES : STAGE_BYTES; }
-  static int stages_for(int n_staging, bool b_resident, int num_k_blocks) {
+  // one pipeline stage = one k-block of a group: the A tiles of its `ways` M tiles + (unless the weights
+  // are resident) ONE B tile, behind one full / one empty barrier
+  static int stage_bytes(bool b_resident, int ways) {
+    return ways * A_STAGE_BYTES + (b_resident ? 0 : B_STAGE_BYTES);
+  }
+  static int stages_for(int n_staging, bool b_resident, int num_k_blocks, int ways) {
     const int fixed = 1024 + BAR_BYTES + n_staging * STAGING_BYTES +
                       (b_resident ? num_k_blocks * B_STAGE_BYTES : 0);
-    int s = (MAX_BYTES - fixed) / stage_bytes(b_resident);
+    int s = (MAX_BYTES - fixed) / stage_bytes(b_resident, ways);
     return s > MAX_STAGES ? MAX_STAGES : s;
   }
-  static int bytes(int stages, int n_staging, bool b_resident, int num_k_blocks) {
-    return stages * stage_bytes(b_resident) + n_staging * STAGING_BYTES +
+  static int bytes(int stages, int n_staging, bool b_resident, int num_k_blocks, int ways) {
+    return stages * stage_bytes(b_resident, ways) + n_staging * STAGING_BYTES +
            (b_resident ? num_k_blocks * B_STAGE_BYTES : 0) + 1024 + BAR_BYTES;
   }
 };
@@ -96,7 +100,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   unsigned char* smem = reinterpret_cast<unsigned char*>(
       (reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
   const int STAGES = p.stages;
-  const int stage_bytes = p.b_resident ? A_STAGE_BYTES : S::STAGE_BYTES;
+  const int stage_bytes = WAYS * A_STAGE_BYTES + (p.b_resident ? 0 : S::B_STAGE_BYTES);
   unsigned char* staging = smem + STAGES * stage_bytes;
   unsigned char* bres = staging + p.n_staging * STAGING_BYTES;     // resident weights (optional)
   uint64_t* bars = reinterpret_cast<uint64_t*>(bres + (p.b_resident ? p.num_k_blocks * S::B_STAGE_BYTES : 0));
@@ -187,20 +191,20 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         int tap = 0, kc = 0, kh = 0, kw = 0;       // incremental (no divisions in the K loop)
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          // one stage per k-block: the A tiles of all ways + the shared B tile, one barrier pair
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          unsigned char* sa = smem + stage * stage_bytes;
+          mbar_expect_tx(&full_bar[stage],
+                         (uint32_t)WAYS * a_bytes + (p.b_resident ? 0u : (uint32_t)S::B_STAGE_BYTES));
 #pragma unroll
-          for (int w = 0; w < WAYS; ++w) {         // one stage per (k-block, way); B rides with way 0
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            unsigned char* sa = smem + stage * stage_bytes;
-            const bool with_b = (w == 0) && !p.b_resident;
-            mbar_expect_tx(&full_bar[stage], a_bytes + (with_b ? (uint32_t)S::B_STAGE_BYTES : 0u));
-            tma_load_4d(sa, &tmA, &full_bar[stage], kc * BLOCK_K + n_tile * p.chunk_cin, cw[w] + kw,
-                        ch[w] + kh, cn[w]);
-            if (with_b)
-              tma_load_2d(sa + A_STAGE_BYTES, &tmB, &full_bar[stage], kb * BLOCK_K, n_tile * BLOCK_N);
-            if (++stage == STAGES) {
-              stage = 0;
-              phase ^= 1;
-            }
+          for (int w = 0; w < WAYS; ++w)
+            tma_load_4d(sa + w * A_STAGE_BYTES, &tmA, &full_bar[stage], kc * BLOCK_K + n_tile * p.chunk_cin,
+                        cw[w] + kw, ch[w] + kh, cn[w]);
+          if (!p.b_resident)
+            tma_load_2d(sa + WAYS * A_STAGE_BYTES, &tmB, &full_bar[stage], kb * BLOCK_K, n_tile * BLOCK_N);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
           }
           if (++kc == p.kc_per_tap) {
             kc = 0;
@@ -228,23 +232,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * WAYS * BLOCK_N);
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-          // the WAYS stages of this k-block are consecutive in the ring
-          uint64_t a_desc[WAYS];
-          int st = stage;
-          uint32_t ph = phase;
-#pragma unroll
-          for (int w = 0; w < WAYS; ++w) {
-            mbar_wait(&full_bar[st], ph);
-            a_desc[w] = make_smem_desc<S::ROW_BYTES>(smem_u32(smem + st * stage_bytes));
-            if (++st == STAGES) {
-              st = 0;
-              ph ^= 1;
-            }
-          }
+          mbar_wait(&full_bar[stage], phase);
           tcgen05_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+          uint64_t a_desc[WAYS];
+#pragma unroll
+          for (int w = 0; w < WAYS; ++w) a_desc[w] = make_smem_desc<S::ROW_BYTES>(sa + (uint32_t)(w * A_STAGE_BYTES));
           const uint64_t b_desc = p.b_resident
               ? make_smem_desc<S::ROW_BYTES>(bres_addr + (uint32_t)(kb * S::B_STAGE_BYTES))
-              : a_desc[0] + (uint64_t)(A_STAGE_BYTES >> 4);
+              : make_smem_desc<S::ROW_BYTES>(sa + (uint32_t)(WAYS * A_STAGE_BYTES));
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             // advance 16 bf16 = 32 bytes inside the swizzle row: +2 in the (>>4) address field;
@@ -254,13 +250,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               umma_bf16(d_tmem + (uint32_t)(w * BLOCK_N), a_desc[w] + (uint64_t)(2 * k),
                         b_desc + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
           }
-#pragma unroll
-          for (int w = 0; w < WAYS; ++w) {
-            tcgen05_commit(&empty_bar[stage]);  // frees the smem slots when these MMAs retire
-            if (++stage == STAGES) {
-              stage = 0;
-              phase ^= 1;
-            }
+          tcgen05_commit(&empty_bar[stage]);    // frees the stage when these MMAs retire
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
           }
         }
         tcgen05_commit(&tmem_full[acc]);      // accumulators ready for the epilogue
@@ -558,16 +551,19 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tm
       kp.b_resident = 1;
     }
   }
-  kp.stages = S::stages_for(kp.n_staging, kp.b_resident, kp.num_k_blocks);
-  if (kp.b_resident && kp.stages < 2 * kp.ways) {           // resident weights must not starve the A ring
+  kp.stages = S::stages_for(kp.n_staging, kp.b_resident, kp.num_k_blocks, kp.ways);
+  if (kp.b_resident && kp.stages < 2) {                     // resident weights must not starve the A ring
     kp.b_resident = 0;
     grid = tiles < sms ? tiles : sms;
-    kp.stages = S::stages_for(kp.n_staging, false, kp.num_k_blocks);
+    kp.stages = S::stages_for(kp.n_staging, false, kp.num_k_blocks, kp.ways);
   }
-  while (kp.ways > 1 && kp.stages < 2 * kp.ways) kp.ways >>= 1;
-  if (kp.stages > kp.num_k_blocks * 4 * kp.ways) kp.stages = kp.num_k_blocks * 4 * kp.ways;
+  while (kp.ways > 1 && kp.stages < 2) {                    // (cannot happen with <= 4 ways of 16 KiB)
+    kp.ways >>= 1;
+    kp.stages = S::stages_for(kp.n_staging, kp.b_resident, kp.num_k_blocks, kp.ways);
+  }
+  if (kp.stages > kp.num_k_blocks * 4) kp.stages = kp.num_k_blocks * 4;
   if (kp.stages < 2) kp.stages = 2;
-  const int smem = S::bytes(kp.stages, kp.n_staging, kp.b_resident, kp.num_k_blocks);
+  const int smem = S::bytes(kp.stages, kp.n_staging, kp.b_resident, kp.num_k_blocks, kp.ways);
   const int groups = ((m_tiles + kp.ways - 1) / kp.ways) * kp.n_tiles;
   if (grid > groups) grid = groups;
   if constexpr (BLOCK_N <= 64) {
