@@ -122,8 +122,12 @@ _workspaces = {}
 
 
 def workspace(nbytes, device):
-    """Grow-only per-device scratch buffer owned by the caller side (torch), 256-byte aligned."""
-    key = (device.type, device.index)
+    """Grow-only scratch buffer owned by the caller side (torch), 256-byte aligned — one per (device,
+    stream): work queued on different streams (e.g. the detector's post-processing side stream) never
+    shares scratch memory, and a buffer that is replaced by a larger one is only ever recycled by the
+    caching allocator on the stream that used it."""
+    stream = torch.cuda.current_stream(device).cuda_stream if device.type == "cuda" else 0
+    key = (device.type, device.index, stream)
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)

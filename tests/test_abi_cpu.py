@@ -63,3 +63,14 @@ def test_extract_targets_bad_match_raises_like_reference():
     from ssds_pytorch_b200 import extract_targets
     with pytest.raises(ValueError):
         extract_targets(torch.zeros(1, 1, 5), {8: torch.zeros(1, 4)}, 3, 8, (4, 4), match=["x", 1])
+
+
+def test_workspace_is_grow_only_and_keyed():
+    import torch
+    from ssds_pytorch_b200 import _lib
+    dev = torch.device("cpu")                     # exercises the keying / growth logic without a GPU
+    a = _lib.workspace(100, dev)
+    assert a.numel() >= 1 << 20 and a.dtype == torch.uint8
+    assert _lib.workspace(4096, dev) is a         # reused while it is large enough
+    b = _lib.workspace(a.numel() + 1, dev)
+    assert b is not a and b.numel() >= a.numel() + 1 and _lib.workspace(10, dev) is b
