@@ -4,6 +4,7 @@
 
 The .so lands next to this file so that it travels to the GPU box with the repo snapshot.
 """
+import fcntl
 import hashlib
 import os
 import subprocess
@@ -14,6 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB = os.path.join(HERE, "libssdsb200.so")
 STAMP = os.path.join(HERE, ".libssdsb200.stamp")
+LOCK = os.path.join(HERE, ".libssdsb200.lock")
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-fvisibility=hidden",
@@ -45,10 +47,24 @@ def nvcc():
     raise RuntimeError("nvcc not found")
 
 
+def _fresh(d):
+    return os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read() == d
+
+
 def build(force=False, verbose=False):
     d = digest()
-    if not force and os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read() == d:
+    if not force and _fresh(d):
         return LIB
+    # one builder at a time: under torchrun every rank imports the package at once; the others wait here
+    # and then find the library up to date
+    with open(LOCK, "w") as lk:
+        fcntl.flock(lk, fcntl.LOCK_EX)
+        if not force and _fresh(d):
+            return LIB
+        return _build_locked(d, verbose)
+
+
+def _build_locked(d, verbose):
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
     objs, procs = [], []
@@ -68,8 +84,9 @@ def build(force=False, verbose=False):
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    link = [nvcc()] + ARCH + ["-shared", "-o", LIB] + objs 
-    subprocess.check_call(link)
+    tmp = LIB + f".tmp.{os.getpid()}"
+    subprocess.check_call([nvcc()] + ARCH + ["-shared", "-o", tmp] + objs)
+    os.replace(tmp, LIB)                     # atomic: a concurrent loader never sees a half-written file
     open(STAMP, "w").write(d)
     return LIB
 
