@@ -6,8 +6,9 @@
 `cfg` uses the reference's config keys (ssds/core/config.py): MODEL.{SSDS,NETS,IMAGE_SIZE,
 NUM_CLASSES,FEATURE_LAYER,SIZES,ASPECT_RATIOS}, POST_PROCESS.{SCORE_THRESHOLD,IOU_THRESHOLD,
 MAX_DETECTIONS,MAX_DETECTIONS_PER_LEVEL,USE_DIOU,RESCORE_CENTER}, DATASET.PREPROC.{MEAN,STD}; a path to
-a yml file is accepted too.  On the tcgen05 conv stack in this round: SSD + ResNet*, SSDFPN + ResNet*, SSD + MobileNetV2
-(BiFPN / RegNet are the next rows; YOLO/FSSD/FCOS are out of scope).
+a yml file is accepted too.  On the tcgen05 conv stack: SSD / SSDFPN / SSDBiFPN over ResNet18-152 and
+RegNetX032, SSD over MobileNetV2 (model.ENGINES); YOLO/FSSD/FCOS are out of scope.
+`ssds_pytorch_b200.checkpoint.detector_from_checkpoint` builds one from a reference `.pth`.
 
 One process per GPU.  Under torch.distributed each rank runs its shard of the batch and
 `gather_detections` all-gathers the fixed-size [B,D,6] detection block over NCCL — the only
