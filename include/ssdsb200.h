@@ -45,7 +45,14 @@ typedef enum {
 
 #define SSDSB_MAX_LEVELS 8
 
-SSDSB_API int ssdsb_version(void);
+#define SSDSB_ABI_VERSION 200
+
+SSDSB_API int ssdsb_version(void);          /* == SSDSB_ABI_VERSION of the header the library was built from */
+
+/* ABI handshake for bindings (ctypes / cgo / JNI): out4 = {SSDSB_ABI_VERSION, sizeof(ssdsb_conv_desc),
+ * sizeof(ssdsb_level), SSDSB_MAX_LEVELS}.  A binding compares these with its own mirror of the structs and
+ * refuses to load a library built from a different header. */
+SSDSB_API int ssdsb_abi_info(int* out4);
 SSDSB_API const char* ssdsb_last_error_string(void);
 
 /* ---------------------------------------------------------------------------------------------
@@ -178,6 +185,43 @@ SSDSB_API int ssdsb_loc_loss_sum_backward(const float* d_pred, const float* d_ta
                                           const float* d_scale, float* d_grad_pred, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * The loss half of one training step in ONE launch (loss_step.cu): for every level and image,
+ * extract_targets (IoU matcher, box.py:362-405) + the classification criterion (MultiBoxLoss with per-image
+ * hard-negative mining, criterion.py:43-71, or FocalLoss :95-108) * (depth >= 0) + the localisation criterion
+ * (SmoothL1 :138-151 or iou/giou/diou/ciou :175-239) * (depth > 0), summed, and the caller's normalisation
+ *   fg_targets = sum_l max(#(depth_l > 0), 1);  cls_loss = sum / fg_targets;  loc_loss = sum / fg_targets
+ * exactly as ssds/pipeline/pipeline_anchor_basic.py:62-97 sequences them.  Reads every logit once; no one-hot
+ * target, and no depth / box_target tensor unless the level asks for them.  Deterministic; no host sync;
+ * CUDA-graph capturable.  MATCHER.CENTER_SAMPLING_RADIUS must be 0 (the default): the class of a positive is
+ * depth-1.  BCE uses ex2.approx + a degree-8 log1p polynomial (relative error <= 5e-7 per element; hard
+ * negatives whose max-CE differ by less than that may swap at the cut).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct ssdsb_loss_level {
+  const float* conf;    /* [B, A*C, H, W] raw logits (model in training mode, ssd.py:72-73)            */
+  const float* loc;     /* [B, A*4, H, W] raw deltas; may be NULL when loc_kind == SSDSB_LOC_NONE      */
+  const float* anchors; /* [A, 4] base anchors (device, 16-byte aligned)                                */
+  float* depth;         /* optional out [B,A,1,H,W] (what extract_targets returns), or NULL            */
+  float* box_target;    /* optional out [B,A,4,H,W], or NULL                                            */
+  int A, C, H, W, stride;
+} ssdsb_loss_level;
+
+enum { SSDSB_CLS_MULTIBOX = 0, SSDSB_CLS_FOCAL = 1 };
+enum { SSDSB_LOC_NONE = -1, SSDSB_LOC_SMOOTHL1 = 0, SSDSB_LOC_IOU = 1, SSDSB_LOC_GIOU = 2, SSDSB_LOC_DIOU = 3,
+       SSDSB_LOC_CIOU = 4 };
+
+SSDSB_API size_t ssdsb_detection_loss_workspace_bytes(const ssdsb_loss_level* levels, int n_levels, int B);
+SSDSB_API int ssdsb_detection_loss(const ssdsb_loss_level* levels, int n_levels, int B,
+                                   const float* d_targets /*[B,T,5] (x,y,w,h,label), label <= -1: padding*/, int T,
+                                   float match_threshold, float unmatch_threshold,
+                                   int cls_kind, int negpos_ratio, float focal_alpha, float focal_gamma,
+                                   int loc_kind, float smoothl1_beta,
+                                   float* d_out_scalars /*[3] cls_loss, loc_loss, fg_targets*/,
+                                   float* d_out_cls_sum /*[L*B] per (level, image), may be NULL*/,
+                                   float* d_out_loc_sum /*[L*B], may be NULL*/,
+                                   float* d_out_num_pos /*[L*B], may be NULL*/,
+                                   void* d_workspace /*256-byte aligned*/, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Conv stack (tcgen05 / TMA implicit GEMM), bf16 x bf16 -> fp32 accumulate.
  * One call replaces nn.Conv2d -> BatchNorm2d(eval, folded) -> [+ residual] -> [ReLU] of the
  * reference model graph (ssds/modeling/ssds/ssd.py:42-74, nets/resnet.py:41-56, torchvision
@@ -224,6 +268,12 @@ typedef struct {
 SSDSB_API int ssdsb_conv2d_bf16(const ssdsb_conv_desc* desc, const void* d_x, const void* d_w,
                                 const float* d_bias, const void* d_residual, void* d_y, void* d_y2,
                                 void* stream);
+
+/* Introspection (no reference counterpart; used by the parity tests and bench.py's self-check to PROVE
+ * which instantiation a shape ran): fills out8 with what the calling thread's last ssdsb_conv2d_bf16
+ * launched: {BLOCK_N, BLOCK_K, ways (interleaved accumulators), weight-resident flag, pipeline stages,
+ * grid, groups, m_tiles % ways (!= 0: the last group runs ghost tiles)}. */
+SSDSB_API int ssdsb_conv_last_launch(int* out8);
 
 /* Two chained pointwise convolutions in one launch (conv_pair.cu):
  *   y1 = act1(conv1x1(x, w1) + bias1 [+ residual]);   y2 = act2(conv1x1(y1, w2) + bias2)
@@ -272,6 +322,11 @@ SSDSB_API int ssdsb_bifpn_fuse_nhwc_bf16(const void* d_a, const void* d_b, const
  * (nearest 2x upsample + add), NHWC bf16, in place on `fine` ([N,H,W,C]; coarse is [N,H/2,W/2,C]). */
 SSDSB_API int ssdsb_upsample2x_add_nhwc_bf16(const void* d_coarse, void* d_fine, int N, int H, int W,
                                              int C, void* stream);
+
+/* YOLOv3 top-down merge (reference ssds/modeling/ssds/yolo.py:70-72): out = cat(fine, nearest_up2(coarse)) along
+ * channels; fine [N,H,W,Cf], coarse [N,H/2,W/2,Cc], out [N,H,W,Cf+Cc], dense NHWC bf16, Cf % 8 == Cc % 8 == 0. */
+SSDSB_API int ssdsb_upsample2x_concat_nhwc_bf16(const void* d_fine, const void* d_coarse, int N, int H, int W,
+                                                int Cf, int Cc, void* d_out, void* stream);
 
 #ifdef __cplusplus
 }

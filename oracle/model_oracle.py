@@ -167,6 +167,42 @@ def ssdfpn_resnet_forward(sd, x, feature_layer, training=False, policy="fp32"):
     return tuple(loc), tuple(conf)
 
 
+def yolov3_resnet_forward(sd, x, feature_layer, training=False, policy="fp32"):
+    """reference yolo.py:44-87 (YOLOV3.forward) on a state_dict, int depths; ConvBNReLU / ConvBNReLUx2 of
+    basic_layers.py:27-57 (plain ReLU).  bf16 policy: every conv output and the concatenated map are stored."""
+    layers = feature_layer[0]
+    outputs = [l for l in layers if isinstance(l, int)]
+    feats = resnet_features(sd, x, outputs, policy)
+    n_back = len(feats)
+    raw_top = feats[-1]
+    xx = feats[-1]
+    for i in range(n_back - 1, -1, -1):                                   # yolo.py:67-74
+        if i != n_back - 1:
+            t = _r(_conv_bn(xx, sd, f"transforms.{i}.0.weight", f"transforms.{i}.1", 1, 1, True, policy), policy)
+            xx = torch.cat((feats[i], F.interpolate(t, scale_factor=2)), dim=1)
+        else:
+            xx = feats[i]
+        p = f"extras.{i}"
+        xx = _r(_conv_bn(xx, sd, p + ".0.weight", p + ".1", 1, 0, True, policy), policy)
+        xx = _r(_conv_bn(xx, sd, p + ".3.weight", p + ".4", 1, 1, True, policy), policy)
+        feats[i] = xx
+    loc, conf = [], []
+    for i in range(len(layers)):                                          # yolo.py:77-84
+        if i < n_back:
+            xx = feats[i]
+        else:
+            src = raw_top if i == n_back else xx
+            xx = _r(_conv_bn(src, sd, f"extras.{i}.0.weight", f"extras.{i}.1", 2, 1, True, policy), policy)
+        outs = []
+        for tower in ("loc", "conf"):
+            t = _r(_conv_bn(xx, sd, f"{tower}.{i}.0.0.weight", f"{tower}.{i}.0.1", 1, 1, True, policy), policy)
+            outs.append(_conv_bn(t, sd, f"{tower}.{i}.1.weight", None, 1, 1, False, policy,
+                                 bias=sd[f"{tower}.{i}.1.bias"]))
+        loc.append(outs[0])
+        conf.append(outs[1] if training else torch.sigmoid(outs[1]))
+    return tuple(loc), tuple(conf)
+
+
 def ssd_mobilenetv2_forward(sd, x, feature_layer, training=False, policy="fp32"):
     """SSD.forward (ssd.py:42-74) over the MobileNetV2 backbone."""
     return ssd_resnet_forward(sd, x, feature_layer, training, policy, backbone="mobilenetv2")

@@ -13,12 +13,20 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libssdsb200.so")
 
 SSDSB_MAX_LEVELS = 8
+ABI_VERSION = 200        # == ssdsb_version(); bumped whenever include/ssdsb200.h changes incompatibly
 
 
 class Level(C.Structure):
     """mirror of `ssdsb_level` (include/ssdsb200.h)."""
     _fields_ = [("conf", C.c_void_p), ("loc", C.c_void_p), ("anchors", C.c_void_p),
                 ("A", C.c_int), ("C", C.c_int), ("H", C.c_int), ("W", C.c_int),
+                ("stride", C.c_int)]
+
+
+class LossLevel(C.Structure):
+    """mirror of `ssdsb_loss_level` (include/ssdsb200.h)."""
+    _fields_ = [("conf", C.c_void_p), ("loc", C.c_void_p), ("anchors", C.c_void_p), ("depth", C.c_void_p),
+                ("box_target", C.c_void_p), ("A", C.c_int), ("C", C.c_int), ("H", C.c_int), ("W", C.c_int),
                 ("stride", C.c_int)]
 
 
@@ -37,16 +45,28 @@ def _load():
     try:
         _build.build()
     except Exception as e:   # noqa: BLE001
-        if not os.path.exists(LIB_PATH):
-            raise ImportError(
-                f"{LIB_PATH} is missing and could not be built ({e}). There is no CPU/PyTorch "
-                "fallback for the hot path.") from e
+        # never load a library that does not match the sources it sits next to: a stale .so with a changed
+        # struct layout or argument list would corrupt memory silently
+        why = "is missing" if not os.path.exists(LIB_PATH) else "is STALE (csrc/ or include/ changed since it was built)"
+        raise ImportError(
+            f"{LIB_PATH} {why} and could not be rebuilt ({e}). There is no CPU/PyTorch fallback for the hot "
+            "path; build it where nvcc exists: python -m ssds_pytorch_b200.build") from e
     lib = C.CDLL(LIB_PATH)
+    # ABI handshake: version + the size of the one struct passed by pointer with many fields
+    lib.ssdsb_abi_info.restype, lib.ssdsb_abi_info.argtypes = C.c_int, [C.POINTER(C.c_int)]
+    abi = (C.c_int * 4)()
+    lib.ssdsb_abi_info(abi)
+    if abi[0] != ABI_VERSION or abi[1] != C.sizeof(ConvDesc) or abi[2] != C.sizeof(Level) or abi[3] != SSDSB_MAX_LEVELS:
+        raise ImportError(f"{LIB_PATH}: ABI mismatch (library version {abi[0]}, sizeof(ssdsb_conv_desc) {abi[1]}, "
+                          f"sizeof(ssdsb_level) {abi[2]}, max levels {abi[3]}; binding expects {ABI_VERSION}, "
+                          f"{C.sizeof(ConvDesc)}, {C.sizeof(Level)}, {SSDSB_MAX_LEVELS})")
     vp, i, f, sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
     fp = C.POINTER(C.c_float)
     lp = C.POINTER(Level)
+    llp = C.POINTER(LossLevel)
     sig = {
         "ssdsb_version": (i, []),
+        "ssdsb_abi_info": (i, [C.POINTER(C.c_int)]),
         "ssdsb_last_error_string": (C.c_char_p, []),
         "ssdsb_generate_anchors": (i, [i, fp, i, fp, i, vp, vp]),
         "ssdsb_anchor_grid": (i, [vp, i, i, i, i, vp, vp]),
@@ -68,11 +88,15 @@ def _load():
         "ssdsb_multibox_loss_sum_backward": (i, [vp, vp, i, i, i, i, i, i, vp, vp, vp, sz, vp]),
         "ssdsb_focal_loss_sum_backward": (i, [vp, vp, i, i, i, i, i, f, f, vp, vp, vp]),
         "ssdsb_loc_loss_sum_backward": (i, [vp, vp, vp, i, i, i, i, i, f, vp, vp, vp]),
+        "ssdsb_detection_loss_workspace_bytes": (sz, [llp, i, i]),
+        "ssdsb_detection_loss": (i, [llp, i, i, vp, i, f, f, i, i, f, f, i, f, vp, vp, vp, vp, vp, sz, vp]),
         "ssdsb_conv1x1_pair_bf16": (i, [i, i, i, i, i, i, i, i, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+        "ssdsb_conv_last_launch": (i, [C.POINTER(C.c_int)]),
         "ssdsb_conv2d_bf16": (i, [C.POINTER(ConvDesc), vp, vp, vp, vp, vp, vp, vp]),
         "ssdsb_pack_image_s2d": (i, [vp, i, i, i, i, f, f, i, i, vp, vp]),
         "ssdsb_maxpool3x3s2_nhwc_bf16": (i, [vp, i, i, i, i, vp, vp]),
         "ssdsb_upsample2x_add_nhwc_bf16": (i, [vp, vp, i, i, i, i, vp]),
+        "ssdsb_upsample2x_concat_nhwc_bf16": (i, [vp, vp, i, i, i, i, i, vp, vp]),
         "ssdsb_dwconv3x3_nhwc_bf16": (i, [vp, vp, vp, i, i, i, i, i, i, vp, vp]),
         "ssdsb_bifpn_fuse_nhwc_bf16": (i, [vp, vp, vp, i, f, f, f, i, i, i, i, vp, vp]),
     }

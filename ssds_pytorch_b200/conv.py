@@ -82,6 +82,13 @@ def conv2d(x, w, bias, KH, KW, stride, pad, relu=False, residual=None, out=None,
     return out
 
 
+def last_launch():
+    """{block_n, block_k, ways, b_resident, stages, grid, groups, ghost} of this thread's last conv2d."""
+    out = (C.c_int * 8)()
+    check(lib.ssdsb_conv_last_launch(out), "conv_last_launch")
+    return dict(zip(("block_n", "block_k", "ways", "b_resident", "stages", "grid", "groups", "ghost"), list(out)))
+
+
 def sm_count():
     return torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
 
@@ -174,6 +181,19 @@ def upsample2x_add(coarse, fine):
         check(lib.ssdsb_upsample2x_add_nhwc_bf16(ptr(coarse), ptr(fine), N, H, W, Cc, stream_ptr()),
               "upsample2x_add")
     return fine
+
+
+def upsample2x_concat(fine, coarse, out=None):
+    """cat(fine, nearest-2x-upsampled coarse) along channels (YOLOv3 top-down merge, yolo.py:70-72); NHWC bf16."""
+    N, H, W, Cf = fine.shape
+    Cc = coarse.shape[3]
+    assert coarse.shape == (N, H // 2, W // 2, Cc) and fine.is_contiguous() and coarse.is_contiguous()
+    if out is None:
+        out = torch.empty((N, H, W, Cf + Cc), dtype=torch.bfloat16, device=fine.device)
+    with torch.cuda.device(fine.device):
+        check(lib.ssdsb_upsample2x_concat_nhwc_bf16(ptr(fine), ptr(coarse), N, H, W, Cf, Cc, ptr(out), stream_ptr()),
+              "upsample2x_concat")
+    return out
 
 
 def pack_dw_weight(w_folded, c_pad=None):

@@ -225,3 +225,16 @@ class IOULoss(_LocLoss):
             raise NotImplementedError(loss_type)        # criterion.py:231
         self.loss_type = loss_type
         self._type = self.TYPES[loss_type]
+
+
+def GIOULoss(**kwargs):
+    """reference criterion.py factory names: `getattr(criterion, cfg.MATCHER.LOCATE_LOSS)()` must resolve."""
+    return IOULoss(loss_type="giou", **kwargs)
+
+
+def DIOULoss(**kwargs):
+    return IOULoss(loss_type="diou", **kwargs)
+
+
+def CIOULoss(**kwargs):
+    return IOULoss(loss_type="ciou", **kwargs)

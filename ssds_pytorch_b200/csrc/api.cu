@@ -22,6 +22,15 @@ int fail(int code, const char* fmt, ...) {
 
 }  // namespace ssdsb
 
-extern "C" int ssdsb_version(void) { return 100; }
+extern "C" int ssdsb_version(void) { return SSDSB_ABI_VERSION; }
+
+extern "C" int ssdsb_abi_info(int* out4) {
+  if (!out4) return ssdsb::fail(SSDSB_ERR_INVALID_ARGUMENT, "abi_info: NULL argument");
+  out4[0] = SSDSB_ABI_VERSION;
+  out4[1] = (int)sizeof(ssdsb_conv_desc);
+  out4[2] = (int)sizeof(ssdsb_level);
+  out4[3] = SSDSB_MAX_LEVELS;
+  return SSDSB_OK;
+}
 
 extern "C" const char* ssdsb_last_error_string(void) { return ssdsb::last_error().c_str(); }

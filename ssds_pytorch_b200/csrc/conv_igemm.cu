@@ -490,10 +490,18 @@ int pick_block_n(int cout) {
   return 256;
 }
 
+// what the last ssdsb_conv2d_bf16 call of this thread launched (ssdsb_conv_last_launch; tests assert
+// that the BASELINE shapes really run the multi-way / weight-resident instantiations)
+thread_local int g_last_launch[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+
 template <int BLOCK_N, int BLOCK_K, int WAYS>
 int launch_ways(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY,
                 const CUtensorMap& tmR, const ConvKernelParams& kp, int grid, int smem, cudaStream_t st) {
   using S = ConvSmem<BLOCK_N, BLOCK_K>;
+  const int m_tiles = kp.tiles_w * kp.tiles_h * kp.tiles_n;
+  const int info[8] = {BLOCK_N, BLOCK_K, WAYS, kp.b_resident, kp.stages, grid,
+                       ((m_tiles + WAYS - 1) / WAYS) * kp.n_tiles, m_tiles % WAYS};
+  for (int i = 0; i < 8; ++i) g_last_launch[i] = info[i];
   static bool configured = false;
   if (!configured) {
     SSDSB_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BLOCK_N, BLOCK_K, WAYS>,
@@ -580,6 +588,12 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tm
 }  // namespace ssdsb
 
 using namespace ssdsb;
+
+extern "C" int ssdsb_conv_last_launch(int* out8) {
+  SSDSB_REQUIRE(out8, "conv_last_launch: NULL argument");
+  for (int i = 0; i < 8; ++i) out8[i] = g_last_launch[i];
+  return SSDSB_OK;
+}
 
 extern "C" int ssdsb_conv2d_bf16(const ssdsb_conv_desc* d, const void* x, const void* w,
                                  const float* bias, const void* residual, void* y, void* y2,

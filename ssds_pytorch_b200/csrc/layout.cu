@@ -132,6 +132,27 @@ upsample2x_add_kernel(const uint4* __restrict__ coarse, uint4* __restrict__ fine
   }
 }
 
+// out[n,h,w,:] = cat(fine[n,h,w,:], coarse[n,h/2,w/2,:])  — YOLOv3's top-down merge
+// torch.cat((features[i], F.interpolate(transforms[i](xx), scale_factor=2)), dim=1) (yolo.py:70-72) in NHWC:
+// one pass, 8 channels (16 bytes) per thread, both sources read once.
+__global__ void __launch_bounds__(256)
+upsample2x_concat_kernel(const uint4* __restrict__ fine, const uint4* __restrict__ coarse, uint4* __restrict__ out,
+                         int N, int H, int W, int Cf8, int Cc8) {
+  const int Co8 = Cf8 + Cc8;
+  const size_t total = (size_t)N * H * W * Co8;
+  const int Hc = H >> 1, Wc = W >> 1;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % Co8);
+    const size_t pix = i / Co8;
+    const int w = (int)(pix % W);
+    const int h = (int)((pix / W) % H);
+    const int n = (int)(pix / ((size_t)W * H));
+    out[i] = (c < Cf8) ? __ldg(fine + pix * Cf8 + c)
+                       : __ldg(coarse + (((size_t)n * Hc + (h >> 1)) * Wc + (w >> 1)) * Cc8 + (c - Cf8));
+  }
+}
+
 // BiFPN weighted fusion (reference ssds/modeling/ssds/bifpn.py:41-62), NHWC bf16, 8 channels/thread:
 //   mode 0 (top-down):  out = w0*a + w1*nearest_up2(b)            a [N,H,W,C], b [N,H/2,W/2,C]
 //   mode 1 (bottom-up): out = w0*a + w1*maxpool2x2(b) [+ w2*c]    a,c [N,H,W,C], b [N,2H,2W,C]
@@ -302,6 +323,25 @@ extern "C" int ssdsb_upsample2x_add_nhwc_bf16(const void* d_coarse, void* d_fine
   upsample2x_add_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const uint4*>(d_coarse), reinterpret_cast<uint4*>(d_fine), N, H, W, C / 8);
   SSDSB_LAUNCH_CHECK("upsample2x_add_kernel");
+  return SSDSB_OK;
+}
+
+extern "C" int ssdsb_upsample2x_concat_nhwc_bf16(const void* d_fine, const void* d_coarse, int N, int H, int W,
+                                                 int Cf, int Cc, void* d_out, void* stream) {
+  SSDSB_REQUIRE(d_fine && d_coarse && d_out, "upsample2x_concat: NULL argument");
+  SSDSB_REQUIRE(N >= 1 && H >= 2 && W >= 2 && (H % 2) == 0 && (W % 2) == 0 && Cf >= 8 && Cf % 8 == 0 && Cc >= 8 &&
+                    Cc % 8 == 0,
+                "upsample2x_concat: the fine map must be even-sized, channel counts multiples of 8 "
+                "(N=%d H=%d W=%d Cf=%d Cc=%d)", N, H, W, Cf, Cc);
+  SSDSB_REQUIRE((((uintptr_t)d_fine | (uintptr_t)d_coarse | (uintptr_t)d_out) & 15) == 0,
+                "upsample2x_concat: pointers must be 16-byte aligned");
+  const size_t total = (size_t)N * H * W * ((Cf + Cc) / 8);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  upsample2x_concat_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const uint4*>(d_fine), reinterpret_cast<const uint4*>(d_coarse),
+      reinterpret_cast<uint4*>(d_out), N, H, W, Cf / 8, Cc / 8);
+  SSDSB_LAUNCH_CHECK("upsample2x_concat_kernel");
   return SSDSB_OK;
 }
 

@@ -153,6 +153,8 @@ class _Engine(torch.nn.Module):
             y = buf(n, ho, wo, c)
             steps.append(lambda: K.dwconv3x3(x, dw.w, dw.bias, dw.stride, dw.relu, out=y))
             flops[0] += dw.flops_per_pixel * n * ho * wo
+            info[len(steps) - 1] = {"kind": f"dw3x3s{dw.stride} {c} @{ho}x{wo}", "flops": dw.flops_per_pixel * n * ho * wo,
+                                    "bytes": 2 * (x.numel() + y.numel() + dw.w.numel())}
             return y
 
         def add_raw(fn, nflops, kind="raw", nbytes=0):
@@ -607,6 +609,84 @@ class _BiFPNNeck(_FPNNeck):
         return xx
 
 
+class _YOLOV3Neck:
+    """YOLOv3 neck + heads (reference ssds/modeling/ssds/yolo.py:44-160; the model of the shipped
+    experiments/cfgs/tests/test.yml).  Top-down from the last backbone level: extras[i] = ConvBNReLUx2 (1x1 then
+    3x3), transforms[i] = ConvBNReLU 3x3 + nearest-2x upsample, concatenated AFTER the backbone feature
+    (torch.cat((features[i], xx), 1), yolo.py:70-72) -> one `upsample2x_concat` launch; 'Conv:S' extras are
+    stride-2 ConvBNReLU on the raw last backbone map / the previous extra (yolo.py:77-82).  Heads are per
+    level Sequential(ConvBNReLU(c, c, 3), Conv2d(c, A*4 | A*C, 3)): the loc and conf towers read the same map,
+    so their first convs run as ONE c -> 2c launch and the final convs read their half through the channel
+    stride.  All activations are plain ReLU in this reference (basic_layers.py:27-57)."""
+
+    def _build_neck(self, sd, feature_layer):
+        dev = self.device
+        layers, depths = feature_layer
+        if any(isinstance(d, list) for d in depths):
+            raise NotImplementedError("YOLOV3 with [in, out] depth pairs is not on the tcgen05 conv stack yet")
+        n_back = len(self.outputs)
+        self.transforms = [_Conv(sd[f"transforms.{i}.0.weight"], _bn(sd, f"transforms.{i}.1"), None, 1, 1, True, dev)
+                           for i in range(n_back - 1)]
+        self.extras = []
+        for i, layer in enumerate(layers):
+            p = f"extras.{i}"
+            if isinstance(layer, int):
+                self.extras.append([_Conv(sd[p + ".0.weight"], _bn(sd, p + ".1"), None, 1, 0, True, dev),
+                                    _Conv(sd[p + ".3.weight"], _bn(sd, p + ".4"), None, 1, 1, True, dev)])
+            elif layer == "Conv:S":
+                self.extras.append([_Conv(sd[p + ".0.weight"], _bn(sd, p + ".1"), None, 2, 1, True, dev)])
+            else:
+                raise ValueError(layer + " does not support by YOLO")            # yolo.py:136
+        self.towers, self.head_loc, self.head_conf = [], [], []
+        for l in range(len(layers)):
+            w0 = torch.cat([sd[f"loc.{l}.0.0.weight"], sd[f"conf.{l}.0.0.weight"]], 0)
+            bn0 = tuple(torch.cat([a, b], 0) if isinstance(a, torch.Tensor) else a
+                        for a, b in zip(_bn(sd, f"loc.{l}.0.1"), _bn(sd, f"conf.{l}.0.1")))
+            self.towers.append(_Conv(w0, bn0, None, 1, 1, True, dev))
+            hl = _Conv(sd[f"loc.{l}.1.weight"], None, sd[f"loc.{l}.1.bias"], 1, 1, False, dev)
+            hl.n_loc = hl.cout
+            hc = _Conv(sd[f"conf.{l}.1.weight"], None, sd[f"conf.{l}.1.bias"], 1, 1, False, dev)
+            hc.n_loc = 0
+            self.head_loc.append(hl)
+            self.head_conf.append(hc)
+
+    def _plan_neck(self, feats, steps, buf, add_conv, add_head):
+        n_back = len(feats)
+        feats = list(feats)
+        raw_top = feats[-1]
+        xx = None
+        for i in range(n_back - 1, -1, -1):                                       # yolo.py:67-74
+            if i != n_back - 1:
+                t = add_conv(self.transforms[i], xx)
+                n, h, w, cf = feats[i].shape
+                cat = buf(n, h, w, cf + t.shape[3])
+                steps.append(lambda f=feats[i], c=t, o=cat: K.upsample2x_concat(f, c, out=o))
+                xx = cat
+            else:
+                xx = feats[i]
+            for cv in self.extras[i]:
+                xx = add_conv(cv, xx)
+            feats[i] = xx
+        levels = list(feats)
+        for i in range(n_back, len(self.extras)):                                 # yolo.py:77-82
+            src = raw_top if i == n_back else levels[-1]
+            levels.append(add_conv(self.extras[i][0], src))
+        locs, confs = [], []
+        dev = self.device
+        for l, f in enumerate(levels):
+            t = add_conv(self.towers[l], f)                                       # [.., 2c]: loc half | conf half
+            c = t.shape[3] // 2
+            n, fh, fw, _ = f.shape
+            loc = torch.empty((n, self.head_loc[l].cout, fh, fw), dtype=torch.float32, device=dev)
+            conf = torch.empty((n, self.head_conf[l].cout, fh, fw), dtype=torch.float32, device=dev)
+            dummy = torch.empty((1,), dtype=torch.float32, device=dev)
+            add_head(t[..., :c], self.head_loc[l], loc=loc, conf=dummy)
+            add_head(t[..., c:], self.head_conf[l], loc=dummy, conf=conf)
+            locs.append(loc)
+            confs.append(conf)
+        return locs, confs
+
+
 class SSDResNet(_SSDNeck, _ResNetBackbone, _Engine):
     """SSD + ResNet18/34/50/101/152 (reference cfg SSDS='SSD', NETS='ResNet*')."""
 
@@ -631,7 +711,11 @@ class SSDFPNRegNetX(_FPNNeck, _RegNetXBackbone, _Engine):
     """SSDFPN + RegNetX."""
 
 
-ENGINES = {("SSD", "ResNet"): SSDResNet, ("SSDFPN", "ResNet"): SSDFPNResNet,
+class YOLOV3ResNet(_YOLOV3Neck, _ResNetBackbone, _Engine):
+    """YOLOV3 + ResNet18/34/50/... (reference cfg SSDS='YOLOV3'; experiments/cfgs/tests/test.yml is ResNet18 @320)."""
+
+
+ENGINES = {("YOLOV3", "ResNet"): YOLOV3ResNet, ("SSD", "ResNet"): SSDResNet, ("SSDFPN", "ResNet"): SSDFPNResNet,
            ("SSD", "MobileNetV2"): SSDMobileNetV2, ("SSDBIFPN", "ResNet"): SSDBiFPNResNet,
            ("SSDBIFPN", "RegNetX032"): SSDBiFPNRegNetX, ("SSDFPN", "RegNetX032"): SSDFPNRegNetX}
 

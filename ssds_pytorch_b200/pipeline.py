@@ -70,3 +70,119 @@ def detection_loss_step(loc, conf, targets, anchors, num_classes, cls_criterion=
         fg.append(npos.sum().clamp(min=1))
     fg_targets = torch.stack(fg).sum()
     return torch.stack(cls_sum).sum() / fg_targets, torch.stack(loc_sum).sum() / fg_targets, fg_targets
+
+
+_LOC_KINDS = {None: -1, "none": -1, "SmoothL1Loss": 0, "IOULoss": 1, "GIOULoss": 2, "DIOULoss": 3, "CIOULoss": 4}
+_CLS_KINDS = {"MultiBoxLoss": 0, "FocalLoss": 1}
+
+
+def fused_loss_step(loc, conf, targets, anchors, num_classes, cls_criterion="MultiBoxLoss",
+                    loc_criterion=None, match=(0.5, 0.4), negpos_ratio=3, alpha=0.25, gamma=2.0, beta=0.11,
+                    with_targets=False, out=None):
+    """pipeline_anchor_basic.py:62-97 — match + classification criterion + localisation criterion + masking +
+    normalisation for ALL levels and images in ONE kernel launch (csrc/loss_step.cu, `ssdsb_detection_loss`).
+
+    loc / conf: per-level raw head outputs [B, A*4, H, W] / [B, A*C, H, W] (model in training mode);
+    targets [B,T,5]; anchors OrderedDict{stride: [A,4]}; criteria by the reference's config names
+    (MATCHER.CLASSIFY_LOSS in {MultiBoxLoss, FocalLoss}; MATCHER.LOCATE_LOSS in {SmoothL1Loss, IOULoss, GIOULoss,
+    DIOULoss, CIOULoss} or None to skip).  Returns (scalars [3] = cls_loss, loc_loss, fg_targets — a device tensor,
+    no sync —, per-pair dict with 'cls_sum' / 'loc_sum' / 'num_pos' [L,B], and with_targets: 'depth' /
+    'box_target' lists as extract_targets returns them).  Forward only (not connected to autograd)."""
+    import ctypes as C
+    from . import _lib
+    from ._lib import lib, check, ptr, dev_f32, stream_ptr
+    if cls_criterion not in _CLS_KINDS or loc_criterion not in _LOC_KINDS:
+        raise ValueError(f"fused_loss_step: unknown criterion {cls_criterion!r} / {loc_criterion!r}")
+    L = len(conf)
+    conf = [dev_f32(c) for c in conf]
+    device = conf[0].device
+    B = conf[0].shape[0]
+    loc_kind = _LOC_KINDS[loc_criterion]
+    loc = [dev_f32(l, device) for l in loc] if loc_kind >= 0 else [None] * L
+    targets = dev_f32(targets, device)
+    T = targets.shape[1]
+    levels = (_lib.LossLevel * L)()
+    keep, depths, boxes = [], [], []
+    for i, (c, l, (stride, anchor)) in enumerate(zip(conf, loc, anchors.items())):
+        a = dev_f32(anchor, device)
+        keep.append(a)
+        A = a.shape[0]
+        H, W = c.shape[-2:]
+        if c.shape[1] != A * num_classes or (l is not None and (l.shape[1] != A * 4 or l.shape[-2:] != c.shape[-2:])):
+            raise ValueError(f"fused_loss_step: level {i} shapes {tuple(c.shape)} do not match {A} anchors x "
+                             f"{num_classes} classes")
+        d = torch.empty((B, A, 1, H, W), dtype=torch.float32, device=device) if with_targets else None
+        bt = torch.empty((B, A, 4, H, W), dtype=torch.float32, device=device) if with_targets else None
+        depths.append(d)
+        boxes.append(bt)
+        levels[i] = _lib.LossLevel(c.data_ptr(), l.data_ptr() if l is not None else None, a.data_ptr(),
+                                   d.data_ptr() if d is not None else None,
+                                   bt.data_ptr() if bt is not None else None, A, num_classes, H, W, int(stride))
+    scalars = out if out is not None else torch.empty(3, dtype=torch.float32, device=device)
+    per_pair = torch.empty((3, L, B), dtype=torch.float32, device=device)
+    with torch.cuda.device(device):
+        need = lib.ssdsb_detection_loss_workspace_bytes(levels, L, B)
+        ws = _lib.workspace(need, device)
+        check(lib.ssdsb_detection_loss(levels, L, B, ptr(targets), T, float(match[0]), float(match[1]),
+                                       _CLS_KINDS[cls_criterion], int(negpos_ratio), float(alpha), float(gamma),
+                                       loc_kind, float(beta), ptr(scalars), ptr(per_pair[0]), ptr(per_pair[1]),
+                                       ptr(per_pair[2]), ptr(ws), ws.numel(), stream_ptr()), "fused_loss_step")
+    parts = {"cls_sum": per_pair[0], "loc_sum": per_pair[1], "num_pos": per_pair[2]}
+    if with_targets:
+        parts["depth"], parts["box_target"] = depths, boxes
+    return scalars, parts
+
+
+class LossStep(object):
+    """Host-facing training-step front half (pipeline_anchor_basic.py:56-97 up to the loss scalars): a pinned
+    host batch (uint8 NHWC images + [B,T,5] targets) -> H2D -> conv stack in training mode (raw logits) ->
+    match + hard-negative-mined MultiBoxLoss (or Focal + SmoothL1) -> the loss scalars back on the host.
+
+        step = LossStep(cfg, state_dict)                 # cfg: the reference's yml keys (see ssds.load_cfg)
+        out = step.loss_host(images, targets)            # pinned [3] (cls_loss, loc_loss, fg_targets), after step.sync()
+
+    One process per GPU; ranks normalise by their local foreground count like the reference
+    (pipeline_anchor_apex.py:69-71), so there is no collective on this path."""
+
+    def __init__(self, cfg, state_dict, device=None, use_graph=True, cls_criterion="MultiBoxLoss",
+                 loc_criterion=None):
+        from .ssds import load_cfg
+        from .model import engine_for, create_anchors, number_box_from_cfg
+        cfg = load_cfg(cfg)
+        m = cfg["MODEL"]
+        self.device = (torch.device(device) if device is not None
+                       else torch.device("cuda", torch.cuda.current_device()))
+        self.model = engine_for(m["SSDS"], m["NETS"])(
+            state_dict, m["FEATURE_LAYER"], m["NUM_CLASSES"], number_box_from_cfg(m), device=self.device,
+            mean=float(cfg["DATASET"]["PREPROC"]["MEAN"]), std=float(cfg["DATASET"]["PREPROC"]["STD"]))
+        self.model.eval()
+        self.anchors = create_anchors(m, self.model, m["IMAGE_SIZE"])
+        self.model.train()
+        self.num_classes = m["NUM_CLASSES"]
+        self.use_graph = use_graph
+        self.cls_criterion, self.loc_criterion = cls_criterion, loc_criterion
+        self._stage = {}
+
+    def loss_device(self, images, targets):
+        """-> device tensor [3] = (cls_loss, loc_loss, fg_targets); loc_loss is 0 when loc_criterion is None."""
+        loc, conf = self.model(images, use_graph=self.use_graph)
+        scalars, _ = fused_loss_step(loc, conf, targets, self.anchors, self.num_classes, self.cls_criterion,
+                                     self.loc_criterion)
+        return scalars
+
+    def loss_host(self, images, targets):
+        images, targets = torch.as_tensor(images), torch.as_tensor(targets)
+        key = (tuple(images.shape), images.dtype, tuple(targets.shape))
+        st = self._stage.get(key)
+        if st is None:
+            st = {"img": torch.empty(images.shape, dtype=images.dtype, device=self.device),
+                  "tg": torch.empty(targets.shape, dtype=torch.float32, device=self.device),
+                  "out": torch.empty(3, dtype=torch.float32).pin_memory()}
+            self._stage[key] = st
+        st["img"].copy_(images, non_blocking=True)
+        st["tg"].copy_(targets, non_blocking=True)
+        st["out"].copy_(self.loss_device(st["img"], st["tg"]), non_blocking=True)
+        return st["out"]
+
+    def sync(self):
+        torch.cuda.current_stream(self.device).synchronize()

@@ -75,6 +75,7 @@ class SSDDetector(object):
         self._copy_stream = None
         self._post_stream = None        # decode + NMS of step i overlap the backbone of step i+1
         self._post_done = None
+        self._post_out = None
 
     # -------------------------------------------------------------- device-side entry points
     def detect_device(self, images, overlap=False):
@@ -84,7 +85,9 @@ class SSDDetector(object):
 
         overlap=True runs decode + NMS on a side stream so that they overlap the conv stack of the next
         call (the memory-/latency-bound post-processing hides behind tensor-core work); the results are
-        then produced on that stream — call `join()` (or use `detect_host`) before consuming them."""
+        then produced on that stream — call `join()` before consuming them on the current stream (join makes
+        the current stream wait for the side stream and hands the returned tensors over to it with
+        `record_stream`, so the caching allocator cannot recycle them under a pending reader)."""
         if not overlap:
             loc, conf = self.model(images, use_graph=self.use_graph)
             return self.decoder(loc, conf, self.anchors)
@@ -99,18 +102,31 @@ class SSDDetector(object):
             out = self.decoder(loc, conf, self.anchors)
             self._post_done = torch.cuda.Event()
             self._post_done.record(self._post_stream)
+        self._post_out = out
         return out
 
     def join(self):
-        """Make the current stream wait for the side-stream post-processing of the last call."""
+        """Make the current stream wait for the side-stream post-processing of the last call.  Tensors returned
+        by `detect_device(overlap=True)` were allocated on the side stream: they are handed to the current
+        stream here (`record_stream`) so that freeing them cannot let the allocator reuse their memory on
+        the side stream while the current stream still reads them."""
         if self._post_done is not None:
-            torch.cuda.current_stream().wait_event(self._post_done)
+            cur = torch.cuda.current_stream()
+            cur.wait_event(self._post_done)
+            for t in self._post_out or ():
+                if isinstance(t, torch.Tensor) and t.is_cuda:
+                    t.record_stream(cur)
+            self._post_out = None
 
     def detect_host(self, imgs, out=None, slot=0, gather=False):
         """Host numpy/torch batch -> pinned staging -> H2D -> detect -> [all-gather] -> packed
         [B,D,6] on the host (score, x1, y1, x2, y2, class).  The H2D copy runs on a side stream into
         one of two device slots, so the copy of step i+1 overlaps the kernels of step i when callers
-        alternate `slot`.  One small D2H copy; the caller synchronises the current stream."""
+        alternate `slot`.  One small D2H copy into the returned pinned tensor, issued on the post-processing
+        side stream: the result is valid only after `det.join()` followed by a synchronize of the current
+        stream (what `__call__` does); syncing the current stream alone is NOT enough.
+        Unpinned input is first copied into the slot's pinned staging buffer; that host copy waits for the
+        slot's previous H2D transfer, so pipelined callers cannot overwrite bytes the GPU has not read yet."""
         t = torch.as_tensor(imgs)
         key = (tuple(t.shape), t.dtype, slot)
         st = self._stage.get(key)
@@ -119,13 +135,17 @@ class SSDDetector(object):
             st = {"pin_in": torch.empty(t.shape, dtype=t.dtype).pin_memory(),
                   "dev_in": torch.empty(t.shape, dtype=t.dtype, device=self.device),
                   "dev_out": torch.empty((t.shape[0], D, 6), dtype=torch.float32, device=self.device),
-                  "pin_out": None, "copied": torch.cuda.Event(), "consumed": torch.cuda.Event()}
+                  "pin_out": None, "copied": torch.cuda.Event(), "consumed": torch.cuda.Event(),
+                  "pin_used": False}
             st["consumed"].record()
             self._stage[key] = st
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=self.device)
         if not t.is_pinned():
+            if st["pin_used"]:
+                st["copied"].synchronize()        # the previous async H2D copy out of pin_in must have finished
             st["pin_in"].copy_(t)
+            st["pin_used"] = True
             t = st["pin_in"]
         cur = torch.cuda.current_stream()
         self._copy_stream.wait_event(st["consumed"])      # the slot's previous user has read it
@@ -178,16 +198,33 @@ class SSDDetector(object):
         return out_scores, out_boxes.astype(int), out_classes.astype(int)
 
 
-def gather_detections(det_local, group=None):
+def gather_detections(det_local, group=None, n_items=None):
     """All-gather the per-rank detection block [B_local, D, 6] -> [B_global, D, 6] (NCCL over
-    NVLink on the GPU box, gloo in the CPU tests).  Ranks hold contiguous shards of the batch."""
+    NVLink on the GPU box, gloo in the CPU tests).  Ranks hold contiguous shards of the batch.
+
+    `all_gather_into_tensor` needs the same shard size on every rank: pass `n_items` (the global batch)
+    when it is not divisible by the world size — every rank then pads its `shard_batch` shard with zero rows
+    to ceil(n_items / world) before the collective and the padding is trimmed afterwards.  Without
+    `n_items` the shards must be equal (checked with a cheap all-reduce only in debug mode, so stated here)."""
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return det_local
     world = dist.get_world_size(group)
-    out = torch.empty((world * det_local.shape[0],) + tuple(det_local.shape[1:]),
-                      dtype=det_local.dtype, device=det_local.device)
+    per = det_local.shape[0]
+    if n_items is not None:
+        per = (n_items + world - 1) // world
+        if det_local.shape[0] > per:
+            raise ValueError(f"gather_detections: local shard of {det_local.shape[0]} rows exceeds ceil({n_items}/{world})")
+        if det_local.shape[0] < per:
+            pad = torch.zeros((per - det_local.shape[0],) + tuple(det_local.shape[1:]), dtype=det_local.dtype,
+                              device=det_local.device)
+            det_local = torch.cat([det_local, pad], 0)
+    out = torch.empty((world * per,) + tuple(det_local.shape[1:]), dtype=det_local.dtype, device=det_local.device)
     dist.all_gather_into_tensor(out, det_local.contiguous(), group=group)
+    if n_items is not None and world * per != n_items:
+        # rank r holds rows [r*per, min((r+1)*per, n_items)): drop each rank's padding
+        keep = [out[r * per:r * per + max(0, min(per, n_items - r * per))] for r in range(world)]
+        out = torch.cat(keep, 0)
     return out
 
 

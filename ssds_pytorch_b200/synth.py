@@ -148,10 +148,55 @@ def model_shapes(ssds, nets, feature_layer, number_box, num_classes):
         back = resnet_backbone_shapes(nets)
     if ssds == "SSD":
         return back + ssd_neck_shapes(feature_layer, number_box, num_classes)
+    if ssds == "YOLOV3":
+        return back + yolov3_neck_shapes(feature_layer, number_box, num_classes)
     stacks = 0
     if ssds == "SSDBIFPN":
         stacks = 1 if len(feature_layer) == 2 else feature_layer[2]
     return back + fpn_neck_shapes(feature_layer, number_box, num_classes, stacks)
+
+
+def yolov3_neck_shapes(feature_layer, number_box, num_classes):
+    """YOLOV3.add_extras (yolo.py:88-160) with int depths: transforms.{i} = ConvBNReLU 3x3 on every backbone level
+    but the last, extras.{i} = ConvBNReLUx2 (levels) / ConvBNReLU stride 2 ('Conv:S'), per-level heads
+    loc.{l} / conf.{l} = Sequential(ConvBNReLU(c, c, 3), Conv2d(c, A*4 | A*C, 3))."""
+    layers, depths = feature_layer
+    if any(isinstance(d, list) for d in depths):
+        raise NotImplementedError("YOLOV3 with [in, out] depth pairs is not packed here")
+    ints = [l for l in layers if isinstance(l, int)]
+    tr, ex, heads = [], [], []
+    in_ch = None
+    for idx, (layer, depth) in enumerate(zip(layers, depths)):
+        if isinstance(layer, int):
+            if layer == ints[-1]:
+                ex.append(("x2", depth, depth // 2))
+            else:
+                prev = depths[idx + 1]
+                tr.append((prev // 2, depth // 2))
+                ex.append(("x2", int(depth * 1.5), depth // 2))
+            head_c = depth // 2
+        elif layer == "Conv:S":
+            ex.append(("s2", in_ch, depth))
+            head_c = depth
+        else:
+            raise ValueError(layer + " does not support by YOLO")
+        heads.append(head_c)
+        in_ch = depth
+    out = []
+    for i, (cin, cout) in enumerate(tr):
+        out.append((f"transforms.{i}.0.weight", (cout, cin, 3, 3))); _bn_keys(out, f"transforms.{i}.1", cout)
+    for i, (kind, cin, cout) in enumerate(ex):
+        if kind == "x2":
+            out.append((f"extras.{i}.0.weight", (cout // 2, cin, 1, 1))); _bn_keys(out, f"extras.{i}.1", cout // 2)
+            out.append((f"extras.{i}.3.weight", (cout, cout // 2, 3, 3))); _bn_keys(out, f"extras.{i}.4", cout)
+        else:
+            out.append((f"extras.{i}.0.weight", (cout, cin, 3, 3))); _bn_keys(out, f"extras.{i}.1", cout)
+    for tower, per in (("loc", 4), ("conf", num_classes)):
+        for l, (c, nb) in enumerate(zip(heads, number_box)):
+            out.append((f"{tower}.{l}.0.0.weight", (c, c, 3, 3))); _bn_keys(out, f"{tower}.{l}.0.1", c)
+            out.append((f"{tower}.{l}.1.weight", (nb * per, c, 3, 3)))
+            out.append((f"{tower}.{l}.1.bias", (nb * per,)))
+    return out
 
 
 def ssd_neck_shapes(feature_layer, number_box, num_classes):
@@ -261,8 +306,11 @@ def synthetic_state_dict(nets, feature_layer, number_box, num_classes, seed=0, s
     shapes = model_shapes(ssds, nets, feature_layer, number_box, num_classes)
     bn_prefixes = {k.rsplit(".", 1)[0] for k, _ in shapes if k.endswith("running_mean")}
     fpn_like = ssds.upper() != "SSD"
-    head_final = {k for k, _ in shapes if k.startswith(("loc.", "conf.")) and
-                  k.rsplit(".", 1)[0] not in bn_prefixes and (not fpn_like or k.split(".")[1] == "4")}
+    if ssds.upper() == "YOLOV3":
+        head_final = {k for k, _ in shapes if k.startswith(("loc.", "conf.")) and k.split(".")[2] == "1"}
+    else:
+        head_final = {k for k, _ in shapes if k.startswith(("loc.", "conf.")) and
+                      k.rsplit(".", 1)[0] not in bn_prefixes and (not fpn_like or k.split(".")[1] == "4")}
     for key, shape in shapes:
         if key.endswith("num_batches_tracked"):
             sd[key] = torch.tensor(0, dtype=torch.long)
@@ -292,7 +340,8 @@ def synthetic_state_dict(nets, feature_layer, number_box, num_classes, seed=0, s
             sd[key] = torch.randn(shape, generator=g) * (0.01 if style == "init" else 0.03)
         elif key.startswith("transforms."):
             if key.endswith("weight"):
-                fan_in, fan_out = shape[1], shape[0]
+                k2 = shape[2] * shape[3] if len(shape) == 4 else 1
+                fan_in, fan_out = shape[1] * k2, shape[0] * k2
                 a = math.sqrt(6.0 / (fan_in + fan_out))
                 sd[key] = (torch.rand(shape, generator=g) * 2 - 1) * a
             else:
@@ -308,3 +357,16 @@ def synthetic_state_dict(nets, feature_layer, number_box, num_classes, seed=0, s
             fan_out = shape[0] * shape[2] * shape[3]
             sd[key] = torch.randn(shape, generator=g) * math.sqrt(2.0 / fan_out)
     return sd
+
+
+def synthetic_targets(B, T=32, seed=4321):
+    """SURVEY 8d cfg-4 targets [B,T,5] = (x, y, w, h, label): per image n~U{1..T} boxes, xy~U(0,480),
+    wh~U(16,256), label~U{0..79}; unused rows are -1 (the reference's padding, dataset_factory.py:29-35)."""
+    g = torch.Generator().manual_seed(seed)
+    tg = torch.full((B, T, 5), -1.0)
+    for b in range(B):
+        n = int(torch.randint(1, T + 1, (1,), generator=g))
+        tg[b, :n, :2] = torch.rand((n, 2), generator=g) * 480
+        tg[b, :n, 2:4] = torch.rand((n, 2), generator=g) * 240 + 16
+        tg[b, :n, 4] = torch.randint(0, 80, (n,), generator=g).float()
+    return tg

@@ -23,7 +23,12 @@ CASES = {
     "r18": ("ResNet18", [[3, 4, 5, "Conv:S"], [128, 256, 512, 256]], 20, 3, [96, 160]),
     "r50": ("ResNet50", [[3, 4, 5, "Conv:S", "Conv:S", "Conv:S"], [512, 1024, 2048, 512, 256, 256]], 80, 1,
             [256, 256]),
+    # the model of the reference's shipped experiments/cfgs/tests/test.yml (YOLOV3 + ResNet18, 80 classes)
+    "yolo": ("ResNet18", [[3, 4, 5], [128, 256, 512]], 80, 2, [128, 160]),
+    "yolo50x": ("ResNet50", [[3, 4, 5, "Conv:S"], [512, 1024, 2048, 512]], 20, 2, [128, 128]),
 }
+NBOX = {"yolo": [6, 6, 9]}
+SSDS_OF = {"fpn50": "SSDFPN", "bifpn": "SSDBiFPN", "yolo": "YOLOV3", "yolo50x": "YOLOV3"}
 
 
 @pytest.fixture(scope="module")
@@ -41,14 +46,15 @@ def build(tag, S):
     from ssds_pytorch_b200.model import engine_for
     nets, fl, ncls, B, image = CASES[tag]
     L = len(fl[0])
-    ssds = {"fpn50": "SSDFPN", "bifpn": "SSDBiFPN"}.get(tag, "SSD")
-    sd = synth.synthetic_state_dict(nets, fl, [6] * L, ncls, seed=11, style="test", ssds=ssds)
+    ssds = SSDS_OF.get(tag, "SSD")
+    nb = NBOX.get(tag, [6] * L)
+    sd = synth.synthetic_state_dict(nets, fl, nb, ncls, seed=11, style="test", ssds=ssds)
     x = torch.rand((B, 3, image[0], image[1]), generator=torch.Generator().manual_seed(1234))
-    model = engine_for(ssds, nets)(sd, fl, ncls, [6] * L, device="cuda").eval()
+    model = engine_for(ssds, nets)(sd, fl, ncls, nb, device="cuda").eval()
     return sd, fl, x, model, image, ncls
 
 
-@pytest.mark.parametrize("tag", ["r18", "r50", "fpn50", "mbv2", "bifpn"])
+@pytest.mark.parametrize("tag", ["r18", "r50", "fpn50", "mbv2", "bifpn", "yolo", "yolo50x"])
 def test_conv_stack_vs_oracle_bf16_policy(env, tag):
     from oracle import model_oracle as M
     sd, fl, x, model, image, ncls = build(tag, env)
@@ -56,8 +62,8 @@ def test_conv_stack_vs_oracle_bf16_policy(env, tag):
     torch.cuda.synchronize()
     sd_gpu = {k: v.cuda() for k, v in sd.items()}
     with torch.no_grad():
-        fwd = {"fpn50": M.ssdfpn_resnet_forward, "mbv2": M.ssd_mobilenetv2_forward,
-               "bifpn": M.ssdbifpn_forward}.get(tag, M.ssd_resnet_forward)
+        fwd = {"fpn50": M.ssdfpn_resnet_forward, "mbv2": M.ssd_mobilenetv2_forward, "bifpn": M.ssdbifpn_forward,
+               "yolo": M.yolov3_resnet_forward, "yolo50x": M.yolov3_resnet_forward}.get(tag, M.ssd_resnet_forward)
         rloc, rconf = fwd(sd_gpu, x.cuda(), fl, training=False, policy="bf16")
     worst_l = worst_c = 0.0
     for l, c, rl, rc in zip(loc, conf, rloc, rconf):
@@ -148,3 +154,109 @@ def test_pair_launch_plan_is_bit_identical_to_separate_launches(env, tag, monkey
     assert outs[1][0] == outs[0][0] - 15          # 15 of ResNet50's 16 bottlenecks have a successor
     for a, b in zip(outs[0][1] + outs[0][2], outs[1][1] + outs[1][2]):
         assert torch.equal(a, b)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# BASELINE.json configs[1] at its real shape: SSD-ResNet50 512x512, the plan bench.py times
+# ---------------------------------------------------------------------------------------------------------------
+CFG2_FL = [[3, 4, 5, "Conv:S", "Conv:S", "Conv:S"], [512, 1024, 2048, 512, 256, 256]]
+
+
+def _cfg2(B, style="init"):
+    from ssds_pytorch_b200 import synth
+    from ssds_pytorch_b200.model import engine_for
+    sd = synth.synthetic_state_dict("ResNet50", CFG2_FL, [6] * 6, 80, seed=0, style=style)
+    x = torch.randint(0, 256, (B, 512, 512, 3), generator=torch.Generator().manual_seed(1234), dtype=torch.uint8)
+    model = engine_for("SSD", "ResNet50")(sd, CFG2_FL, 80, [6] * 6, device="cuda", mean=0.0, std=255.0).eval()
+    return sd, x, model
+
+
+def test_cfg2_full_shape_plan_vs_oracle_and_vs_1way_unpaired_plan(env, monkeypatch):
+    """The 512x512, B=64 plan (4-way / 2-way / weight-resident conv_igemm instantiations, conv_pair launches,
+    CUDA-graph replay — exactly what bench.py times) against
+      (a) the SAME model planned with SSDSB_WAYS=1 SSDSB_NO_PAIR=1, un-graphed: bit-identical;
+      (b) the model oracle under the bf16 policy (ssd.py:42-74 / resnet.py:41-56 restated with torch fp32
+          ops) on sampled images of the batch (images are independent): the test_conv_stack tolerance."""
+    from oracle import model_oracle as M
+    from ssds_pytorch_b200 import conv as K
+    B = 64
+    sd, x, model = _cfg2(B, style="test")
+    xg = x.cuda()
+    loc, conf = model(xg, use_graph=True)
+    torch.cuda.synchronize()
+    got = [t.clone() for t in loc + conf]
+    plan = model.plan_for(xg)
+    kinds = [v["kind"] for v in plan["info"].values()]
+    assert sum(k.startswith("pair1x1") for k in kinds) >= 6, kinds       # layer1 + layer2 pairs at B=64
+    # which instantiations does this plan launch?  replay it un-graphed, reading the launch record
+    seen = set()
+    for s in plan["steps"]:
+        s()
+        ll = K.last_launch()
+        seen.add((ll["block_n"], ll["block_k"], ll["ways"], ll["b_resident"]))
+    torch.cuda.synchronize()
+    assert any(w == 4 for _, _, w, _ in seen) and any(w == 2 for _, _, w, _ in seen), seen
+    assert any(r == 1 for _, _, _, r in seen), seen
+    for a, b in zip(got, loc + conf):
+        assert torch.equal(a, b), "graph replay differs from eager replay"
+    # (a) 1-way, unpaired plan
+    monkeypatch.setenv("SSDSB_WAYS", "1")
+    monkeypatch.setenv("SSDSB_NO_PAIR", "1")
+    _, _, plain = _cfg2(B, style="test")
+    loc1, conf1 = plain(xg, use_graph=False)
+    torch.cuda.synchronize()
+    assert not any(v["kind"].startswith("pair1x1") for v in plain.plan_for(xg)["info"].values())
+    monkeypatch.delenv("SSDSB_WAYS")
+    monkeypatch.delenv("SSDSB_NO_PAIR")
+    for a, b in zip(got, loc1 + conf1):
+        assert torch.equal(a, b), "multi-way / paired plan differs from the 1-way unpaired plan"
+    del plain, loc1, conf1
+    # (b) oracle on sampled images
+    sd_gpu = {k: v.cuda() for k, v in sd.items()}
+    worst_l = worst_c = 0.0
+    for i in (0, 21, 63):
+        xi = (xg[i:i + 1].float() / 255.0).permute(0, 3, 1, 2).contiguous()
+        with torch.no_grad():
+            rloc, rconf = M.ssd_resnet_forward(sd_gpu, xi, CFG2_FL, training=False, policy="bf16")
+        for l, c, rl, rc in zip(got[:6], got[6:], rloc, rconf):
+            worst_l = max(worst_l, (l[i:i + 1] - rl).abs().max().item() / (1.0 + rl.abs().max().item()))
+            worst_c = max(worst_c, ((c[i:i + 1] - rc).abs() / (5e-4 + 4e-2 * rc)).max().item())
+    print(f"cfg2 512x512 B={B}: max |loc err|/(1+max|loc|) {worst_l:.3e}, max conf err / tol {worst_c:.3f}")
+    assert worst_l <= 2e-2 and worst_c <= 1.0
+
+
+def test_cfg2_bf16_stack_vs_fp32_reference_detections(env):
+    """How far is the bf16 B200 stack from the reference's fp32 arithmetic AT cfg 2 (the number
+    north_star's 1e-4 bar cannot apply to: bf16 storage has 8 mantissa bits)?  fp32 oracle (torch fp32
+    convs + BN, TF32 off = what the reference computes) -> the same Decoder, vs the bf16 engine -> Decoder,
+    on 4 images of 512x512.  Reported (printed) and bounded loosely; profiles/NOTES.md quotes the numbers."""
+    from oracle import model_oracle as M
+    from ssds_pytorch_b200.ssds import SSDDetector
+    import bench
+    B = 4
+    sd, x, _ = _cfg2(B, style="test")
+    det = SSDDetector(bench.cfg_dict(), sd, use_graph=False)
+    s, b, c = [t.cpu().numpy() for t in det.detect_device(x.cuda())]
+    sd_gpu = {k: v.cuda() for k, v in sd.items()}
+    xi = (x.cuda().float() / 255.0).permute(0, 3, 1, 2).contiguous()
+    with torch.no_grad():
+        rloc, rconf = M.ssd_resnet_forward(sd_gpu, xi, CFG2_FL, training=False, policy="fp32")
+    rs, rb, rc = [t.cpu().numpy() for t in det.decoder(rloc, rconf, det.anchors)]
+    torch.cuda.synchronize()
+    found = total = 0
+    dscore, dbox = [], []
+    for i in range(B):
+        for j in range(rs.shape[1]):
+            if rs[i, j] <= 0:
+                continue
+            total += 1
+            m = (c[i] == rc[i, j]) & (np.abs(b[i] - rb[i, j]).max(axis=1) <= 2.0)
+            if m.any():
+                k = int(np.argmax(m))
+                found += 1
+                dscore.append(abs(s[i, k] - rs[i, j]) / rs[i, j])
+                dbox.append(np.abs(b[i, k] - rb[i, j]).max())
+    print(f"cfg2 fp32-reference vs bf16 engine: {found}/{total} detections matched (same class, box within 2 px); "
+          f"median/max rel score diff {np.median(dscore):.3e}/{np.max(dscore):.3e}, "
+          f"median/max box diff {np.median(dbox):.3f}/{np.max(dbox):.3f} px")
+    assert total > 0 and found >= 0.8 * total

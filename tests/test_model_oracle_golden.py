@@ -68,3 +68,36 @@ def test_end_to_end_oracle_detections_r18():
     np.testing.assert_array_equal(c, gold[tag + "_det_classes"])
     np.testing.assert_allclose(s, gold[tag + "_det_scores"], rtol=1e-4, atol=1e-6)
     np.testing.assert_allclose(b, gold[tag + "_det_boxes"], rtol=1e-4, atol=1e-3)
+
+
+YOLO_FL = [[3, 4, 5], [128, 256, 512]]
+YOLO_SIZES = [[2.0, 2.828], [2.0, 2.828], [2.0, 4.0, 8.0]]
+
+
+def test_yolov3_oracle_matches_reference_module():
+    """oracle.yolov3_resnet_forward (yolo.py:44-87 restated) vs the reference's own YOLOV3 module outputs for the
+    model of experiments/cfgs/tests/test.yml (tests/golden/model_yolo.npz, make_golden_model.py --yolo), and the
+    box oracle's Decoder on them vs the reference's detections."""
+    from collections import OrderedDict
+    gold = np.load(os.path.join(os.path.dirname(GOLD), "model_yolo.npz"))
+    sd = synth.synthetic_state_dict("ResNet18", YOLO_FL, [6, 6, 9], 80, seed=11, style="test", ssds="YOLOV3")
+    image = [int(v) for v in gold["yolo_image"]]
+    x = torch.rand((2, 3, image[0], image[1]), generator=torch.Generator().manual_seed(1234))
+    np.testing.assert_array_equal(x.numpy().astype(np.float16), gold["yolo_x"])
+    with torch.no_grad():
+        loc, conf = M.yolov3_resnet_forward(sd, x, YOLO_FL, training=False, policy="fp32")
+    for i, (l, c) in enumerate(zip(loc, conf)):
+        np.testing.assert_allclose(l.numpy(), gold[f"yolo_loc{i}"], rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(c.numpy()[:, ::7], gold[f"yolo_conf{i}"], rtol=1e-4, atol=1e-6)
+    strides = [image[1] // c.shape[-1] for c in conf]
+    np.testing.assert_array_equal(strides, gold["yolo_strides"])
+    anchors = OrderedDict()
+    for i, s in enumerate(strides):
+        a = O.generate_anchors(s, [1, 2, 0.5], YOLO_SIZES[i])
+        np.testing.assert_array_equal(a, gold[f"yolo_anchors{i}"])
+        anchors[s] = a
+    s_, b_, c_ = O.decoder_call([l.numpy() for l in loc], [c.numpy() for c in conf], anchors, 0.01, 0.6, 100, 300,
+                                True, True)
+    np.testing.assert_array_equal(c_, gold["yolo_det_classes"])
+    np.testing.assert_allclose(s_, gold["yolo_det_scores"], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(b_, gold["yolo_det_boxes"], rtol=1e-4, atol=1e-3)

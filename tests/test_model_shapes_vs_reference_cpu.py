@@ -25,6 +25,8 @@ CASES = {
     "SSDBiFPN-ResNet50": ("SSDBiFPN", "ResNet50", FPN),
     "SSDBiFPN-RegNetX032": ("SSDBiFPN", "RegNetX032", [[2, 3, 4, "Conv:S", "Conv:S"], [192, 432, 1008, 1008, 256]]),
     "SSDFPN-RegNetX032": ("SSDFPN", "RegNetX032", [[2, 3, 4, "Conv:S", "Conv:S"], [192, 432, 1008, 1008, 256]]),
+    "YOLOV3-ResNet18": ("YOLOV3", "ResNet18", [[3, 4, 5], [128, 256, 512]]),            # experiments/cfgs/tests/test.yml
+    "YOLOV3-ResNet50+extras": ("YOLOV3", "ResNet50", [[3, 4, 5, "Conv:S"], [512, 1024, 2048, 512]]),
 }
 
 
