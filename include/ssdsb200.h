@@ -108,6 +108,9 @@ SSDSB_API int ssdsb_nms(const float* d_scores /*[B,N]*/, const float* d_boxes /*
                         float* d_out_scores /*[B,D]*/, float* d_out_boxes /*[B,D,4]*/,
                         float* d_out_classes /*[B,D]*/,
                         int32_t* d_out_index /*[B,D] position in the input row, -1 pad; may be NULL*/,
+                        float* d_out_packed /*[B,D,6] (score, x1, y1, x2, y2, class) zero padded, the block
+                                              ssds.py:60-68 returns / the ranks all-gather; may be NULL.  When
+                                              given, the three separate outputs may all be NULL.*/,
                         void* d_workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------

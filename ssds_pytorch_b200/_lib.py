@@ -75,7 +75,7 @@ def _load():
         "ssdsb_decode_workspace_bytes": (sz, [lp, i, i, i]),
         "ssdsb_decode": (i, [lp, i, i, f, i, i, vp, vp, vp, vp, vp, sz, vp]),
         "ssdsb_nms_workspace_bytes": (sz, [i, i, i]),
-        "ssdsb_nms": (i, [vp, vp, vp, i, i, f, i, i, vp, vp, vp, vp, vp, sz, vp]),
+        "ssdsb_nms": (i, [vp, vp, vp, i, i, f, i, i, vp, vp, vp, vp, vp, vp, sz, vp]),
         "ssdsb_match_iou": (i, [vp, i, i, vp, i, i, i, i, i, f, f, f, vp, vp, vp, vp]),
         "ssdsb_multibox_loss_workspace_bytes": (sz, [i, i, i, i, i]),
         "ssdsb_multibox_loss": (i, [vp, vp, vp, i, i, i, i, i, i, vp, vp, sz, vp]),

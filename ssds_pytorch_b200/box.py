@@ -144,22 +144,37 @@ def decode(all_cls_head, all_box_head, stride=1, threshold=0.05, top_n=1000, anc
 
 
 def nms(all_scores, all_boxes, all_classes, nms=0.5, ndetections=100, using_diou=True,
-        return_indices=False):
-    """Non maximum suppression — reference box.py:480-546."""
+        return_indices=False, packed_out=None):
+    """Non maximum suppression — reference box.py:480-546.
+    packed_out: optional [B,D,6] fp32 CUDA tensor that additionally receives (score, x1, y1, x2, y2, class)
+    per detection straight from the kernel (no packing launches); `packed_out=True` allocates it and returns
+    ONLY that tensor."""
     scores = dev_f32(all_scores)
     device = scores.device
     boxes = dev_f32(all_boxes, device)
     classes = dev_f32(all_classes, device)
     B, N = scores.shape
     D = int(ndetections)
-    out_s = torch.empty((B, D), dtype=torch.float32, device=device)
-    out_b = torch.empty((B, D, 4), dtype=torch.float32, device=device)
-    out_c = torch.empty((B, D), dtype=torch.float32, device=device)
+    only_packed = packed_out is True
+    if only_packed:
+        packed_out = torch.empty((B, D, 6), dtype=torch.float32, device=device)
+    if packed_out is not None and (tuple(packed_out.shape) != (B, D, 6) or packed_out.dtype != torch.float32 or
+                                   not packed_out.is_contiguous()):
+        raise ValueError("nms: packed_out must be a contiguous fp32 [B, ndetections, 6] tensor")
+    out_s = out_b = out_c = None
+    if not only_packed:
+        out_s = torch.empty((B, D), dtype=torch.float32, device=device)
+        out_b = torch.empty((B, D, 4), dtype=torch.float32, device=device)
+        out_c = torch.empty((B, D), dtype=torch.float32, device=device)
     out_i = torch.empty((B, D), dtype=torch.int32, device=device) if return_indices else None
     with torch.cuda.device(device):
+        need = lib.ssdsb_nms_workspace_bytes(B, N, D)          # > 0 for long rows (multi-CTA pre-selection)
+        ws = _lib.workspace(need, device) if need else None
         check(lib.ssdsb_nms(ptr(scores), ptr(boxes), ptr(classes), B, N, float(nms), D,
                             int(bool(using_diou)), ptr(out_s), ptr(out_b), ptr(out_c), ptr(out_i),
-                            None, 0, stream_ptr()), "nms")
+                            ptr(packed_out), ptr(ws), ws.numel() if ws is not None else 0, stream_ptr()), "nms")
+    if only_packed:
+        return packed_out
     if return_indices:
         return out_s, out_b, out_c, out_i
     return out_s, out_b, out_c

@@ -16,7 +16,11 @@
 //             anchor, delta2box (box.py:74-87), clamp, centerness rescore (box.py:464-471), and
 //             write straight into the concatenated [B, L*K] outputs (zero padded).
 // Order: descending score, ascending flat index among equal scores (torch.topk leaves it open).
+#include <stdlib.h>
+
 #include "common.cuh"
+#include "decode_emit.cuh"
+#include "decode_large.h"
 
 namespace ssdsb {
 namespace {
@@ -210,11 +214,6 @@ decode_select(const __grid_constant__ DecodeParams p, void* __restrict__ ws) {
   }
 }
 
-__device__ __forceinline__ float clampf_nanprop(float t, float lo, float hi) {
-  // torch.max(m, torch.min(t, M)) — NaN propagates
-  return (t != t) ? t : fmaxf(lo, fminf(t, hi));
-}
-
 __global__ void __launch_bounds__(DEC_NT)
 decode_finalize(const __grid_constant__ DecodeParams p, void* __restrict__ ws,
                 float* __restrict__ out_scores, float* __restrict__ out_boxes,
@@ -258,60 +257,13 @@ decode_finalize(const __grid_constant__ DecodeParams p, void* __restrict__ ws,
   topk_prune<DEC_NT>(buf, &s_cnt, &s_thr, K);                                       // one small sort
   const int nout = min(s_cnt, K);
 
-  const int W = lv.W, H = lv.H, C = lv.C;
-  const int HW = H * W;
-  const float stride_f = (float)lv.stride;
-  const float Mx = (float)W * stride_f - 1.0f;  // box.py:83  size=[W,H] * stride - 1
-  const float My = (float)H * stride_f - 1.0f;
-  const float* loc = lv.loc + (size_t)b * lv.A * 4 * HW;
   const size_t row = (size_t)b * L * p.K_total + (size_t)l * p.K_total + p.out_off;
   if (tid == 0)   // bound for the next round: the smallest key emitted now, or "exhausted"
     ws_upper(ws, p.B, L)[(size_t)b * L + l] = (nout == K) ? buf[K - 1] : 0ull;
 
-  for (int t = tid; t < K; t += DEC_NT) {
-    float score = 0.f, cls = 0.f, x1 = 0.f, y1 = 0.f, x2 = 0.f, y2 = 0.f;
-    int32_t flat = -1;
-    if (t < nout) {
-      const unsigned long long key = buf[t];
-      score = key_score(key);
-      const uint32_t idx = key_index(key);
-      flat = (int32_t)idx;
-      const int x = idx % W;                       // box.py:452-454
-      const int y = (idx / W) % H;
-      const int c = (idx / W / H) % C;             // box.py:448
-      const int a = idx / C / H / W;
-      cls = (float)c;
-      const float d0 = __ldg(loc + (size_t)(a * 4 + 0) * HW + y * W + x);
-      const float d1 = __ldg(loc + (size_t)(a * 4 + 1) * HW + y * W + x);
-      const float d2 = __ldg(loc + (size_t)(a * 4 + 2) * HW + y * W + x);
-      const float d3 = __ldg(loc + (size_t)(a * 4 + 3) * HW + y * W + x);
-      const float4 an = __ldg(reinterpret_cast<const float4*>(lv.anchors) + a);
-      // grid anchor: (x,y,x,y)*stride + anchors[a]   box.py:459-462
-      const float gx1 = (float)x * stride_f + an.x, gy1 = (float)y * stride_f + an.y;
-      const float gx2 = (float)x * stride_f + an.z, gy2 = (float)y * stride_f + an.w;
-      // delta2box  box.py:74-87
-      const float aw = gx2 - gx1 + 1.0f, ah = gy2 - gy1 + 1.0f;
-      const float cx = gx1 + 0.5f * aw, cy = gy1 + 0.5f * ah;
-      const float pcx = d0 * aw + cx, pcy = d1 * ah + cy;
-      const float pw = (float)exp((double)d2) * aw, ph = (float)exp((double)d3) * ah;
-      x1 = clampf_nanprop(pcx - 0.5f * pw, 0.0f, Mx);
-      y1 = clampf_nanprop(pcy - 0.5f * ph, 0.0f, My);
-      x2 = clampf_nanprop(pcx + 0.5f * pw - 1.0f, 0.0f, Mx);
-      y2 = clampf_nanprop(pcy + 0.5f * ph - 1.0f, 0.0f, My);
-      if (p.rescore) {  // box.py:464-471
-        const float gcx = (gx1 + gx2) / 2.0f, gcy = (gy1 + gy2) / 2.0f;
-        const float ltx = fabsf(gcx - x1), lty = fabsf(gcy - y1);
-        const float rbx = fabsf(x2 - gcx), rby = fabsf(y2 - gcy);
-        const float qx = fminf(ltx, rbx) / fmaxf(ltx, rbx);
-        const float qy = fminf(lty, rby) / fmaxf(lty, rby);
-        score = score * sqrtf(qx * qy);
-      }
-    }
-    out_scores[row + t] = score;
-    out_classes[row + t] = cls;
-    reinterpret_cast<float4*>(out_boxes)[row + t] = make_float4(x1, y1, x2, y2);
-    if (out_index) out_index[row + t] = flat;
-  }
+  for (int t = tid; t < K; t += DEC_NT)
+    emit_detection(lv, b, t < nout, t < nout ? buf[t] : 0ull, p.rescore, row + t, out_scores, out_boxes,
+                   out_classes, out_index);
 }
 
 int fill_params(DecodeParams& p, const ssdsb_level* levels, int n_levels, int B, int top_n_total) {
@@ -367,6 +319,7 @@ static int validate_levels(const ssdsb_level* levels, int n_levels, int B, int t
 extern "C" size_t ssdsb_decode_workspace_bytes(const ssdsb_level* levels, int n_levels, int B,
                                                int top_n) {
   if (validate_levels(levels, n_levels, B, top_n, false) != SSDSB_OK) return 0;
+  if (top_n > DEC_MAX_K && top_n <= decode_large_max_k()) return decode_large_workspace_bytes(n_levels, B, top_n);
   DecodeParams p;
   fill_params(p, levels, n_levels, B, top_n);
   return ws_head_bytes(B, n_levels) + (size_t)B * n_levels * 8 + (size_t)B * p.cand_off[n_levels] * 8 + 16;
@@ -385,11 +338,16 @@ extern "C" int ssdsb_decode(const ssdsb_level* levels, int n_levels, int B, floa
   if (!d_workspace || workspace_bytes < need || ((uintptr_t)d_workspace & 15) != 0)
     return fail(SSDSB_ERR_WORKSPACE, "decode: workspace %zu B given, %zu B (16-byte aligned) needed",
                 workspace_bytes, need);
+  cudaStream_t st = (cudaStream_t)stream;
+  // 1024 < top_n <= 24576: three streaming passes + one shared-memory sort per (image, level) (decode_large.cu)
+  // instead of one pass over the score maps per 1024 results.  SSDSB_DECODE_ROUNDS=1 keeps the rounds (A/B runs).
+  if (top_n > DEC_MAX_K && top_n <= decode_large_max_k() && !getenv("SSDSB_DECODE_ROUNDS"))
+    return decode_large(levels, n_levels, B, threshold, top_n, rescore, d_scores, d_boxes, d_classes, d_index,
+                        d_workspace, workspace_bytes, st);
   DecodeParams p;
   fill_params(p, levels, n_levels, B, top_n);
   p.threshold = threshold;
   p.rescore = rescore;
-  cudaStream_t st = (cudaStream_t)stream;
   const size_t head = ws_head_bytes(B, n_levels);
   // upper bounds start at "none"
   SSDSB_CUDA(cudaMemsetAsync(reinterpret_cast<unsigned char*>(d_workspace) + head, 0xff,

@@ -6,6 +6,8 @@
 //   maxpool3x3s2     resnet.py:45 nn.MaxPool2d(3, 2, 1) on NHWC bf16, 8 channels per thread.
 #include <cuda_bf16.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace ssdsb {
@@ -49,6 +51,45 @@ pack_image_s2d_kernel(const void* __restrict__ src, int N, int H, int W, float m
     const size_t o = ((size_t)n * Ho + ii) * row_px + left_pad + j;   // pixel index in the padded rows
     out[o * 2 + 0] = lo;
     out[o * 2 + 1] = hi;
+  }
+}
+
+// uint8 NHWC fast path (W % 4 == 0): a thread packs TWO horizontally adjacent s2d pixels = 2 rows x 4 source pixels
+// x 3 bytes = 2 x 12 contiguous, 4-byte aligned bytes -> 6 32-bit loads instead of 24 byte loads, 4 16-byte stores.
+__global__ void __launch_bounds__(256)
+pack_image_s2d_u8x2_kernel(const uint32_t* __restrict__ src, int N, int H, int W, float mean, float stdv,
+                           int row_px, int left_pad, uint4* __restrict__ out) {
+  const int Ho = H >> 1, Wo2 = W >> 2;
+  const size_t total = (size_t)N * Ho * Wo2;
+  const int row_words = (W * 3) >> 2;                  // 32-bit words per source row (W % 4 == 0)
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const int j2 = (int)(i % Wo2);
+    const int ii = (int)((i / Wo2) % Ho);
+    const int n = (int)(i / ((size_t)Wo2 * Ho));
+    float v[2][12];                                     // [s2d pixel][(a*2+b)*3+c]
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const uint32_t* row = src + ((size_t)n * H + 2 * ii + a) * row_words + (size_t)j2 * 3;
+      const uint32_t w0 = __ldg(row), w1 = __ldg(row + 1), w2 = __ldg(row + 2);
+      const uint32_t words[3] = {w0, w1, w2};
+#pragma unroll
+      for (int k = 0; k < 12; ++k) {                    // byte k of the 12: source pixel k/3, channel k%3
+        const float f = (float)((words[k >> 2] >> ((k & 3) * 8)) & 0xffu);
+        const int px = k / 3, c = k % 3;                // px 0,1 -> first s2d pixel (b = px), px 2,3 -> second
+        v[px >> 1][(a * 2 + (px & 1)) * 3 + c] = (f - mean) / stdv;     // ssds.py:57
+      }
+    }
+    const size_t o = ((size_t)n * Ho + ii) * row_px + left_pad + 2 * j2;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      uint4 lo, hi;
+      lo.x = pack2(v[q][0], v[q][1]); lo.y = pack2(v[q][2], v[q][3]); lo.z = pack2(v[q][4], v[q][5]);
+      lo.w = pack2(v[q][6], v[q][7]);
+      hi.x = pack2(v[q][8], v[q][9]); hi.y = pack2(v[q][10], v[q][11]); hi.z = 0u; hi.w = 0u;
+      out[(o + q) * 2 + 0] = lo;
+      out[(o + q) * 2 + 1] = hi;
+    }
   }
 }
 
@@ -264,6 +305,115 @@ dwconv3x3_kernel(const uint4* __restrict__ x, const uint4* __restrict__ w, const
   }
 }
 
+
+// Depthwise 3x3, row-streaming variant (the one ssdsb_dwconv3x3_nhwc_bf16 launches): a thread owns 4 channels of
+// one output column and walks DOWN a chunk of output rows.  Every input row it needs is loaded once (3 x 8-byte
+// loads: left / centre / right column; neighbours' loads hit L1) and feeds the three output rows it touches from
+// registers (stride 1: a 3-deep accumulator ring; stride 2: the odd row is reused as the next output's top row),
+// the 9 x 4 folded weights live in registers for the whole chunk.  3 loads per output row instead of 9 + 9, and the
+// unrolled row loop keeps >= 6 independent loads in flight per thread — the per-output variant above was bound by
+// load latency at ~1.2 TB/s.  fp32 accumulation in the same tap order (dy-major, dx-minor) for dy = 0..2 per output.
+__device__ __forceinline__ void bf4_to_f(const uint2 v, float (&f)[4]) {
+  f[0] = __uint_as_float(v.x << 16);
+  f[1] = __uint_as_float(v.x & 0xffff0000u);
+  f[2] = __uint_as_float(v.y << 16);
+  f[3] = __uint_as_float(v.y & 0xffff0000u);
+}
+
+template <int S>
+__global__ void __launch_bounds__(256, S == 1 ? 2 : 3)
+dwconv3x3_rows_kernel(const uint2* __restrict__ x, const uint2* __restrict__ w, const float* __restrict__ bias,
+                      int N, int H, int W, int C4, int Ho, int Wo, int relu, int rows_per, int chunks,
+                      uint2* __restrict__ y) {
+  const size_t total = (size_t)N * chunks * Wo * C4;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = (int)(idx % C4);
+  const int wo = (int)((idx / C4) % Wo);
+  const int ch = (int)((idx / ((size_t)C4 * Wo)) % chunks);
+  const int n = (int)(idx / ((size_t)C4 * Wo * chunks));
+  const int ho0 = ch * rows_per;
+  const int ho1 = min(Ho, ho0 + rows_per);
+  float wf[9][4], b[4];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) bf4_to_f(__ldg(w + (size_t)k * C4 + c), wf[k]);
+  {
+    const float4 bv = __ldg(reinterpret_cast<const float4*>(bias) + c);
+    b[0] = bv.x; b[1] = bv.y; b[2] = bv.z; b[3] = bv.w;
+  }
+  const int w0 = wo * S - 1;                       // leftmost input column of this output column
+  const bool has_l = w0 >= 0, has_r = w0 + 2 < W;  // the centre column wo*S is always inside
+  const uint2* xin = x + (size_t)n * H * W * C4 + c;
+  auto load_row = [&](int h, float (&f)[3][4]) {
+    uint2 r0 = make_uint2(0u, 0u), r1 = r0, r2 = r0;
+    if (h >= 0 && h < H) {
+      const uint2* row = xin + ((size_t)h * W + w0) * C4;
+      if (has_l) r0 = __ldg(row);
+      r1 = __ldg(row + C4);
+      if (has_r) r2 = __ldg(row + 2 * C4);
+    }
+    bf4_to_f(r0, f[0]); bf4_to_f(r1, f[1]); bf4_to_f(r2, f[2]);
+  };
+  auto fma_row = [&](float (&a)[4], const float (&f)[3][4], int dy) {
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) a[e] = fmaf(f[dx][e], wf[dy * 3 + dx][e], a[e]);
+  };
+  auto emit = [&](int ho, float (&a)[4]) {
+    float o[4] = {a[0], a[1], a[2], a[3]};
+    if (relu) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[e] = fmaxf(o[e], 0.0f);
+      if (relu == 2) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) o[e] = fminf(o[e], 6.0f);
+      }
+    }
+    y[(((size_t)n * Ho + ho) * Wo + wo) * C4 + c] = make_uint2(pack2(o[0], o[1]), pack2(o[2], o[3]));
+  };
+  if (S == 1) {
+    // input row h feeds output rows h+1 (dy 0), h (dy 1), h-1 (dy 2): ring E (row h-1), M (row h), Nn (row h+1)
+    float E[4] = {b[0], b[1], b[2], b[3]}, M[4] = {b[0], b[1], b[2], b[3]}, Nn[4];
+#pragma unroll 3
+    for (int h = ho0 - 1; h <= ho1; ++h) {
+      float f[3][4];
+      load_row(h, f);
+      fma_row(E, f, 2);
+      if (h - 1 >= ho0) emit(h - 1, E);            // (h - 1 < ho1 always: h <= ho1)
+      fma_row(M, f, 1);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) Nn[e] = b[e];
+      fma_row(Nn, f, 0);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        E[e] = M[e];
+        M[e] = Nn[e];
+      }
+    }
+  } else {
+    // output row ho = rows 2ho-1 (dy 0), 2ho (dy 1), 2ho+1 (dy 2); row 2ho+1 is also the top row of output ho+1
+    float a[4] = {b[0], b[1], b[2], b[3]};
+    {
+      float f[3][4];
+      load_row(2 * ho0 - 1, f);
+      fma_row(a, f, 0);
+    }
+#pragma unroll 2
+    for (int ho = ho0; ho < ho1; ++ho) {
+      float f1[3][4], f2[3][4];
+      load_row(2 * ho, f1);
+      load_row(2 * ho + 1, f2);
+      fma_row(a, f1, 1);
+      fma_row(a, f2, 2);
+      emit(ho, a);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) a[e] = b[e];
+      fma_row(a, f2, 0);
+    }
+  }
+}
+
 }  // namespace
 }  // namespace ssdsb
 
@@ -300,12 +450,32 @@ extern "C" int ssdsb_dwconv3x3_nhwc_bf16(const void* d_x, const void* d_w, const
   SSDSB_REQUIRE((((uintptr_t)d_x | (uintptr_t)d_w | (uintptr_t)d_y | (uintptr_t)d_bias) & 15) == 0,
                 "dwconv3x3: pointers must be 16-byte aligned");
   const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
-  const size_t total = (size_t)N * Ho * Wo * (C / 8);
-  int blocks = (int)((total + 255) / 256);
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  dwconv3x3_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const uint4*>(d_x), reinterpret_cast<const uint4*>(d_w), d_bias, N, H, W, C / 8,
-      stride, Ho, Wo, relu, reinterpret_cast<uint4*>(d_y));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (getenv("SSDSB_DW_SIMPLE")) {                 // the per-output variant (A/B runs, parity reference)
+    const size_t total = (size_t)N * Ho * Wo * (C / 8);
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    dwconv3x3_kernel<<<blocks, 256, 0, st>>>(
+        reinterpret_cast<const uint4*>(d_x), reinterpret_cast<const uint4*>(d_w), d_bias, N, H, W, C / 8,
+        stride, Ho, Wo, relu, reinterpret_cast<uint4*>(d_y));
+  } else {
+    // rows per thread: as long as possible (2 halo rows are re-read per chunk) while >= ~2 waves of threads remain
+    const size_t items = (size_t)N * Ho * Wo * (C / 4);
+    int rows_per = 16;
+    while (rows_per > 2 && items / rows_per < (size_t)148 * 2048 * 2) rows_per >>= 1;
+    if (rows_per > Ho) rows_per = Ho;
+    const int chunks = (Ho + rows_per - 1) / rows_per;
+    const size_t total = (size_t)N * chunks * Wo * (C / 4);
+    const unsigned blocks = (unsigned)((total + 255) / 256);
+    if (stride == 1)
+      dwconv3x3_rows_kernel<1><<<blocks, 256, 0, st>>>(reinterpret_cast<const uint2*>(d_x),
+          reinterpret_cast<const uint2*>(d_w), d_bias, N, H, W, C / 4, Ho, Wo, relu, rows_per, chunks,
+          reinterpret_cast<uint2*>(d_y));
+    else
+      dwconv3x3_rows_kernel<2><<<blocks, 256, 0, st>>>(reinterpret_cast<const uint2*>(d_x),
+          reinterpret_cast<const uint2*>(d_w), d_bias, N, H, W, C / 4, Ho, Wo, relu, rows_per, chunks,
+          reinterpret_cast<uint2*>(d_y));
+  }
   SSDSB_LAUNCH_CHECK("dwconv3x3_kernel");
   return SSDSB_OK;
 }
@@ -365,7 +535,13 @@ extern "C" int ssdsb_pack_image_s2d(const void* d_src, int src_format, int N, in
   if (src_format == 0)
     pack_image_s2d_kernel<0><<<blocks, 256, 0, st>>>(d_src, N, H, W, mean, stdv, out_row_pixels,
                                                      left_pad, reinterpret_cast<uint4*>(d_out));
-  else
+  else if ((W % 4) == 0 && ((uintptr_t)d_src & 3) == 0) {
+    const size_t total2 = (size_t)N * (H / 2) * (W / 4);
+    int blocks2 = (int)((total2 + 255) / 256);
+    if (blocks2 > 148 * 16) blocks2 = 148 * 16;
+    pack_image_s2d_u8x2_kernel<<<blocks2, 256, 0, st>>>(reinterpret_cast<const uint32_t*>(d_src), N, H, W, mean, stdv,
+                                                        out_row_pixels, left_pad, reinterpret_cast<uint4*>(d_out));
+  } else
     pack_image_s2d_kernel<1><<<blocks, 256, 0, st>>>(d_src, N, H, W, mean, stdv, out_row_pixels,
                                                      left_pad, reinterpret_cast<uint4*>(d_out));
   SSDSB_LAUNCH_CHECK("pack_image_s2d_kernel");

@@ -181,26 +181,32 @@ loss_step_kernel(const __grid_constant__ LsParams p) {
     const int cpos = is_pos ? (int)depth - 1 : -1;
     if (p.cls_kind == 0) {
       float mx = 0.0f, sum = 0.0f;      // softplus > 0, so 0 is a valid identity for the max
-      int c = 0;
-      for (; c + 8 <= C; c += 8) {
-        float v[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = __ldcs(lg + (size_t)(c + k) * HW);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          float ce = softplus_fast(v[k]);
-          if (c + k == cpos) ce -= v[k];                // BCE(x, t=1) = softplus(x) - x
-          mx = fmaxf(mx, ce);
-          sum += ce;
-        }
-      }
-      for (; c < C; ++c) {
-        const float v = __ldcs(lg + (size_t)c * HW);
-        float ce = softplus_fast(v);
-        if (c == cpos) ce -= v;
+      auto take = [&](float x, int cc) {
+        float ce = softplus_fast(x);
+        if (cc == cpos) ce -= x;                          // BCE(x, t=1) = softplus(x) - x
         mx = fmaxf(mx, ce);
         sum += ce;
+      };
+      // software pipeline: the 8 plane loads of the NEXT group are issued before the current group is reduced, so
+      // 16 independent loads per thread are in flight (the pass is bound by load latency x occupancy otherwise)
+      int c = 0;
+      float v[8], nx[8];
+      const int groups = C >> 3;
+      if (groups > 0) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = __ldcs(lg + (size_t)k * HW);
       }
+      for (int gq = 0; gq < groups; ++gq, c += 8) {
+        if (gq + 1 < groups) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) nx[k] = __ldcs(lg + (size_t)(c + 8 + k) * HW);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) take(v[k], c + k);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = nx[k];
+      }
+      for (; c < C; ++c) take(__ldcs(lg + (size_t)c * HW), c);
       if (is_pos) {                                     // always kept; max_ce := 0 (criterion.py:59)
         cls_v = (double)sum;
         p.mce[lv.off + (size_t)b * N + i] = float_to_ordered(0.0f);
@@ -265,9 +271,18 @@ loss_step_kernel(const __grid_constant__ LsParams p) {
         __syncthreads();
         const uint32_t prefix = s_prefix;
         const int shift = shifts[pass];
-        for (int j = tid; j < N; j += LS_NT) {
-          const uint32_t v = __ldcg(u + j);
-          if ((v & mask) == prefix) atomicAdd(&s_hist[(v >> shift) & (uint32_t)(nb - 1)], 1);
+        // warp-aggregated histogram: max-CE values of one image cluster in a handful of bins (same exponent,
+        // same top mantissa bits), which would serialise plain shared-memory atomics
+        const int n_up = (N + LS_NT - 1) / LS_NT * LS_NT;            // warp-uniform trip count
+        for (int j = tid; j < n_up; j += LS_NT) {
+          const uint32_t v = (j < N) ? __ldcg(u + j) : 0u;
+          const bool in = (j < N) && ((v & mask) == prefix);
+          const unsigned act = __ballot_sync(0xffffffffu, in);
+          if (in) {
+            const int bin = (int)((v >> shift) & (uint32_t)(nb - 1));
+            const unsigned peers = __match_any_sync(act, bin);
+            if ((int)(__ffs(peers) - 1) == (tid & 31)) atomicAdd(&s_hist[bin], __popc(peers));
+          }
         }
         __syncthreads();
         if (tid < 32) {

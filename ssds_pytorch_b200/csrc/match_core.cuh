@@ -22,18 +22,24 @@ struct Tgt {
 __device__ __forceinline__ void stage_targets_warp(const float* __restrict__ tg, int T, int t0, float r,
                                                    Tgt* s_t, int* s_n, int lane) {
   int n = 0;
-  for (int tt = lane; tt < MATCH_TCHUNK; tt += 32) {
-    const int t = t0 + tt;
-    const bool valid = (t < T) && (tg[t * 5 + 4] > -1.0f);
+  const int t_end = min(T, t0 + MATCH_TCHUNK);
+  for (int tb = t0; tb < t_end; tb += 32) {            // warp-uniform trip count; usually ONE trip (T <= 32)
+    const int t = tb + lane;
+    // all five fields are fetched before the ballot: one memory latency per trip instead of two dependent ones
+    float tx = 0.f, ty = 0.f, tw = 0.f, th = 0.f, tc = -1.0f;
+    if (t < t_end) {
+      tx = __ldg(tg + t * 5 + 0); ty = __ldg(tg + t * 5 + 1); tw = __ldg(tg + t * 5 + 2);
+      th = __ldg(tg + t * 5 + 3); tc = __ldg(tg + t * 5 + 4);
+    }
+    const bool valid = (t < t_end) && (tc > -1.0f);
     const unsigned m = __ballot_sync(0xffffffffu, valid);
     if (valid) {
       const int slot = n + __popc(m & ((1u << lane) - 1u));
-      const float tx = tg[t * 5 + 0], ty = tg[t * 5 + 1], tw = tg[t * 5 + 2], th = tg[t * 5 + 3];
       Tgt g;
       g.x1 = tx; g.y1 = ty;
       g.x2 = tx + tw - 1.0f; g.y2 = ty + th - 1.0f;                       // box.py:162
       g.area = (g.x2 - g.x1 + 1.0f) * (g.y2 - g.y1 + 1.0f);              // box.py:166
-      g.cls = tg[t * 5 + 4];
+      g.cls = tc;
       const float cx = (g.x1 + g.x2) / 2.0f, cy = (g.y1 + g.y2) / 2.0f;  // box.py:98
       g.sx1 = fmaxf(cx - r, g.x1); g.sy1 = fmaxf(cy - r, g.y1);          // box.py:105
       g.sx2 = fminf(cx + r, g.x2); g.sy2 = fminf(cy + r, g.y2);          // box.py:108

@@ -18,7 +18,11 @@
 // The loop stops as soon as `ndetections` pivots exist, so the common case touches one chunk.
 // If a round's SEL candidates are exhausted before D pivots are found, another selection round
 // runs over keys below the last one processed (rare; bounded by N/SEL rounds).
+#include <float.h>
+#include <stdlib.h>
+
 #include "common.cuh"
+#include "decode_large.h"
 
 namespace ssdsb {
 namespace {
@@ -30,6 +34,7 @@ constexpr int NMS_SEL = 2048;  // candidates sorted per round
 constexpr int NMS_CAP = 4096;  // shared key buffer (>= SEL + TILE)
 constexpr int NMS_CH = 128;    // chunk width of the suppression matrix
 constexpr int NMS_CW = NMS_CH / 32;
+constexpr int NMS_PRESEL_MIN = 8192;   // rows longer than this get their first SEL candidates from topk_rows
 
 struct Cand {
   float x1, y1, x2, y2;
@@ -64,7 +69,8 @@ __global__ void __launch_bounds__(NMS_NT, 1)
 nms_kernel(const float* __restrict__ scores, const float* __restrict__ boxes,
            const float* __restrict__ classes, int N, float thr, int D, int diou,
            float* __restrict__ out_scores, float* __restrict__ out_boxes,
-           float* __restrict__ out_classes, int32_t* __restrict__ out_index) {
+           float* __restrict__ out_classes, int32_t* __restrict__ out_index, float* __restrict__ out_packed,
+           const unsigned long long* __restrict__ presel_keys, const int* __restrict__ presel_count) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);  // [NMS_CAP]
   unsigned long long* keys2 = keys + NMS_CAP;                                   // [NMS_SEL] prune scratch
@@ -92,34 +98,45 @@ nms_kernel(const float* __restrict__ scores, const float* __restrict__ boxes,
   unsigned long long upper = ~0ull;  // process keys strictly below this
   bool exhausted = false;
 
+  bool first = true;
   while (nkept < D && !exhausted) {
-    // ---------------- selection round: top-SEL keys below `upper` ----------------
-    if (tid == 0) {
-      s_cnt = 0;
-      s_thr = 0ull;
-    }
-    __syncthreads();
-    bool pruned = false;
-    for (int base = 0; base < N; base += NMS_TILE) {
-      unsigned long long k[NMS_EPT];
-      bool take[NMS_EPT];
-      const unsigned long long cur = s_thr;
+    int count;
+    if (first && presel_keys) {
+      // ---------------- round 0 of a long row: the sorted top-SEL keys were selected by topk_rows ----------------
+      count = presel_count[b];
+      for (int i = tid; i < count; i += NMS_NT) keys[i] = presel_keys[(size_t)b * NMS_SEL + i];
+      if (count < NMS_SEL) exhausted = true;          // every candidate with score > 0 is in the list
+      __syncthreads();
+    } else {
+      // ---------------- selection round: top-SEL keys below `upper` ----------------
+      if (tid == 0) {
+        s_cnt = 0;
+        s_thr = 0ull;
+      }
+      __syncthreads();
+      bool pruned = false;
+      for (int base = 0; base < N; base += NMS_TILE) {
+        unsigned long long k[NMS_EPT];
+        bool take[NMS_EPT];
+        const unsigned long long cur = s_thr;
 #pragma unroll
-      for (int e = 0; e < NMS_EPT; ++e) {
-        int i = base + e * NMS_NT + tid;
-        float s = (i < N) ? __ldg(sc + i) : 0.0f;
-        k[e] = make_key(s, (uint32_t)i);
-        take[e] = (s > 0.0f) && (k[e] < upper) && (k[e] > cur);
+        for (int e = 0; e < NMS_EPT; ++e) {
+          int i = base + e * NMS_NT + tid;
+          float s = (i < N) ? __ldg(sc + i) : 0.0f;
+          k[e] = make_key(s, (uint32_t)i);
+          take[e] = (s > 0.0f) && (k[e] < upper) && (k[e] > cur);
+        }
+        const int fill = topk_append<NMS_EPT>(keys, &s_cnt, k, take);
+        if (__syncthreads_or(fill > NMS_CAP - NMS_TILE)) {  // block-uniform, race-free
+          topk_prune_select<NMS_NT>(keys, keys2, &s_cnt, &s_thr, NMS_SEL, s_scratch, &s_kth);
+          pruned = true;
+        }
       }
-      const int fill = topk_append<NMS_EPT>(keys, &s_cnt, k, take);
-      if (__syncthreads_or(fill > NMS_CAP - NMS_TILE)) {  // block-uniform, race-free
-        topk_prune_select<NMS_NT>(keys, keys2, &s_cnt, &s_thr, NMS_SEL, s_scratch, &s_kth);
-        pruned = true;
-      }
+      topk_prune<NMS_NT>(keys, &s_cnt, &s_thr, NMS_SEL);
+      count = s_cnt;  // sorted, descending, in keys[0..count)
+      if (!pruned && count <= NMS_SEL) exhausted = true;  // nothing was ever discarded
     }
-    topk_prune<NMS_NT>(keys, &s_cnt, &s_thr, NMS_SEL);
-    const int count = s_cnt;  // sorted, descending, in keys[0..count)
-    if (!pruned && count <= NMS_SEL) exhausted = true;  // nothing was ever discarded
+    first = false;
     if (count == 0) break;
 
     // ---------------- consume in chunks of CH ----------------
@@ -210,10 +227,18 @@ nms_kernel(const float* __restrict__ scores, const float* __restrict__ boxes,
         kcls[o] = ccls[j];
         karea[o] = carea[j];
         const size_t ob = (size_t)b * D + o;
-        out_scores[ob] = cscore[j];
-        reinterpret_cast<Cand*>(out_boxes)[ob] = cbox[j];
-        out_classes[ob] = ccls[j];
+        if (out_scores) {
+          out_scores[ob] = cscore[j];
+          reinterpret_cast<Cand*>(out_boxes)[ob] = cbox[j];
+          out_classes[ob] = ccls[j];
+        }
         if (out_index) out_index[ob] = (int32_t)cidx[j];
+        if (out_packed) {      // [B,D,6] = (score, x1, y1, x2, y2, class): the block SSDDetector ships / all-gathers
+          float* pk = out_packed + ob * 6;
+          pk[0] = cscore[j];
+          pk[1] = cbox[j].x1; pk[2] = cbox[j].y1; pk[3] = cbox[j].x2; pk[4] = cbox[j].y2;
+          pk[5] = ccls[j];
+        }
       }
       nkept += nk;
       pos += m;
@@ -222,14 +247,22 @@ nms_kernel(const float* __restrict__ scores, const float* __restrict__ boxes,
     upper = keys[count - 1];
     __syncthreads();
   }
+  (void)s_kth;
 
   // zero padding of the tail (reference rows start as torch.zeros)
   for (int o = nkept + tid; o < D; o += NMS_NT) {
     const size_t ob = (size_t)b * D + o;
-    out_scores[ob] = 0.0f;
-    reinterpret_cast<Cand*>(out_boxes)[ob] = Cand{0.f, 0.f, 0.f, 0.f};
-    out_classes[ob] = 0.0f;
+    if (out_scores) {
+      out_scores[ob] = 0.0f;
+      reinterpret_cast<Cand*>(out_boxes)[ob] = Cand{0.f, 0.f, 0.f, 0.f};
+      out_classes[ob] = 0.0f;
+    }
     if (out_index) out_index[ob] = -1;
+    if (out_packed) {
+      float* pk = out_packed + ob * 6;
+#pragma unroll
+      for (int e = 0; e < 6; ++e) pk[e] = 0.0f;
+    }
   }
 }
 
@@ -238,32 +271,55 @@ nms_kernel(const float* __restrict__ scores, const float* __restrict__ boxes,
 
 using namespace ssdsb;
 
+static size_t nms_presel_bytes(int B) {
+  return align_up((size_t)B * NMS_SEL * 8, 256) + align_up((size_t)B * 4, 256);
+}
+
 extern "C" size_t ssdsb_nms_workspace_bytes(int B, int N, int ndetections) {
-  (void)B; (void)N; (void)ndetections;
-  return 0;  // everything lives in shared memory
+  (void)ndetections;
+  if (B < 1 || N <= NMS_PRESEL_MIN) return 0;  // short rows: everything lives in shared memory
+  // long rows: the first NMS_SEL candidates of every row come from a multi-CTA exact selection (decode_large.cu)
+  return nms_presel_bytes(B) + topk_rows_workspace_bytes(B, NMS_SEL) + 256;
 }
 
 extern "C" int ssdsb_nms(const float* d_scores, const float* d_boxes, const float* d_classes,
                          int B, int N, float nms_threshold, int ndetections, int using_diou,
                          float* d_out_scores, float* d_out_boxes, float* d_out_classes,
-                         int32_t* d_out_index, void* d_workspace, size_t workspace_bytes,
+                         int32_t* d_out_index, float* d_out_packed, void* d_workspace, size_t workspace_bytes,
                          void* stream) {
-  (void)d_workspace; (void)workspace_bytes;
   SSDSB_REQUIRE(B >= 0 && N >= 0, "nms: negative size (B=%d, N=%d)", B, N);
   SSDSB_REQUIRE(ndetections >= 1 && ndetections <= 4096, "nms: ndetections=%d outside [1,4096]",
                 ndetections);
   if (B == 0) return SSDSB_OK;
-  SSDSB_REQUIRE(d_out_scores && d_out_boxes && d_out_classes, "nms: NULL output");
+  SSDSB_REQUIRE((d_out_scores && d_out_boxes && d_out_classes) || (d_out_packed && !d_out_scores && !d_out_boxes &&
+                                                                     !d_out_classes),
+                "nms: give the three separate outputs, the packed output, or both");
   SSDSB_REQUIRE(N == 0 || (d_scores && d_boxes && d_classes), "nms: NULL input");
-  SSDSB_REQUIRE(((uintptr_t)d_boxes & 15) == 0 && ((uintptr_t)d_out_boxes & 15) == 0,
+  SSDSB_REQUIRE(((uintptr_t)d_boxes & 15) == 0 && (!d_out_boxes || ((uintptr_t)d_out_boxes & 15) == 0),
                 "nms: boxes must be 16-byte aligned");
   const size_t smem = sizeof(unsigned long long) * (NMS_CAP + NMS_SEL) + (size_t)ndetections * (16 + 4 + 4);
   static_assert(NMS_CAP >= NMS_SEL + NMS_TILE, "buffer too small");
   SSDSB_CUDA(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
-  nms_kernel<<<B, NMS_NT, smem, (cudaStream_t)stream>>>(
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned long long* presel_keys = nullptr;
+  const int* presel_count = nullptr;
+  const size_t need = ssdsb_nms_workspace_bytes(B, N, ndetections);
+  if (need > 0 && d_workspace && workspace_bytes >= need && !getenv("SSDSB_NMS_NO_PRESEL")) {
+    // (callers that pass no workspace keep the single-CTA streaming selection: same results, slower on long rows)
+    unsigned char* ws = reinterpret_cast<unsigned char*>(((uintptr_t)d_workspace + 255) & ~(uintptr_t)255);
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(ws);
+    int* count = reinterpret_cast<int*>(ws + align_up((size_t)B * NMS_SEL * 8, 256));
+    unsigned char* rest = ws + nms_presel_bytes(B);
+    int rc = topk_rows(d_scores, B, N, FLT_TRUE_MIN, NMS_SEL, keys, count, rest,
+                       workspace_bytes - (size_t)(rest - reinterpret_cast<unsigned char*>(d_workspace)), st);
+    if (rc != SSDSB_OK) return rc;
+    presel_keys = keys;
+    presel_count = count;
+  }
+  nms_kernel<<<B, NMS_NT, smem, st>>>(
       d_scores, d_boxes, d_classes, N, nms_threshold, ndetections, using_diou, d_out_scores,
-      d_out_boxes, d_out_classes, d_out_index);
+      d_out_boxes, d_out_classes, d_out_index, d_out_packed, presel_keys, presel_count);
   SSDSB_LAUNCH_CHECK("nms_kernel");
   return SSDSB_OK;
 }

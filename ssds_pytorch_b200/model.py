@@ -71,6 +71,46 @@ class _DwConv:
         self.flops_per_pixel = 2 * 9 * c
 
 
+class _Steps(list):
+    """The recorded launch sequence.  Every step carries the id of the BRANCH it was recorded on (0 = main).
+    Branches express independence between chains of small launches (the per-level towers of FPN / BiFPN /
+    YOLOv3 heads, SSD extras): under CUDA-graph capture each branch is captured on its own stream, forked from
+    the main stream where its first step was recorded (it depends on everything recorded on main before that)
+    or from another branch (`fork(new, after=parent)`), and joined back at the end of the graph, so that kernels
+    too small to fill the GPU run side by side.  Eager replay runs the steps in recording order on one stream —
+    same kernels, same values."""
+
+    def __init__(self):
+        super().__init__()
+        self.tags = []
+        self.parents = {}          # branch id -> (parent branch id, number of steps recorded at fork time)
+        self.cur = 0
+        self._next = 1
+
+    def append(self, fn):
+        super().append(fn)
+        self.tags.append(self.cur)
+
+    def fork(self, after=0):
+        """Start a new branch that depends on everything recorded so far on branch `after`; returns its id."""
+        b = self._next
+        self._next += 1
+        self.parents[b] = (after, len(self))
+        return b
+
+    def on(self, branch):
+        steps = self
+
+        class _Ctx:
+            def __enter__(self_):
+                self_.prev = steps.cur
+                steps.cur = branch
+
+            def __exit__(self_, *a):
+                steps.cur = self_.prev
+        return _Ctx()
+
+
 class _Engine(torch.nn.Module):
     """Shared machinery: plan recording (static buffers), CUDA-graph replay.  Subclasses provide a
     backbone (`_build_backbone`, `_plan_backbone`) and a neck (`_build_neck`, `_plan_neck`)."""
@@ -97,7 +137,7 @@ class _Engine(torch.nn.Module):
             N, H, W, _ = images.shape
         else:
             N, _, H, W = images.shape
-        steps = []          # list of zero-arg callables
+        steps = _Steps()    # list of zero-arg callables (+ the branch each one was recorded on)
         info = {}           # step index -> {kind, flops, bytes}: algorithmic work of that launch (profiling tools)
         flops = [0]
         split = [None]
@@ -137,8 +177,6 @@ class _Engine(torch.nn.Module):
                 loc = torch.empty((n, h.n_loc, fh, fw), dtype=torch.float32, device=dev)
             if conf is None:
                 conf = torch.empty((n, h.cout - h.n_loc, fh, fw), dtype=torch.float32, device=dev)
-            if split[0] is None:
-                split[0] = len(steps)          # first launch that writes the loc/conf outputs
             steps.append(lambda: K.conv2d_head(f, h.w, h.bias, h.n_loc, not self.training,
                                                loc=loc, conf=conf))
             flops[0] += h.flops_per_pixel * n * fh * fw
@@ -164,10 +202,13 @@ class _Engine(torch.nn.Module):
 
         self._add_raw = add_raw
         feats = self._plan_backbone(packed, H, W, steps, buf, add_conv, add_dw)
+        # everything after the backbone may write the loc/conf outputs: the graph is split here, and the second
+        # part waits for the consumer of the previous step's outputs (decode/NMS on another stream)
+        split[0] = len(steps)
         locs, confs = self._plan_neck(feats, steps, buf, add_conv, add_head)
         return {"src": src, "steps": steps, "loc": tuple(locs), "conf": tuple(confs),
                 "flops": flops[0], "graph": None, "launches": len(steps), "info": info,
-                "split": split[0] if split[0] is not None else len(steps)}
+                "split": split[0]}
 
     def plan_for(self, images):
         key = (tuple(images.shape), images.dtype, self.training)
@@ -186,14 +227,7 @@ class _Engine(torch.nn.Module):
                 for s in plan["steps"]:                # warm-up: sets kernel attributes etc.
                     s()
                 torch.cuda.synchronize(self.device)
-                graphs = []
-                for part in (plan["steps"][:k], plan["steps"][k:]):
-                    g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g):
-                        for s in part:
-                            s()
-                    graphs.append(g)
-                plan["graph"] = graphs
+                plan["graph"] = [self._capture(plan["steps"], 0, k), self._capture(plan["steps"], k, len(plan["steps"]))]
             plan["graph"][0].replay()
             if outputs_free is not None:
                 torch.cuda.current_stream().wait_event(outputs_free)
@@ -204,6 +238,30 @@ class _Engine(torch.nn.Module):
                     torch.cuda.current_stream().wait_event(outputs_free)
                 s()
         return plan["loc"], plan["conf"]
+
+    def _capture(self, steps, lo, hi):
+        """CUDA graph of steps[lo:hi]; branches (see _Steps) are captured on forked side streams."""
+        use_branches = os.environ.get("SSDSB_NO_BRANCH", "0") != "1"
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            main = torch.cuda.current_stream()
+            streams = {0: main}
+            for i in range(lo, hi):
+                tag = steps.tags[i] if use_branches else 0
+                st = streams.get(tag)
+                if st is None:                                  # first step of this branch inside the part: fork
+                    st = streams[tag] = torch.cuda.Stream(device=self.device)
+                    parent = steps.parents[tag][0]
+                    st.wait_stream(streams.get(parent, main))   # depends on what its parent has recorded so far
+                if st is main:
+                    steps[i]()
+                else:
+                    with torch.cuda.stream(st):
+                        steps[i]()
+            for tag, st in streams.items():                     # join
+                if st is not main:
+                    main.wait_stream(st)
+        return g
 
     def forward(self, x, use_graph=False, outputs_free=None):
         """x: fp32 NCHW [B,3,H,W] (already `(img-mean)/std`-normalised if mean/std were left at
@@ -463,16 +521,21 @@ class _SSDNeck:
 
     def _plan_neck(self, feats, steps, buf, add_conv, add_head):
         feats = list(feats)
-        for ex in self.extras:                         # ssd.py:61-64
-            y = feats[-1]
-            for cv in ex:
-                y = add_conv(cv, y)
-            feats.append(y)
-        locs, confs = [], []
-        for f, h in zip(feats, self.heads):            # ssd.py:67-70
-            loc, conf = add_head(f, h)
-            locs.append(loc)
-            confs.append(conf)
+        n_back = len(feats)
+        locs, confs = [None] * len(self.heads), [None] * len(self.heads)
+        # the extras chain and the heads of its (small) levels run on side branches next to each other; the
+        # heads of the backbone levels follow on main (see _Steps)
+        chain = steps.fork() if self.extras else 0
+        for j, ex in enumerate(self.extras):           # ssd.py:61-64
+            with steps.on(chain):
+                y = feats[-1]
+                for cv in ex:
+                    y = add_conv(cv, y)
+                feats.append(y)
+            with steps.on(steps.fork(after=chain)):
+                locs[n_back + j], confs[n_back + j] = add_head(y, self.heads[n_back + j])
+        for l in range(n_back):                        # ssd.py:67-70
+            locs[l], confs[l] = add_head(feats[l], self.heads[l])
         return locs, confs
 
 
@@ -531,32 +594,44 @@ class _FPNNeck:
         n_back = len(feats)
         raw_top = feats[-1]
         pyr = self._plan_pyramid(feats, steps, buf, add_conv)
-        levels = []
-        xx = None
-        for i, ex in enumerate(self.extras):           # fpn.py:89-95
-            if i < n_back:
-                xx = add_conv(ex, pyr[i])
-            elif i == n_back:
-                xx = add_conv(ex, raw_top)
-            else:
-                xx = add_conv(ex, xx)
-            levels.append(xx)
-        locs, confs = [], []
+        # every pyramid level is an independent chain (extra -> fused tower layer 0 -> loc tower | conf tower ->
+        # heads): level 0 stays on main, the others run on their own branches, the conf tower of a level on a
+        # sub-branch of it (see _Steps) — the 5x5 ... 40x40 levels cannot fill 148 SMs one launch at a time
+        # Recording order matters: a branch depends on what its parent had recorded when the branch's first step
+        # was recorded, so the branches are recorded first and the main (level-0) chain last.
+        L = len(self.extras)
+        locs, confs = [None] * L, [None] * L
         dev = self.device
-        for f in levels:                               # shared towers, fpn.py:94-95
-            t = add_conv(self.tower0, f)               # [.., 512]: loc half | conf half
-            tl, tc = t[..., :256], t[..., 256:]
-            for j in range(3):
-                tl = add_conv(self.tower["loc"][j], tl)
-                tc = add_conv(self.tower["conf"][j], tc)
-            n, fh, fw, _ = f.shape
-            loc = torch.empty((n, self.head_loc.cout, fh, fw), dtype=torch.float32, device=dev)
-            conf = torch.empty((n, self.head_conf.cout, fh, fw), dtype=torch.float32, device=dev)
-            dummy_c = torch.empty((1,), dtype=torch.float32, device=dev)
-            add_head(tl, self.head_loc, loc=loc, conf=dummy_c)
-            add_head(tc, self.head_conf, loc=dummy_c, conf=conf)
-            locs.append(loc)
-            confs.append(conf)
+        level_in = {}                                   # level -> (branch, extra output) once recorded
+
+        def record_level(i, br):
+            with steps.on(br):
+                if i < n_back:
+                    f = add_conv(self.extras[i], pyr[i])                       # fpn.py:89-95
+                elif i == n_back:
+                    f = add_conv(self.extras[i], raw_top)
+                else:
+                    f = add_conv(self.extras[i], level_in[i - 1][1])
+                level_in[i] = (br, f)
+                t = add_conv(self.tower0, f)               # [.., 512]: loc half | conf half   (fpn.py:94-95)
+                tl, tc = t[..., :256], t[..., 256:]
+                n, fh, fw, _ = f.shape
+                loc = torch.empty((n, self.head_loc.cout, fh, fw), dtype=torch.float32, device=dev)
+                conf = torch.empty((n, self.head_conf.cout, fh, fw), dtype=torch.float32, device=dev)
+                dummy_c = torch.empty((1,), dtype=torch.float32, device=dev)
+                with steps.on(steps.fork(after=br) if br != 0 else 0):        # conf tower: sub-branch
+                    for j in range(3):
+                        tc = add_conv(self.tower["conf"][j], tc)
+                    add_head(tc, self.head_conf, loc=dummy_c, conf=conf)
+                for j in range(3):
+                    tl = add_conv(self.tower["loc"][j], tl)
+                add_head(tl, self.head_loc, loc=loc, conf=dummy_c)
+            locs[i], confs[i] = loc, conf
+
+        for i in range(1, L):
+            br = steps.fork() if i <= n_back else steps.fork(after=level_in[i - 1][0])
+            record_level(i, br)
+        record_level(0, 0)
         return locs, confs
 
 
@@ -654,6 +729,31 @@ class _YOLOV3Neck:
         n_back = len(feats)
         feats = list(feats)
         raw_top = feats[-1]
+        L = len(self.extras)
+        locs, confs = [None] * L, [None] * L
+        dev = self.device
+
+        def record_heads(l, f, br):
+            with steps.on(br):
+                t = add_conv(self.towers[l], f)                                   # [.., 2c]: loc half | conf half
+                c = t.shape[3] // 2
+                n, fh, fw, _ = f.shape
+                loc = torch.empty((n, self.head_loc[l].cout, fh, fw), dtype=torch.float32, device=dev)
+                conf = torch.empty((n, self.head_conf[l].cout, fh, fw), dtype=torch.float32, device=dev)
+                dummy = torch.empty((1,), dtype=torch.float32, device=dev)
+                add_head(t[..., :c], self.head_loc[l], loc=loc, conf=dummy)
+                add_head(t[..., c:], self.head_conf[l], loc=dummy, conf=conf)
+            locs[l], confs[l] = loc, conf
+
+        # 'Conv:S' levels hang off the raw last backbone map (yolo.py:77-82): their chain runs on a branch of its
+        # own, next to the top-down path; every level's heads fork off as soon as its map exists (see _Steps)
+        prev, src = 0, raw_top
+        for i in range(n_back, L):
+            br = steps.fork(after=prev)
+            with steps.on(br):
+                src = add_conv(self.extras[i][0], src)
+            record_heads(i, src, steps.fork(after=br))
+            prev = br
         xx = None
         for i in range(n_back - 1, -1, -1):                                       # yolo.py:67-74
             if i != n_back - 1:
@@ -667,23 +767,7 @@ class _YOLOV3Neck:
             for cv in self.extras[i]:
                 xx = add_conv(cv, xx)
             feats[i] = xx
-        levels = list(feats)
-        for i in range(n_back, len(self.extras)):                                 # yolo.py:77-82
-            src = raw_top if i == n_back else levels[-1]
-            levels.append(add_conv(self.extras[i][0], src))
-        locs, confs = [], []
-        dev = self.device
-        for l, f in enumerate(levels):
-            t = add_conv(self.towers[l], f)                                       # [.., 2c]: loc half | conf half
-            c = t.shape[3] // 2
-            n, fh, fw, _ = f.shape
-            loc = torch.empty((n, self.head_loc[l].cout, fh, fw), dtype=torch.float32, device=dev)
-            conf = torch.empty((n, self.head_conf[l].cout, fh, fw), dtype=torch.float32, device=dev)
-            dummy = torch.empty((1,), dtype=torch.float32, device=dev)
-            add_head(t[..., :c], self.head_loc[l], loc=loc, conf=dummy)
-            add_head(t[..., c:], self.head_conf[l], loc=dummy, conf=conf)
-            locs.append(loc)
-            confs.append(conf)
+            record_heads(i, xx, steps.fork() if i != 0 else 0)
         return locs, confs
 
 

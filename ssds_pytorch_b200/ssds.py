@@ -78,10 +78,11 @@ class SSDDetector(object):
         self._post_out = None
 
     # -------------------------------------------------------------- device-side entry points
-    def detect_device(self, images, overlap=False):
+    def detect_device(self, images, overlap=False, packed_out=None):
         """images already on the GPU: uint8 NHWC [B,H,W,3] (raw pixels) or fp32 NCHW [B,3,H,W] raw
         pixel values; normalisation (x-mean)/std (ssds.py:57) is fused into the first kernel.
-        Returns device tensors (scores [B,D], boxes [B,D,4], classes [B,D]).
+        Returns device tensors (scores [B,D], boxes [B,D,4], classes [B,D]); with `packed_out` (a [B,D,6]
+        fp32 tensor) the NMS kernel also fills (score, x1, y1, x2, y2, class) there.
 
         overlap=True runs decode + NMS on a side stream so that they overlap the conv stack of the next
         call (the memory-/latency-bound post-processing hides behind tensor-core work); the results are
@@ -90,7 +91,7 @@ class SSDDetector(object):
         `record_stream`, so the caching allocator cannot recycle them under a pending reader)."""
         if not overlap:
             loc, conf = self.model(images, use_graph=self.use_graph)
-            return self.decoder(loc, conf, self.anchors)
+            return self.decoder(loc, conf, self.anchors, packed_out=packed_out)
         if self._post_stream is None:
             self._post_stream = torch.cuda.Stream(device=self.device)
         main = torch.cuda.current_stream()
@@ -99,10 +100,10 @@ class SSDDetector(object):
         heads_done.record(main)
         with torch.cuda.stream(self._post_stream):
             self._post_stream.wait_event(heads_done)
-            out = self.decoder(loc, conf, self.anchors)
+            out = self.decoder(loc, conf, self.anchors, packed_out=packed_out)
             self._post_done = torch.cuda.Event()
             self._post_done.record(self._post_stream)
-        self._post_out = out
+        self._post_out = out if isinstance(out, (tuple, list)) else (out,)
         return out
 
     def join(self):
@@ -153,13 +154,11 @@ class SSDDetector(object):
             st["dev_in"].copy_(t, non_blocking=True)
             st["copied"].record()
         cur.wait_event(st["copied"])
-        s, b, c = self.detect_device(st["dev_in"], overlap=True)
+        # the NMS kernel writes the packed [B,D,6] block itself (no packing launches on the post stream)
+        self.detect_device(st["dev_in"], overlap=True, packed_out=st["dev_out"])
         st["consumed"].record()          # (the plan copied dev_in into its own buffer first)
-        with torch.cuda.stream(self._post_stream):      # packing, all-gather and D2H ride with decode/NMS
+        with torch.cuda.stream(self._post_stream):      # all-gather and D2H ride with decode/NMS
             o = st["dev_out"]
-            o[:, :, 0] = s
-            o[:, :, 1:5] = b
-            o[:, :, 5] = c
             if gather:
                 o = gather_detections(o)
             if out is None:

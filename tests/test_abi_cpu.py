@@ -35,7 +35,7 @@ def test_argument_errors_without_gpu():
     """Validation happens before any CUDA call, so it is testable on CPU."""
     from ssds_pytorch_b200 import _lib
     lib = _lib.lib
-    rc = lib.ssdsb_nms(None, None, None, 1, 10, 0.5, 0, 1, None, None, None, None, None, 0, None)
+    rc = lib.ssdsb_nms(None, None, None, 1, 10, 0.5, 0, 1, None, None, None, None, None, None, 0, None)
     assert rc == _lib.ERR_INVALID
     assert b"ndetections" in lib.ssdsb_last_error_string()
     with pytest.raises(ValueError):

@@ -521,3 +521,108 @@ def test_detection_loss_step_backward_vs_oracle(B):
             el = LG.loc_sum_grad(l.reshape(Bn, 9, 4, hw, hw), box_t, dep, scale, ty)
             np.testing.assert_allclose(cpu(gl.grad).reshape(el.shape), el, rtol=1e-4, atol=2e-8)
             assert np.abs(el).max() > 0
+
+
+# ----------------------------------------------------------------------------- decode, large top_n (decode_large.cu)
+def _cmp_decode(B, O, conf, loc, stride, thr, top_n, anc):
+    """indices / classes bit-exact; boxes 1e-4; raw scores (rescore off) bit-exact.  Rescored scores: the centerness
+    ratio min(l,r)/max(l,r) amplifies the 1-ulp difference between the GPU's and numpy's exp() when a box edge sits
+    next to the anchor centre, so over tens of thousands of results a few exceed the 2e-6 of the small tests: 2e-5
+    absolute / 1e-3 relative here (observed worst case 8.3e-6 absolute, 2.2e-4 relative)."""
+    tc, tl, ta = torch.from_numpy(conf), torch.from_numpy(loc), torch.from_numpy(anc)
+    got = B.decode(tc, tl, stride, thr, top_n, ta, True, return_indices=True)
+    exp = O.decode(conf, loc, stride, thr, top_n, anc, True, return_indices=True)
+    np.testing.assert_array_equal(cpu(got[3]).astype(np.int64), exp[3])
+    np.testing.assert_array_equal(cpu(got[2]), exp[2])
+    np.testing.assert_allclose(cpu(got[0]), exp[0], rtol=1e-3, atol=2e-5)
+    np.testing.assert_allclose(cpu(got[1]), exp[1], rtol=1e-5, atol=1e-4)
+    raw = B.decode(tc, tl, stride, thr, top_n, ta, False, return_indices=True)
+    rexp = O.decode(conf, loc, stride, thr, top_n, anc, False, return_indices=True)
+    np.testing.assert_array_equal(cpu(raw[3]).astype(np.int64), rexp[3])
+    np.testing.assert_array_equal(cpu(raw[0]), rexp[0])
+    return got
+
+
+def test_decode_large_top_n_stress_geometry(B):
+    """SURVEY 8d cfg-5 stress: 20 000 candidates per level out of a 160x160x3x80 map whose scores are CLUSTERED like a
+    random-init head's (sigmoid(-4.6 + small): nearly all within two exponents), several 64Ki slices; indices bit-exact."""
+    from oracle import box_oracle as O
+    rng = np.random.default_rng(99)
+    A, C, H, W, stride = 3, 80, 80, 80, 16           # 1 536 000 scores / image (24 slices)
+    anc = O.generate_anchors(stride, [1, 2, 0.5], [4.0])
+    logits = rng.normal(-4.6, 0.25, (2, A * C, H, W)).astype(np.float32)
+    conf = (1.0 / (1.0 + np.exp(-logits))).astype(np.float32)
+    loc = rng.normal(0, 0.3, (2, A * 4, H, W)).astype(np.float32)
+    for top_n in (20000, 4097, 40000):
+        _cmp_decode(B, O, conf, loc, stride, 0.01, top_n, anc)
+
+
+def test_decode_large_top_n_edge_cases(B, monkeypatch):
+    """fewer survivors than top_n; ties at the cut (quantised scores -> big groups of equal keys, lowest flat index
+    first); a constant map (the degenerate single-CTA re-scan path); large path == rounds path bit for bit."""
+    from oracle import box_oracle as O
+    rng = np.random.default_rng(5)
+    A, C, H, W, stride = 3, 20, 48, 48, 8            # 138 240 scores / image
+    anc = O.generate_anchors(stride, [1, 2, 0.5], [4.0])
+    loc = rng.normal(0, 0.3, (2, A * 4, H, W)).astype(np.float32)
+    conf = distinct(rng, (2, A * C, H, W), 0.0, 1.0)
+    conf[1] *= (rng.uniform(size=conf[1].shape) < 0.01)          # ~1400 survivors < top_n
+    _cmp_decode(B, O, conf, loc, stride, 0.3, 3000, anc)
+    q = (np.floor(rng.uniform(0, 1, (2, A * C, H, W)) * 64) / 64).astype(np.float32)      # 64 distinct values
+    _cmp_decode(B, O, q, loc, stride, 0.05, 5000, anc)
+    const = np.full((2, A * C, H, W), 0.5, np.float32)          # every key equal: first top_n flat indices
+    const[1, :, :, 7] = 0.75
+    got = _cmp_decode(B, O, const, loc, stride, 0.01, 20000, anc)
+    np.testing.assert_array_equal(cpu(got[3])[0], np.arange(20000, dtype=np.int32))
+    # rounds path (SSDSB_DECODE_ROUNDS=1) == large path
+    a = B.decode(torch.from_numpy(conf), torch.from_numpy(loc), stride, 0.05, 6000, torch.from_numpy(anc), True,
+                 return_indices=True)
+    monkeypatch.setenv("SSDSB_DECODE_ROUNDS", "1")
+    b_ = B.decode(torch.from_numpy(conf), torch.from_numpy(loc), stride, 0.05, 6000, torch.from_numpy(anc), True,
+                  return_indices=True)
+    monkeypatch.delenv("SSDSB_DECODE_ROUNDS")
+    for x, y in zip(a, b_):
+        assert torch.equal(x, y)
+
+
+def test_nms_packed_output_equals_separate_outputs(B):
+    """The [B,D,6] block the NMS kernel can write directly (what SSDDetector ships / all-gathers) equals the three
+    separate outputs, with and without them being requested."""
+    rng = np.random.default_rng(3)
+    scores, boxes, classes = clustered(rng, 3, 900, 5)
+    s, b, c = B.nms(torch.from_numpy(scores), torch.from_numpy(boxes), torch.from_numpy(classes), 0.5, 100, True)
+    pk = torch.full((3, 100, 6), float("nan"), device="cuda")
+    s2, b2, c2 = B.nms(torch.from_numpy(scores), torch.from_numpy(boxes), torch.from_numpy(classes), 0.5, 100, True,
+                       packed_out=pk)
+    only = B.nms(torch.from_numpy(scores), torch.from_numpy(boxes), torch.from_numpy(classes), 0.5, 100, True,
+                 packed_out=True)
+    ref = torch.cat([s[..., None], b, c[..., None]], -1)
+    assert torch.equal(s, s2) and torch.equal(b, b2) and torch.equal(c, c2)
+    assert torch.equal(pk, ref) and torch.equal(only, ref)
+
+
+def test_nms_long_rows_preselection_equals_streaming_selection(B, monkeypatch):
+    """N > 8192: the first 2048 candidates come from the multi-CTA exact selection (decode_large.cu topk_rows); the
+    outputs (scores, boxes, classes, keep indices) must equal the single-CTA streaming selection bit for bit — also
+    when 2048 candidates are not enough and the kernel falls back to streaming rounds (one class, one tight cluster),
+    with tied scores (ascending input position), and with fewer than 2048 positive scores."""
+    rng = np.random.default_rng(17)
+    cases = []
+    s, b, c = clustered(rng, 2, 100000, 80, img=1280.0, nclusters=40)
+    cases.append((s, b, c, 100))
+    s, b, c = clustered(rng, 2, 20000, 1, img=200.0, nclusters=1)                # > 2048 candidates per pivot set
+    cases.append((s, b, c, 300))
+    s, b, c = clustered(rng, 2, 30000, 3, img=900.0, nclusters=12)
+    s = (np.floor(s * 50) / 50).astype(np.float32)                              # heavy score ties
+    cases.append((s, b, c, 100))
+    s, b, c = clustered(rng, 2, 9000, 5, img=700.0, nclusters=9, frac_zero=0.9)  # ~900 positive scores
+    cases.append((s, b, c, 100))
+    for s, b, c, D in cases:
+        ts, tb, tc = torch.from_numpy(s), torch.from_numpy(b), torch.from_numpy(c)
+        got = B.nms(ts, tb, tc, 0.6, D, True, return_indices=True)
+        monkeypatch.setenv("SSDSB_NMS_NO_PRESEL", "1")
+        ref = B.nms(ts, tb, tc, 0.6, D, True, return_indices=True)
+        monkeypatch.delenv("SSDSB_NMS_NO_PRESEL")
+        for x, y in zip(got, ref):
+            assert torch.equal(x, y)
+        assert (got[0] > 0).sum() > 0

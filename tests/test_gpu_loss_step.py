@@ -46,14 +46,14 @@ def setup(seed, Bn, C, levels, T, img, scales=(4.0, 5.04, 6.35)):
     return rng, anchors, tanc, tg, conf, loc, A
 
 
-def oracle_step(O, anchors, levels, tg, conf, loc, Bn, A, C, cls, ty):
+def oracle_step(O, anchors, levels, tg, conf, loc, Bn, A, C, cls, ty, ratio=3):
     ecs = els = 0.0
     efg = 0
     per = []
     for (s, hw), c, l in zip(levels, conf, loc):
         cls_t, box_t, dep = O.extract_targets(tg, anchors, C, s, (hw, hw), [0.5, 0.4])
         if cls == "MultiBoxLoss":
-            sums, npos = O.multibox_loss_reduced(c.reshape(Bn, A, C, hw, hw), cls_t, dep, 3)
+            sums, npos = O.multibox_loss_reduced(c.reshape(Bn, A, C, hw, hw), cls_t, dep, ratio)
             lsum = np.zeros(Bn)
             if ty is not None:
                 lv = O.loc_loss(l.reshape(Bn, A, 4, hw, hw), box_t, ty)
@@ -153,19 +153,25 @@ def test_fused_step_cfg4_geometry_vs_per_level_kernels(P):
 
 
 def test_fused_step_many_targets_and_negpos_clamp(P):
-    """T = 150 (second staging chunk) and so many positives that 3 * num_pos exceeds N - 1 (criterion.py:65)."""
+    """T = 150 (second staging chunk) and a negpos_ratio so large that ratio * num_pos exceeds N - 1 (the clamp of
+    criterion.py:65: every anchor but one ranks as a hard negative, zeros included, in index order)."""
     from oracle import box_oracle as O
     Bn, C = 2, 6
     levels = [(16, 12)]
     rng, anchors, tanc, tg, conf, loc, A = setup(5, Bn, C, levels, 150, 192, scales=(2.0, 2.828))
     tg[:, :, 2:4] = np.where(tg[:, :, 2:4] > 0, np.minimum(tg[:, :, 2:4], 64.0), tg[:, :, 2:4])
-    sc, parts = P.fused_loss_step([torch.from_numpy(x).cuda() for x in loc], [torch.from_numpy(x).cuda() for x in conf],
-                                  torch.from_numpy(tg).cuda(), tanc, C, "MultiBoxLoss", None, with_targets=True)
-    ecl, _, efg, per = oracle_step(O, anchors, levels, tg, conf, loc, Bn, A, C, "MultiBoxLoss", None)
-    np.testing.assert_array_equal(parts["depth"][0].cpu().numpy(), per[0][3])
-    N = A * 12 * 12
-    assert (3 * per[0][2] > N - 1).any(), "case must exercise the num_neg clamp"
-    np.testing.assert_allclose(sc.cpu().numpy()[0], ecl, rtol=3e-4)
+    for ratio in (3, 60):
+        sc, parts = P.fused_loss_step([torch.from_numpy(x).cuda() for x in loc], [torch.from_numpy(x).cuda() for x in conf],
+                                      torch.from_numpy(tg).cuda(), tanc, C, "MultiBoxLoss", None, negpos_ratio=ratio,
+                                      with_targets=True)
+        ecl, _, efg, per = oracle_step(O, anchors, levels, tg, conf, loc, Bn, A, C, "MultiBoxLoss", None, ratio)
+        np.testing.assert_array_equal(parts["depth"][0].cpu().numpy(), per[0][3])
+        np.testing.assert_array_equal(parts["num_pos"][0].cpu().numpy(), per[0][2].astype(np.float32))
+        N = A * 12 * 12
+        if ratio == 60:
+            assert (ratio * per[0][2] > N - 1).all() and (per[0][2] > 0).all(), "case must exercise the num_neg clamp"
+        np.testing.assert_allclose(parts["cls_sum"][0].cpu().numpy(), per[0][0], rtol=3e-4)
+        np.testing.assert_allclose(sc.cpu().numpy()[0], ecl, rtol=3e-4)
 
 
 def test_loss_step_host_api_matches_device_path(P):

@@ -1,0 +1,153 @@
+"""Run every NON-conv kernel of the hot path once (after a warm-up) at the BASELINE geometry it is benchmarked
+on, so that ONE `ncu --set full` capture of this script has a warm launch of each:
+
+    python tools/profile_misc.py [loss] [match] [decode] [decode_large] [nms] [dw] [layout]
+
+loss          loss_step_kernel (cfg 4: 5 levels, A=9, C=80, 76 725 anchors/img, 16 images, T=32) MultiBox + SmoothL1
+match         match_kernel + mbl_ce/mbl_select/mbl_sum + focal_kernel + loc_loss_kernel + masked_sum (cfg-4 level 0)
+decode        decode_select + decode_finalize (cfg 2: 6 levels, 64 images)
+decode_large  dl_pass<1,2,3> + dl_finalize (cfg-5 stress: 5 levels, A=3, 4 images, 20 000 per level)
+nms           nms_kernel at N=1800 x 64 images and N=100 000 x 4 images
+dw            dwconv3x3_kernel at the MobileNetV2-SSD 300x300 B=64 block shapes
+layout        pack_image_s2d, maxpool3x3s2, upsample2x_add, upsample2x_concat, bifpn_fuse
+Without a profiler it prints CUDA-event timings of each section.
+"""
+import sys
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+sys.path.insert(0, __file__.rsplit("/", 2)[0])
+import ssds_pytorch_b200 as S                              # noqa: E402
+from ssds_pytorch_b200 import conv as K                   # noqa: E402
+from ssds_pytorch_b200 import pipeline as P               # noqa: E402
+from ssds_pytorch_b200 import synth                       # noqa: E402
+
+
+def timed(name, fn, iters=5):
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"{name}: {e0.elapsed_time(e1) / iters * 1e3:.1f} us")
+
+
+def levels_cfg4(B):
+    g = torch.Generator(device="cuda").manual_seed(1)
+    lv = [(8, 80), (16, 40), (32, 20), (64, 10), (128, 5)]
+    anchors = OrderedDict((s, S.generate_anchors(s, [1, 2, 0.5], [4.0, 5.04, 6.35])) for s, _ in lv)
+    conf = [torch.randn((B, 9 * 80, hw, hw), generator=g, device="cuda") - 4.6 for _, hw in lv]
+    loc = [torch.randn((B, 9 * 4, hw, hw), generator=g, device="cuda") * 0.5 for _, hw in lv]
+    tg = synth.synthetic_targets(B, seed=4321).cuda()
+    return lv, anchors, conf, loc, tg
+
+
+def run_loss():
+    B = 16
+    lv, anchors, conf, loc, tg = levels_cfg4(B)
+    out = torch.empty(3, device="cuda")
+    timed("loss_step (MultiBox + SmoothL1), cfg4 16 img", lambda: P.fused_loss_step(loc, conf, tg, anchors, 80, "MultiBoxLoss",
+                                                                                 "SmoothL1Loss", out=out))
+    timed("loss_step (MultiBox only), cfg4 16 img", lambda: P.fused_loss_step(loc, conf, tg, anchors, 80, "MultiBoxLoss", None, out=out))
+    timed("loss_step (Focal + SmoothL1), cfg4 16 img", lambda: P.fused_loss_step(loc, conf, tg, anchors, 80, "FocalLoss",
+                                                                               "SmoothL1Loss", out=out))
+    print("scalars", out.tolist())
+
+
+def run_match():
+    B = 16
+    lv, anchors, conf, loc, tg = levels_cfg4(B)
+    crit, foc, sl1 = S.MultiBoxLoss(3), S.FocalLoss(), S.SmoothL1Loss()
+    s, hw = lv[0]
+    c5 = conf[0].view(B, 9, 80, hw, hw)
+    l5 = loc[0].view(B, 9, 4, hw, hw)
+    _, bt, dep = S.extract_targets(tg, anchors, 80, s, (hw, hw), [0.5, 0.4], with_cls_target=False)
+    timed("match_kernel cfg4 L0", lambda: S.extract_targets(tg, anchors, 80, s, (hw, hw), [0.5, 0.4], with_cls_target=False))
+    timed("mbl sum cfg4 L0", lambda: crit.forward_sum(c5, dep))
+    timed("focal sum cfg4 L0", lambda: foc.forward_sum(c5, dep))
+    timed("smoothl1 sum cfg4 L0", lambda: sl1.forward_sum(l5, bt, dep))
+
+
+def score_levels(B, lv, A, C, seed):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    conf = [torch.sigmoid(torch.randn((B, A * C, h, w), generator=g, device="cuda") * 0.3 - 4.6) for _, h, w in lv]
+    loc = [torch.randn((B, A * 4, h, w), generator=g, device="cuda") * 0.3 for _, h, w in lv]
+    return conf, loc
+
+
+def run_decode():
+    B = 64
+    lv = [(8, 64, 64), (16, 32, 32), (32, 16, 16), (64, 8, 8), (128, 4, 4), (256, 2, 2)]
+    conf, loc = score_levels(B, lv, 6, 80, 2)
+    items = [(s, S.generate_anchors(s, [1, 2, 0.5], [2.0, 2.828])) for s, _, _ in lv]
+    timed("decode cfg2 64 img (select + finalize)", lambda: S.decode_levels(conf, loc, items, 0.01, 300, True))
+    return S.decode_levels(conf, loc, items, 0.01, 300, True)
+
+
+def run_decode_large():
+    B = 4
+    lv = [(8, 160, 160), (16, 80, 80), (32, 40, 40), (64, 20, 20), (128, 10, 10)]
+    conf, loc = score_levels(B, lv, 3, 80, 3)
+    items = [(s, S.generate_anchors(s, [1, 2, 0.5], [4.0])) for s, _, _ in lv]
+    timed("decode cfg5stress 4 img, 20 000/level (3 passes + finalize)",
+          lambda: S.decode_levels(conf, loc, items, 0.01, 20000, True))
+    return S.decode_levels(conf, loc, items, 0.01, 20000, True)
+
+
+def run_nms(dec_small=None, dec_large=None):
+    if dec_small is None:
+        dec_small = run_decode()
+    timed("nms N=1800 x 64 img", lambda: S.nms(*dec_small, 0.6, 100, True))
+    if dec_large is None:
+        dec_large = run_decode_large()
+    timed("nms N=100 000 x 4 img", lambda: S.nms(*dec_large, 0.6, 100, True))
+
+
+def run_dw():
+    g = torch.Generator(device="cuda").manual_seed(4)
+    for (h, c, stride) in [(150, 96, 2), (75, 160, 1), (75, 160, 2), (38, 192, 1), (38, 192, 2), (19, 384, 1), (19, 576, 1),
+                           (19, 576, 2), (10, 960, 1)]:
+        x = torch.randn((64, h, h, c), generator=g, device="cuda").to(torch.bfloat16)
+        w = K.pack_dw_weight(torch.randn((c, 1, 3, 3)) * 0.3).cuda()
+        b = torch.zeros(c, device="cuda")
+        timed(f"dwconv3x3 s{stride} {c} @{h}", lambda: K.dwconv3x3(x, w, b, stride, 2))
+
+
+def run_layout():
+    g = torch.Generator(device="cuda").manual_seed(5)
+    img = torch.randint(0, 256, (64, 512, 512, 3), dtype=torch.uint8, device="cuda")
+    timed("pack_image_s2d 64x512x512", lambda: K.pack_image_s2d(img, 0.0, 255.0, padded=True))
+    x = torch.randn((64, 256, 256, 64), generator=g, device="cuda").to(torch.bfloat16)
+    timed("maxpool3x3s2 64x256x256x64", lambda: K.maxpool3x3s2(x))
+    fine = torch.randn((16, 80, 80, 256), generator=g, device="cuda").to(torch.bfloat16)
+    coarse = torch.randn((16, 40, 40, 256), generator=g, device="cuda").to(torch.bfloat16)
+    timed("upsample2x_add 16x80x80x256", lambda: K.upsample2x_add(coarse, fine))
+    timed("upsample2x_concat 16x80x80x(256+256)", lambda: K.upsample2x_concat(fine, coarse))
+    a = torch.randn((4, 160, 160, 256), generator=g, device="cuda").to(torch.bfloat16)
+    bb = torch.randn((4, 80, 80, 256), generator=g, device="cuda").to(torch.bfloat16)
+    timed("bifpn_fuse up 4x160x160x256", lambda: K.bifpn_fuse(a, bb, 0.5, 0.5, mode=0))
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["loss", "match", "decode", "decode_large", "nms", "dw", "layout"]
+    small = large = None
+    for w in which:
+        if w == "loss":
+            run_loss()
+        elif w == "match":
+            run_match()
+        elif w == "decode":
+            small = run_decode()
+        elif w == "decode_large":
+            large = run_decode_large()
+        elif w == "nms":
+            run_nms(small, large)
+        elif w == "dw":
+            run_dw()
+        elif w == "layout":
+            run_layout()
