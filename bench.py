@@ -286,8 +286,7 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from ssds_pytorch_b200 import synth
-    from ssds_pytorch_b200.box import decode_levels, nms as nms_op, extract_targets
-    from ssds_pytorch_b200.criterion import MultiBoxLoss
+    from ssds_pytorch_b200.box import decode_levels, nms as nms_op
     from ssds_pytorch_b200.model import number_box_from_cfg
     from ssds_pytorch_b200.pipeline import LossStep
     from ssds_pytorch_b200.ssds import SSDDetector, gather_detections
@@ -435,17 +434,11 @@ def run_b200(args):
             dec = decode_levels(conf, loc, items, 0.01, pl, True)
             sec["nms"] = _timed(lambda: nms_op(*dec, 0.6, 100, True), K, barrier)
         else:
-            crit = MultiBoxLoss(3)
-            views = [(cf.view(B, cf.shape[1] // C, C, cf.shape[2], cf.shape[3]), st, cf.shape[-2:])
-                     for cf, st in zip(conf, anchors.keys())]
-
-            def match_all():
-                return [extract_targets(tg_dev, anchors, C, st, hw, [0.5, 0.4], 0, with_cls_target=False)[2]
-                        for _, st, hw in views]
-            sec["match"] = _timed(match_all, K, barrier)
-            depths = match_all()
-            sec["loss"] = _timed(lambda: [crit.forward_sum(v[0], d) for v, d in zip(views, depths)], K, barrier)
-    launches += 3 if detect else 4 * L
+            from ssds_pytorch_b200.pipeline import fused_loss_step
+            out3 = torch.empty(3, dtype=torch.float32, device=device)
+            sec["loss"] = _timed(lambda: fused_loss_step(loc, conf, tg_dev, anchors, C, "MultiBoxLoss", None, out=out3),
+                                 K, barrier)
+    launches += 3 if detect else 1
 
     t = torch.tensor([dev_ms, e2e_ms] + [sec[k] for k in sorted(sec)], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -478,10 +471,10 @@ def run_b200(args):
             rl["decode"] = roof("decode", "hbm", B * (4 * scores_img + L * pl * 56), "B*(4*scores + L*K*56) bytes")
             rl["nms"] = roof("nms", "hbm", B * (24 * L * pl + 24 * 100), "B*(24*N + 24*D) bytes, N = L*K candidates "
                              "(latency/sort-bound at N <= 1800: the fraction is not a bandwidth claim there)")
-        if "match" in sec:
-            rl["match"] = roof("match", "hbm", B * anchors_img * 20, "B*anchors*20 bytes (box_target 16 + depth 4 written; "
-                               "the one-hot class target of SURVEY's 4*(C+5) is never materialised on this path)")
-            rl["loss"] = roof("loss", "hbm", B * (4 * scores_img + 8 * anchors_img), "B*(4*scores + 8*anchors) bytes")
+        if "loss" in sec:
+            rl["loss"] = roof("loss", "hbm", B * (4 * scores_img + 8 * anchors_img),
+                              "B*(4*scores + 8*anchors) bytes: anchor match + MultiBoxLoss hard-negative mining + masks + "
+                              "normalisation of ALL levels in ONE launch (loss_step_kernel); logits read once")
         traffic, tfile = measured_conv_traffic(name)
         main_rl = dict(rl[c["dominant"]])
         main_rl.update({"kernel": "conv_igemm_kernel + conv_pair_kernel (+ dwconv3x3 etc.): all conv-stack launches of a step",

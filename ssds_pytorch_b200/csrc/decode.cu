@@ -319,7 +319,7 @@ static int validate_levels(const ssdsb_level* levels, int n_levels, int B, int t
 extern "C" size_t ssdsb_decode_workspace_bytes(const ssdsb_level* levels, int n_levels, int B,
                                                int top_n) {
   if (validate_levels(levels, n_levels, B, top_n, false) != SSDSB_OK) return 0;
-  if (top_n > DEC_MAX_K && top_n <= decode_large_max_k()) return decode_large_workspace_bytes(n_levels, B, top_n);
+  if (top_n > DEC_MAX_K && top_n <= decode_large_max_k()) return decode_large_workspace_bytes(levels, n_levels, B, top_n);
   DecodeParams p;
   fill_params(p, levels, n_levels, B, top_n);
   return ws_head_bytes(B, n_levels) + (size_t)B * n_levels * 8 + (size_t)B * p.cand_off[n_levels] * 8 + 16;

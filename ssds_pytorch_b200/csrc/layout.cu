@@ -343,15 +343,19 @@ dwconv3x3_rows_kernel(const uint2* __restrict__ x, const uint2* __restrict__ w, 
   }
   const int w0 = wo * S - 1;                       // leftmost input column of this output column
   const bool has_l = w0 >= 0, has_r = w0 + 2 < W;  // the centre column wo*S is always inside
-  const uint2* xin = x + (size_t)n * H * W * C4 + c;
-  auto load_row = [&](int h, float (&f)[3][4]) {
-    uint2 r0 = make_uint2(0u, 0u), r1 = r0, r2 = r0;
-    if (h >= 0 && h < H) {
-      const uint2* row = xin + ((size_t)h * W + w0) * C4;
-      if (has_l) r0 = __ldg(row);
-      r1 = __ldg(row + C4);
-      if (has_r) r2 = __ldg(row + 2 * C4);
-    }
+  // all addressing is pointer bumps: `rp` walks down the input rows at column w0 (it may point outside the tensor for
+  // the halo rows above / below the image: those are never dereferenced), `yp` walks down the output rows
+  const int h_first = ho0 * S - 1;
+  const long long row_stride = (long long)W * C4;
+  const uint2* rp = x + ((long long)n * H + h_first) * row_stride + (long long)w0 * C4 + c;
+  const long long out_stride = (long long)Wo * C4;
+  uint2* yp = y + ((long long)n * Ho + ho0) * out_stride + (long long)wo * C4 + c;
+  const uint2 zero2 = make_uint2(0u, 0u);
+  auto load_row = [&](int h, const uint2* p, float (&f)[3][4]) {
+    const bool v = (unsigned)h < (unsigned)H;
+    const uint2 r0 = (v && has_l) ? __ldg(p) : zero2;
+    const uint2 r1 = v ? __ldg(p + C4) : zero2;
+    const uint2 r2 = (v && has_r) ? __ldg(p + 2 * C4) : zero2;
     bf4_to_f(r0, f[0]); bf4_to_f(r1, f[1]); bf4_to_f(r2, f[2]);
   };
   auto fma_row = [&](float (&a)[4], const float (&f)[3][4], int dy) {
@@ -360,7 +364,7 @@ dwconv3x3_rows_kernel(const uint2* __restrict__ x, const uint2* __restrict__ w, 
 #pragma unroll
       for (int e = 0; e < 4; ++e) a[e] = fmaf(f[dx][e], wf[dy * 3 + dx][e], a[e]);
   };
-  auto emit = [&](int ho, float (&a)[4]) {
+  auto emit = [&](uint2* dst, const float (&a)[4]) {
     float o[4] = {a[0], a[1], a[2], a[3]};
     if (relu) {
 #pragma unroll
@@ -370,17 +374,36 @@ dwconv3x3_rows_kernel(const uint2* __restrict__ x, const uint2* __restrict__ w, 
         for (int e = 0; e < 4; ++e) o[e] = fminf(o[e], 6.0f);
       }
     }
-    y[(((size_t)n * Ho + ho) * Wo + wo) * C4 + c] = make_uint2(pack2(o[0], o[1]), pack2(o[2], o[3]));
+    *dst = make_uint2(pack2(o[0], o[1]), pack2(o[2], o[3]));
   };
+  const int rows = ho1 - ho0;
   if (S == 1) {
     // input row h feeds output rows h+1 (dy 0), h (dy 1), h-1 (dy 2): ring E (row h-1), M (row h), Nn (row h+1)
-    float E[4] = {b[0], b[1], b[2], b[3]}, M[4] = {b[0], b[1], b[2], b[3]}, Nn[4];
-#pragma unroll 3
-    for (int h = ho0 - 1; h <= ho1; ++h) {
+    float E[4], M[4] = {b[0], b[1], b[2], b[3]}, Nn[4];
+    {                                              // row ho0-1: only starts output row ho0
       float f[3][4];
-      load_row(h, f);
+      load_row(h_first, rp, f);
+      fma_row(M, f, 0);
+      rp += row_stride;
+    }
+    {                                              // row ho0: continues ho0, starts ho0+1
+      float f[3][4];
+      load_row(h_first + 1, rp, f);
+      fma_row(M, f, 1);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        E[e] = M[e];
+        M[e] = b[e];
+      }
+      fma_row(M, f, 0);
+      rp += row_stride;
+    }
+#pragma unroll 4
+    for (int r = 0; r < rows; ++r) {               // row ho0+1+r: finishes output row ho0+r
+      float f[3][4];
+      load_row(h_first + 2 + r, rp, f);
       fma_row(E, f, 2);
-      if (h - 1 >= ho0) emit(h - 1, E);            // (h - 1 < ho1 always: h <= ho1)
+      emit(yp, E);
       fma_row(M, f, 1);
 #pragma unroll
       for (int e = 0; e < 4; ++e) Nn[e] = b[e];
@@ -390,26 +413,31 @@ dwconv3x3_rows_kernel(const uint2* __restrict__ x, const uint2* __restrict__ w, 
         E[e] = M[e];
         M[e] = Nn[e];
       }
+      rp += row_stride;
+      yp += out_stride;
     }
   } else {
     // output row ho = rows 2ho-1 (dy 0), 2ho (dy 1), 2ho+1 (dy 2); row 2ho+1 is also the top row of output ho+1
     float a[4] = {b[0], b[1], b[2], b[3]};
     {
       float f[3][4];
-      load_row(2 * ho0 - 1, f);
+      load_row(h_first, rp, f);
       fma_row(a, f, 0);
+      rp += row_stride;
     }
 #pragma unroll 2
-    for (int ho = ho0; ho < ho1; ++ho) {
+    for (int r = 0; r < rows; ++r) {
       float f1[3][4], f2[3][4];
-      load_row(2 * ho, f1);
-      load_row(2 * ho + 1, f2);
+      load_row(h_first + 1 + 2 * r, rp, f1);
+      load_row(h_first + 2 + 2 * r, rp + row_stride, f2);
       fma_row(a, f1, 1);
       fma_row(a, f2, 2);
-      emit(ho, a);
+      emit(yp, a);
 #pragma unroll
       for (int e = 0; e < 4; ++e) a[e] = b[e];
       fma_row(a, f2, 0);
+      rp += 2 * row_stride;
+      yp += out_stride;
     }
   }
 }

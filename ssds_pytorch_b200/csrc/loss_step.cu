@@ -109,7 +109,7 @@ loss_step_kernel(const __grid_constant__ LsParams p) {
   __shared__ int s_flag;
   __shared__ int s_hist[2048];
   __shared__ uint32_t s_prefix;
-  __shared__ int s_remaining, s_running, s_cut;
+  __shared__ int s_remaining, s_running, s_cut, s_tie;
   __shared__ int s_warp[LS_WARPS];
 
   // ---- which (level, image, tile) ----
@@ -181,9 +181,10 @@ loss_step_kernel(const __grid_constant__ LsParams p) {
     const int cpos = is_pos ? (int)depth - 1 : -1;
     if (p.cls_kind == 0) {
       float mx = 0.0f, sum = 0.0f;      // softplus > 0, so 0 is a valid identity for the max
-      auto take = [&](float x, int cc) {
-        float ce = softplus_fast(x);
-        if (cc == cpos) ce -= x;                          // BCE(x, t=1) = softplus(x) - x
+      // every class is reduced as a negative, BCE(x, 0) = softplus(x); the one positive class of a positive anchor is
+      // corrected after the loop (BCE(x, 1) = softplus(x) - x), and a positive's max is never used (criterion.py:59)
+      auto take = [&](float x, int) {
+        const float ce = softplus_fast(x);
         mx = fmaxf(mx, ce);
         sum += ce;
       };
@@ -207,6 +208,7 @@ loss_step_kernel(const __grid_constant__ LsParams p) {
         for (int k = 0; k < 8; ++k) v[k] = nx[k];
       }
       for (; c < C; ++c) take(__ldcs(lg + (size_t)c * HW), c);
+      if (cpos >= 0 && cpos < C) sum -= __ldg(lg + (size_t)cpos * HW);   // (a label >= C matches no class plane)
       if (is_pos) {                                     // always kept; max_ce := 0 (criterion.py:59)
         cls_v = (double)sum;
         p.mce[lv.off + (size_t)b * N + i] = float_to_ordered(0.0f);
@@ -215,17 +217,47 @@ loss_step_kernel(const __grid_constant__ LsParams p) {
         p.mce[lv.off + (size_t)b * N + i] = float_to_ordered(mx);
         p.sce[lv.off + (size_t)b * N + i] = sum;
       }
+    } else if (p.gamma == 2.0f) {
+      // FocalLoss (criterion.py:95-108) with the default gamma = 2, same fast transcendental path as above:
+      // e = exp(-|x|), softplus from the polynomial, sigmoid from one reciprocal.  Every class is reduced as a
+      // negative, (1-alpha) * p^2 * softplus(x); the positive class of a positive anchor is corrected afterwards.
+      const float an = 1.0f - p.alpha;
+      float sum = 0.0f;
+      auto neg_term = [&](float x) {
+        const float e = __expf(-fabsf(x));
+        const float inv = __frcp_rn(1.0f + e);
+        const float pr = (x >= 0.0f) ? inv : e * inv;               // sigmoid(x)
+        return an * (pr * pr) * softplus_fast(x);
+      };
+      int c = 0;
+      float v[8], nx[8];
+      const int groups = C >> 3;
+      if (groups > 0) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = __ldcs(lg + (size_t)k * HW);
+      }
+      for (int gq = 0; gq < groups; ++gq, c += 8) {
+        if (gq + 1 < groups) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) nx[k] = __ldcs(lg + (size_t)(c + 8 + k) * HW);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sum += neg_term(v[k]);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = nx[k];
+      }
+      for (; c < C; ++c) sum += neg_term(__ldcs(lg + (size_t)c * HW));
+      if (cpos >= 0 && cpos < C) {
+        const float x = __ldg(lg + (size_t)cpos * HW);
+        const float e = __expf(-fabsf(x));
+        const float inv = __frcp_rn(1.0f + e);
+        const float q = (x >= 0.0f) ? e * inv : inv;                // 1 - sigmoid(x)
+        sum += p.alpha * (q * q) * (softplus_fast(x) - x) - neg_term(x);
+      }
+      cls_v = (double)sum;
     } else {
       float sum = 0.0f;
-      int c = 0;
-      for (; c + 8 <= C; c += 8) {
-        float v[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = __ldcs(lg + (size_t)(c + k) * HW);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) sum += focal_term(v[k], (c + k == cpos) ? 1.0f : 0.0f, p.alpha, p.gamma);
-      }
-      for (; c < C; ++c)
+      for (int c = 0; c < C; ++c)
         sum += focal_term(__ldcs(lg + (size_t)c * HW), (c == cpos) ? 1.0f : 0.0f, p.alpha, p.gamma);
       cls_v = (double)sum;
     }
@@ -271,19 +303,33 @@ loss_step_kernel(const __grid_constant__ LsParams p) {
         __syncthreads();
         const uint32_t prefix = s_prefix;
         const int shift = shifts[pass];
-        // warp-aggregated histogram: max-CE values of one image cluster in a handful of bins (same exponent,
-        // same top mantissa bits), which would serialise plain shared-memory atomics
-        const int n_up = (N + LS_NT - 1) / LS_NT * LS_NT;            // warp-uniform trip count
-        for (int j = tid; j < n_up; j += LS_NT) {
-          const uint32_t v = (j < N) ? __ldcg(u + j) : 0u;
-          const bool in = (j < N) && ((v & mask) == prefix);
-          const unsigned act = __ballot_sync(0xffffffffu, in);
-          if (in) {
-            const int bin = (int)((v >> shift) & (uint32_t)(nb - 1));
-            const unsigned peers = __match_any_sync(act, bin);
-            if ((int)(__ffs(peers) - 1) == (tid & 31)) atomicAdd(&s_hist[bin], __popc(peers));
+        // 8 independent L2 loads per thread in flight (this tail is latency-bound: one CTA, N up to 76 800 keys).
+        // max-CE values of one image cluster in a handful of bins (same exponent, same top mantissa bits), which
+        // would serialise per-element shared-memory atomics: each thread keeps a one-entry (bin, count) run cache.
+        int run_bin = 0, run_cnt = 0;
+        for (int base = 0; base < N; base += LS_NT * 8) {
+          uint32_t v[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int j = base + k * LS_NT + tid;
+            v[k] = (j < N) ? __ldcg(u + j) : 0u;
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int j = base + k * LS_NT + tid;
+            if (j < N && (v[k] & mask) == prefix) {
+              const int bin = (int)((v[k] >> shift) & (uint32_t)(nb - 1));
+              if (bin == run_bin) {
+                ++run_cnt;
+              } else {
+                if (run_cnt) atomicAdd(&s_hist[run_bin], run_cnt);
+                run_bin = bin;
+                run_cnt = 1;
+              }
+            }
           }
         }
+        if (run_cnt) atomicAdd(&s_hist[run_bin], run_cnt);
         __syncthreads();
         if (tid < 32) {
           // warp 0: find the bin d (from the top) where the running count reaches `rem`
@@ -312,6 +358,7 @@ loss_step_kernel(const __grid_constant__ LsParams p) {
           if (tid == 0) {
             s_remaining = rem;
             s_prefix = prefix | ((uint32_t)d << shift);
+            s_tie = s_hist[d];           // after the last pass: how many keys carry exactly the cut value
           }
         }
         mask |= (uint32_t)(nb - 1) << shift;
@@ -321,10 +368,10 @@ loss_step_kernel(const __grid_constant__ LsParams p) {
       const int r = s_remaining;       // take the first r (index order) of the keys equal to vstar
       if (tid == 0) {
         s_running = 0;
-        s_cut = -1;
-      }
+        s_cut = (s_tie == r) ? N : -1;   // every key equal to the cut value is taken: no index cut needed (the
+      }                                  // usual case: distinct floats, tie group of one)
       __syncthreads();
-      for (int base = 0; base < N; base += LS_NT) {
+      for (int base = 0; s_tie != r && base < N; base += LS_NT) {
         const int j = base + tid;
         const bool eq = (j < N) && (__ldcg(u + j) == vstar);
         const unsigned mm = __ballot_sync(0xffffffffu, eq);
@@ -347,9 +394,20 @@ loss_step_kernel(const __grid_constant__ LsParams p) {
       const uint32_t cut = (uint32_t)s_cut;
       const float* sc = p.sce + lv.off + (size_t)b * N;
       double acc = 0.0;
-      for (int j = tid; j < N; j += LS_NT) {
-        const uint32_t v = __ldcg(u + j);
-        if (v > vstar || (v == vstar && (uint32_t)j <= cut)) acc += (double)__ldcg(sc + j);
+      for (int base = 0; base < N; base += LS_NT * 8) {             // same fixed order as before, 16 loads in flight
+        uint32_t v[8];
+        float f[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int j = base + k * LS_NT + tid;
+          v[k] = (j < N) ? __ldcg(u + j) : 0u;
+          f[k] = (j < N) ? __ldcg(sc + j) : 0.0f;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int j = base + k * LS_NT + tid;
+          if (j < N && (v[k] > vstar || (v[k] == vstar && (uint32_t)j <= cut))) acc += (double)f[k];
+        }
       }
       neg_sum = block_sum(acc, s_w);
     }

@@ -279,7 +279,7 @@ extern "C" size_t ssdsb_nms_workspace_bytes(int B, int N, int ndetections) {
   (void)ndetections;
   if (B < 1 || N <= NMS_PRESEL_MIN) return 0;  // short rows: everything lives in shared memory
   // long rows: the first NMS_SEL candidates of every row come from a multi-CTA exact selection (decode_large.cu)
-  return nms_presel_bytes(B) + topk_rows_workspace_bytes(B, NMS_SEL) + 256;
+  return nms_presel_bytes(B) + topk_rows_workspace_bytes(B, N, NMS_SEL) + 256;
 }
 
 extern "C" int ssdsb_nms(const float* d_scores, const float* d_boxes, const float* d_classes,

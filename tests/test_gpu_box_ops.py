@@ -555,6 +555,10 @@ def test_decode_large_top_n_stress_geometry(B):
     loc = rng.normal(0, 0.3, (2, A * 4, H, W)).astype(np.float32)
     for top_n in (20000, 4097, 40000):
         _cmp_decode(B, O, conf, loc, stride, 0.01, top_n, anc)
+    # a random-init head on a real image: every score within 0.5 % of sigmoid(bias) = 0.01 (all 1.5 M keys share their
+    # top ~17 score bits, thousands share all 32) — the selection must resolve down to the last bit and the index
+    narrow = (1.0 / (1.0 + np.exp(-rng.normal(-4.595, 0.002, (2, A * C, H, W))))).astype(np.float32)
+    _cmp_decode(B, O, narrow, loc, stride, 0.01, 20000, anc)
 
 
 def test_decode_large_top_n_edge_cases(B, monkeypatch):

@@ -128,3 +128,56 @@ def test_plumbing_config_end_to_end_vs_reference(R, which):
     found, total = _match(s, b.astype(np.float32), c.astype(np.float32), rs, np.trunc(rb), rc)
     print(f"{which}: {found}/{total} reference detections reproduced by the bf16 engine")
     assert total > 20 and found >= 0.9 * total
+
+
+def test_checkpoint_to_map_round_trip(R, tmp_path):
+    """SURVEY 8f-2's end-to-end check: weights saved by the reference's own `save_checkpoints`
+    (ssds/core/checkpoint.py:18-34) -> `ssds_pytorch_b200.checkpoint.detector_from_checkpoint` -> detections ->
+    the reference's own `MeanAveragePrecision` (ssds/core/evaluation_metrics.py:5-142), next to the reference model +
+    Decoder scored by the same metric on the same synthetic ground truth (the reference's 12 most confident
+    detections per image play the annotated objects).  bf16 conv stack: the two mAPs must agree within 0.05."""
+    import numpy as _np
+    if not hasattr(_np, "float"):
+        _np.float = float                   # numpy >= 1.24 / 2.0 removed the aliases evaluation_metrics.py:91,123 use
+    if not hasattr(_np, "NAN"):
+        _np.NAN = _np.nan
+    from ssds.core import checkpoint as rckpt
+    from ssds.core.evaluation_metrics import MeanAveragePrecision
+    from ssds_pytorch_b200.checkpoint import detector_from_checkpoint, find_previous_checkpoint
+    model_cfg = dict(SSDS="SSD", NETS="ResNet18", IMAGE_SIZE=[192, 192], NUM_CLASSES=20,
+                     FEATURE_LAYER=[[3, 4, 5, "Conv:S"], [128, 256, 512, 256]],
+                     SIZES=[[2.0, 2.828]] * 4, ASPECT_RATIOS=[[1, 2, 0.5]] * 4)
+    model, anchors, decoder, m = R.build_reference_model(model_cfg, seed=3)
+    g = torch.Generator().manual_seed(8)
+    sd = model.state_dict()
+    for k in sd:
+        if k.endswith("running_mean"):
+            sd[k] = torch.randn(sd[k].shape, generator=g) * 0.1
+        elif k.endswith("running_var"):
+            sd[k] = torch.rand(sd[k].shape, generator=g) + 0.5
+        elif k.startswith("conf.") and k.endswith("weight"):
+            sd[k] = torch.randn(sd[k].shape, generator=g) * 0.012     # spread the scores: a non-trivial ranking
+        elif k.startswith("loc.") and k.endswith("weight"):
+            sd[k] = torch.randn(sd[k].shape, generator=g) * 0.0005    # small deltas: boxes stay inside the image
+    model.load_state_dict(sd)
+    model.eval()
+    rckpt.save_checkpoints(model, str(tmp_path), "ssd_resnet18_synth", 7)
+    cfg = {"MODEL": model_cfg, "DATASET": {"PREPROC": {"MEAN": 0, "STD": 255}}}
+    epochs, files = find_previous_checkpoint(str(tmp_path))          # the reference's checkpoint_list.txt index
+    assert epochs == [7]
+    det, report = detector_from_checkpoint(cfg, files[-1])
+    assert report["resumed"] == len(sd) and not report["unresumed"]
+    img = torch.randint(0, 256, (4, 192, 192, 3), generator=g, dtype=torch.uint8)
+    x = (img.float() / 255.0).permute(0, 3, 1, 2).contiguous()
+    with torch.no_grad():
+        rdet = decoder(*model(x), anchors)
+    s, b, c = det.detect_device(img.cuda())
+    ours = (s.cpu(), b.cpu(), c.cpu())
+    targets = [torch.cat([rdet[1][i, :12], rdet[2][i, :12, None]], 1) for i in range(4)]
+    maps = []
+    for d in (rdet, ours):
+        metric = MeanAveragePrecision(20, 0.01, 0.5)
+        metric(d, targets)
+        maps.append(metric.get_results()[0])
+    print(f"mAP (reference metric) of the reference detections {maps[0]:.4f} vs the B200 engine's {maps[1]:.4f}")
+    assert maps[0] > 0.5 and abs(maps[0] - maps[1]) <= 0.05
