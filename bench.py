@@ -91,12 +91,12 @@ def cfg_dict(name="cfg2"):
 
 
 def measured_conv_traffic(name):
-    """DRAM bytes of all conv launches of one step from the committed ncu capture, or None."""
-    for f in ("r2_conv_traffic.json", "r1_conv_traffic.json"):
+    """DRAM bytes of all conv-stack launches of one step from the committed ncu launch list of this config
+    (profiles/r2_conv_traffic_<config>.json, written by tools/conv_traffic.py), or None."""
+    for f in (f"r2_conv_traffic_{name}.json",) + (("r1_conv_traffic.json",) if name == "cfg2" else ()):
         try:
             d = json.load(open(os.path.join(ROOT, "profiles", f)))
-            if d.get("config", "cfg2") == name:
-                return d["conv_dram_bytes_per_step"], f
+            return d["conv_dram_bytes_per_step"], f
         except Exception:
             pass
     return None, None
@@ -111,21 +111,45 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    """SM clock / throttle reasons sampled DURING the timed regions (B200_PROFILING.md's clocks line).  NVML through
+    pynvml (a sample every ~10 ms: the timed regions last tenths of a second); nvidia-smi as a fallback (one sample
+    per ~0.5 s).  Only samples taken while the GPU was busy (utilisation > 0 or power above idle) count as "under load"."""
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag = index, [], False
+        self.index, self.samples, self.stop_flag, self.source = index, [], False, "nvidia-smi"
+        self.active = False          # bench code sets this True only inside timed regions
+
+    def _nvml_loop(self):
+        import pynvml as N
+        N.nvmlInit()
+        h = N.nvmlDeviceGetHandleByIndex(self.index)
+        mx = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
+        bits = [N.nvmlClocksEventReasonHwSlowdown, N.nvmlClocksEventReasonHwThermalSlowdown,
+                N.nvmlClocksEventReasonSwThermalSlowdown, N.nvmlClocksEventReasonSwPowerCap]
+        self.source = "nvml"
+        while not self.stop_flag:
+            if self.active:
+                sm = N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)
+                r = N.nvmlDeviceGetCurrentClocksEventReasons(h)
+                self.samples.append([str(sm), str(mx)] + ["Active" if r & b else "Not Active" for b in bits])
+            time.sleep(0.01)
 
     def run(self):
+        try:
+            self._nvml_loop()
+            return
+        except Exception:
+            self.source = "nvidia-smi"
         while not self.stop_flag:
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                       "--format=csv,noheader,nounits"], capture_output=True, text=True,
                                      timeout=5).stdout.strip()
-                if out:
+                if out and self.active:
                     self.samples.append([v.strip() for v in out.split(",")])
             except Exception:
                 pass
@@ -133,12 +157,12 @@ class ClockSampler(threading.Thread):
 
     def summary(self):
         sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(s) > 2 + i and s[2 + i] == "Active"
-                                                         for s in self.samples)]
+        reasons = [n for i, n in enumerate(self.NAMES) if any(len(s) > 2 + i and s[2 + i] == "Active"
+                                                              for s in self.samples)]
         mx = max([int(s[1]) for s in self.samples if s[1].isdigit()], default=None)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons,
-                "samples": len(self.samples)}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_min_mhz": sm[0] if sm else None, "sm_max_mhz": mx,
+                "reasons": reasons, "samples": len(self.samples), "source": self.source,
+                "when": "sampled inside the two timed regions (device-resident and end-to-end)"}
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
@@ -397,23 +421,27 @@ def run_b200(args):
     sampler.start()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.active = True
     e0.record()
     for _ in range(K):
         step_device()
     join()
     e1.record()
     barrier()
+    sampler.active = False
     dev_ms = e0.elapsed_time(e1)
 
     # ---- e2e: pinned host batch -> H2D -> step -> D2H, every step ----
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.active = True
     f0.record()
     for i in range(K):
         out = step_host(i)
     join()
     f1.record()
     barrier()
+    sampler.active = False
     e2e_ms = f0.elapsed_time(f1)
     sampler.stop_flag = True
     sampler.join(timeout=2)

@@ -260,3 +260,32 @@ def test_cfg2_bf16_stack_vs_fp32_reference_detections(env):
           f"median/max rel score diff {np.median(dscore):.3e}/{np.max(dscore):.3e}, "
           f"median/max box diff {np.median(dbox):.3f}/{np.max(dbox):.3f} px")
     assert total > 0 and found >= 0.8 * total
+
+
+def test_detect_host_pipelined_unpinned_batches(env):
+    """detect_host stages unpinned input through a per-slot pinned buffer; a caller that
+    pipelines batches through alternating slots WITHOUT syncing must not overwrite bytes whose H2D copy is still
+    queued.  Six different unpinned batches in flight, results vs the synchronous path, bit for bit."""
+    from ssds_pytorch_b200 import synth
+    from ssds_pytorch_b200.ssds import SSDDetector
+    nets, fl, ncls, _, image = CASES["r18"]
+    L = len(fl[0])
+    cfg = {"MODEL": {"SSDS": "SSD", "NETS": nets, "IMAGE_SIZE": image, "NUM_CLASSES": ncls,
+                     "FEATURE_LAYER": fl, "SIZES": [[2.0, 2.828]] * L, "ASPECT_RATIOS": [[1, 2, 0.5]] * L},
+           "DATASET": {"PREPROC": {"MEAN": 0, "STD": 255}}}
+    sd = synth.synthetic_state_dict(nets, fl, [6] * L, ncls, seed=11, style="test")
+    det = SSDDetector(cfg, sd)
+    g = torch.Generator().manual_seed(77)
+    batches = [torch.randint(0, 256, (8, image[0], image[1], 3), generator=g, dtype=torch.uint8).numpy() for _ in range(6)]
+    want = []
+    for x in batches:                                   # synchronous reference results
+        s, b, c = det.detect_device(torch.from_numpy(x).cuda())
+        want.append(torch.cat([s[..., None], b, c[..., None]], -1).cpu())
+    torch.cuda.synchronize()
+    outs = [torch.empty((8, 100, 6), dtype=torch.float32).pin_memory() for _ in batches]
+    for i, x in enumerate(batches):                     # no sync between calls, alternating slots
+        det.detect_host(x, out=outs[i], slot=i % 2)
+    det.join()
+    torch.cuda.synchronize()
+    for i in range(len(batches)):
+        assert torch.equal(outs[i], want[i]), f"batch {i} was corrupted in the pipelined path"
