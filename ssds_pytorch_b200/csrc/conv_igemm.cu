@@ -288,7 +288,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         } else {
           mbar_arrive(&slot_ready[slot]);
         }
-        const int nch = min(BLOCK_N, p.Cout - ta.n_tile * BLOCK_N) >> 6;
+        const int nch = (min(BLOCK_N, p.Cout - ta.n_tile * BLOCK_N) + 63) >> 6;   // last chunk may be half full
         if (++a_chunk == nch) {
           a_chunk = 0;
           if (++a_way == WAYS) {
@@ -309,7 +309,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int m0 = (group / p.n_tiles) * WAYS;
         for (int w = 0; w < WAYS; ++w) {
           const TileCoord t = tile_coord(p, m0 + w, group % p.n_tiles);
-          const int nch = min(BLOCK_N, p.Cout - t.n_tile * BLOCK_N) >> 6;
+          const int nch = (min(BLOCK_N, p.Cout - t.n_tile * BLOCK_N) + 63) >> 6;
           for (int c = 0; c < nch; ++c, ++g) {
             mbar_wait(&slot_full[sring.slot], sring.phase);
             tma_store_4d(&tmY, staging + sring.slot * STAGING_BYTES, t.n_tile * BLOCK_N + c * 64, t.w0, t.h0,
@@ -353,10 +353,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                              (uint32_t)((acc * WAYS + way) * BLOCK_N);
       if (staged) {
         // ---------- staged path: 64-column chunks through swizzled smem + TMA store ----------
-        const int nchunks = min(BLOCK_N, p.Cout - n_tile * BLOCK_N) >> 6;
+        const int nchunks = (min(BLOCK_N, p.Cout - n_tile * BLOCK_N) + 63) >> 6;
         staged_epilogue_item(t_row, nchunks, p.bias + n_tile * BLOCK_N + half * 32, staging_addr,
                              STAGING_BYTES, R, ring, slot_ready, slot_full,
-                             way == WAYS - 1 ? &tmem_empty[acc] : nullptr, has_res, p.relu, r, half, lane);
+                             way == WAYS - 1 ? &tmem_empty[acc] : nullptr, has_res, p.relu, r, half, lane,
+                             p.Cout - n_tile * BLOCK_N - half * 32);
         continue;
       }
       const TileCoord t = tile_coord(p, m0 + way, n_tile);
@@ -731,7 +732,11 @@ extern "C" int ssdsb_conv2d_bf16(const ssdsb_conv_desc* d, const void* x, const 
       return fail(SSDSB_ERR_CUDA, "conv2d: weight tensor map failed (CUresult %d)", (int)r);
   }
 
-  const bool want_staging = d->out_mode == CONV_OUT_NHWC_BF16 && (d->Cout % 64) == 0 && !chunk;
+  // staged TMA-store epilogue for every un-chunked NHWC layer (Cout % 32 == 0: a half-full last 64-column chunk is
+  // clipped by the store's tensor map); SSDSB_DIRECT_RAGGED=1 sends Cout % 64 != 0 back to per-lane 16-byte stores
+  const bool direct_ragged = getenv("SSDSB_DIRECT_RAGGED") != nullptr;        // (read per call: tests A/B it)
+  const bool want_staging = d->out_mode == CONV_OUT_NHWC_BF16 && !chunk &&
+                            ((d->Cout % 64) == 0 || !direct_ragged);
   if (want_staging) {
     cuuint64_t dims[4] = {(cuuint64_t)d->Cout, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)d->N};
     cuuint32_t box[4] = {64, (cuuint32_t)BW, (cuuint32_t)BH, (cuuint32_t)BN};

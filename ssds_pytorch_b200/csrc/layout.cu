@@ -309,10 +309,18 @@ dwconv3x3_kernel(const uint4* __restrict__ x, const uint4* __restrict__ w, const
 // Depthwise 3x3, row-streaming variant (the one ssdsb_dwconv3x3_nhwc_bf16 launches): a thread owns 4 channels of
 // one output column and walks DOWN a chunk of output rows.  Every input row it needs is loaded once (3 x 8-byte
 // loads: left / centre / right column; neighbours' loads hit L1) and feeds the three output rows it touches from
-// registers (stride 1: a 3-deep accumulator ring; stride 2: the odd row is reused as the next output's top row),
-// the 9 x 4 folded weights live in registers for the whole chunk.  3 loads per output row instead of 9 + 9, and the
-// unrolled row loop keeps >= 6 independent loads in flight per thread — the per-output variant above was bound by
-// load latency at ~1.2 TB/s.  fp32 accumulation in the same tap order (dy-major, dx-minor) for dy = 0..2 per output.
+// registers; the 9 x 4 folded weights live in registers for the whole chunk.
+//
+// The kernel is bound by load latency, not by DRAM or issue slots (r2 profiles: 1.6 TB/s at 25 % issue activity
+// when each row's loads were issued right before their use), so the loop is an explicit software pipeline: a ring
+// of PF raw input rows (3 x uint2 each) is always in flight ahead of the row being consumed, loads are predicated
+// instructions (no branches, no out-of-range addresses dereferenced) so that nothing stops the scheduler from
+// keeping them ahead, and the launch cuts the rows into as few chunks as still fill the machine (long threads, few
+// waves) instead of many short ones.
+//   stride 1: input row i feeds outputs i (dy 0), i-1 (dy 1), i-2 (dy 2): three accumulators whose roles rotate
+//             with period 3 — PF is a multiple of 3 so the rotation is static under the unroll;
+//   stride 2: output o = rows 2o-1, 2o, 2o+1; row 2o+1 is also the top row of output o+1.
+// fp32 accumulation in the same order as the per-output kernel above (bias, then dy-major / dx-minor taps).
 __device__ __forceinline__ void bf4_to_f(const uint2 v, float (&f)[4]) {
   f[0] = __uint_as_float(v.x << 16);
   f[1] = __uint_as_float(v.x & 0xffff0000u);
@@ -320,20 +328,37 @@ __device__ __forceinline__ void bf4_to_f(const uint2 v, float (&f)[4]) {
   f[3] = __uint_as_float(v.y & 0xffff0000u);
 }
 
-template <int S>
-__global__ void __launch_bounds__(256, S == 1 ? 2 : 3)
-dwconv3x3_rows_kernel(const uint2* __restrict__ x, const uint2* __restrict__ w, const float* __restrict__ bias,
-                      int N, int H, int W, int C4, int Ho, int Wo, int relu, int rows_per, int chunks,
-                      uint2* __restrict__ y) {
-  const size_t total = (size_t)N * chunks * Wo * C4;
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+// predicated 8-byte read-only load: zero when `pred` is false, and the address is then never dereferenced
+__device__ __forceinline__ uint2 ldg_pred_u2(const uint2* p, bool pred) {
+  uint2 v;
+  asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %3, 0;\n\tmov.b32 %0, 0;\n\tmov.b32 %1, 0;\n\t"
+      "@q ld.global.nc.v2.u32 {%0, %1}, [%2];\n\t}"
+      : "=r"(v.x), "=r"(v.y)
+      : "l"(p), "r"((int)pred));
+  return v;
+}
+
+struct DwRow {
+  uint2 l, m, r;
+};
+
+template <int S, int PF>
+__global__ void __launch_bounds__(256, 2)
+dwconv3x3_stream_kernel(const uint2* __restrict__ x, const uint2* __restrict__ w, const float* __restrict__ bias,
+                        int N, int H, int W, int C4, int Ho, int Wo, int relu, int rows_per, int chunks,
+                        uint2* __restrict__ y) {
+  static_assert(S == 2 || PF % 3 == 0, "stride 1: the accumulator ring has period 3");
+  const unsigned total = (unsigned)N * chunks * Wo * C4;
+  const unsigned idx = blockIdx.x * 256u + threadIdx.x;
   if (idx >= total) return;
-  const int c = (int)(idx % C4);
-  const int wo = (int)((idx / C4) % Wo);
-  const int ch = (int)((idx / ((size_t)C4 * Wo)) % chunks);
-  const int n = (int)(idx / ((size_t)C4 * Wo * chunks));
+  const int c = (int)(idx % (unsigned)C4);
+  unsigned t = idx / (unsigned)C4;
+  const int wo = (int)(t % (unsigned)Wo);
+  t /= (unsigned)Wo;
+  const int ch = (int)(t % (unsigned)chunks);
+  const int n = (int)(t / (unsigned)chunks);
   const int ho0 = ch * rows_per;
-  const int ho1 = min(Ho, ho0 + rows_per);
+  const int rows = min(Ho, ho0 + rows_per) - ho0;
   float wf[9][4], b[4];
 #pragma unroll
   for (int k = 0; k < 9; ++k) bf4_to_f(__ldg(w + (size_t)k * C4 + c), wf[k]);
@@ -341,22 +366,24 @@ dwconv3x3_rows_kernel(const uint2* __restrict__ x, const uint2* __restrict__ w, 
     const float4 bv = __ldg(reinterpret_cast<const float4*>(bias) + c);
     b[0] = bv.x; b[1] = bv.y; b[2] = bv.z; b[3] = bv.w;
   }
+  const float lo = relu ? 0.0f : -INFINITY, hi = (relu == 2) ? 6.0f : INFINITY;
   const int w0 = wo * S - 1;                       // leftmost input column of this output column
   const bool has_l = w0 >= 0, has_r = w0 + 2 < W;  // the centre column wo*S is always inside
-  // all addressing is pointer bumps: `rp` walks down the input rows at column w0 (it may point outside the tensor for
-  // the halo rows above / below the image: those are never dereferenced), `yp` walks down the output rows
-  const int h_first = ho0 * S - 1;
+  const int h_first = ho0 * S - 1;                 // first input row this thread streams (may be -1)
+  const int n_in = (S == 1) ? rows + 2 : 2 * rows + 1;
   const long long row_stride = (long long)W * C4;
-  const uint2* rp = x + ((long long)n * H + h_first) * row_stride + (long long)w0 * C4 + c;
-  const long long out_stride = (long long)Wo * C4;
-  uint2* yp = y + ((long long)n * Ho + ho0) * out_stride + (long long)wo * C4 + c;
-  const uint2 zero2 = make_uint2(0u, 0u);
-  auto load_row = [&](int h, const uint2* p, float (&f)[3][4]) {
-    const bool v = (unsigned)h < (unsigned)H;
-    const uint2 r0 = (v && has_l) ? __ldg(p) : zero2;
-    const uint2 r1 = v ? __ldg(p + C4) : zero2;
-    const uint2 r2 = (v && has_r) ? __ldg(p + 2 * C4) : zero2;
-    bf4_to_f(r0, f[0]); bf4_to_f(r1, f[1]); bf4_to_f(r2, f[2]);
+  // `lp` walks down the input rows at column w0 (it may point outside the tensor: then the load is predicated off)
+  const uint2* lp = x + ((long long)n * H + h_first) * row_stride + (long long)w0 * C4 + c;
+  int li = 0;                                      // index (0 .. n_in) of the next row to load
+  auto load_next = [&]() -> DwRow {
+    const bool v = (li < n_in) && ((unsigned)(h_first + li) < (unsigned)H);
+    DwRow r;
+    r.l = ldg_pred_u2(lp, v && has_l);
+    r.m = ldg_pred_u2(lp + C4, v);
+    r.r = ldg_pred_u2(lp + 2 * C4, v && has_r);
+    lp += row_stride;
+    ++li;
+    return r;
   };
   auto fma_row = [&](float (&a)[4], const float (&f)[3][4], int dy) {
 #pragma unroll
@@ -364,82 +391,98 @@ dwconv3x3_rows_kernel(const uint2* __restrict__ x, const uint2* __restrict__ w, 
 #pragma unroll
       for (int e = 0; e < 4; ++e) a[e] = fmaf(f[dx][e], wf[dy * 3 + dx][e], a[e]);
   };
-  auto emit = [&](uint2* dst, const float (&a)[4]) {
-    float o[4] = {a[0], a[1], a[2], a[3]};
-    if (relu) {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) o[e] = fmaxf(o[e], 0.0f);
-      if (relu == 2) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) o[e] = fminf(o[e], 6.0f);
-      }
-    }
-    *dst = make_uint2(pack2(o[0], o[1]), pack2(o[2], o[3]));
+  auto unpack = [&](const DwRow& r, float (&f)[3][4]) {
+    bf4_to_f(r.l, f[0]); bf4_to_f(r.m, f[1]); bf4_to_f(r.r, f[2]);
   };
-  const int rows = ho1 - ho0;
+  uint2* yp = y + ((long long)n * Ho + ho0) * ((long long)Wo * C4) + (long long)wo * C4 + c;
+  const long long out_stride = (long long)Wo * C4;
+  auto emit = [&](const float (&a)[4]) {
+    float o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o[e] = fminf(fmaxf(a[e], lo), hi);
+    *yp = make_uint2(pack2(o[0], o[1]), pack2(o[2], o[3]));
+    yp += out_stride;
+  };
+
   if (S == 1) {
-    // input row h feeds output rows h+1 (dy 0), h (dy 1), h-1 (dy 2): ring E (row h-1), M (row h), Nn (row h+1)
-    float E[4], M[4] = {b[0], b[1], b[2], b[3]}, Nn[4];
-    {                                              // row ho0-1: only starts output row ho0
-      float f[3][4];
-      load_row(h_first, rp, f);
-      fma_row(M, f, 0);
-      rp += row_stride;
-    }
-    {                                              // row ho0: continues ho0, starts ho0+1
-      float f[3][4];
-      load_row(h_first + 1, rp, f);
-      fma_row(M, f, 1);
+    DwRow ring[PF];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        E[e] = M[e];
-        M[e] = b[e];
+    for (int j = 0; j < PF; ++j) ring[j] = load_next();
+    float acc[3][4];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[a][e] = b[e];
+    for (int i0 = 0; i0 < n_in; i0 += PF) {
+#pragma unroll
+      for (int j = 0; j < PF; ++j) {
+        const int i = i0 + j;                       // input row h_first + i
+        float f[3][4];
+        unpack(ring[j], f);
+        ring[j] = load_next();                      // row i + PF
+        // rows outside [0, n_in) were loaded as zeros; outputs outside [0, rows) are accumulated but never emitted
+        fma_row(acc[j % 3], f, 0);                  // starts output i
+        fma_row(acc[(j + 2) % 3], f, 1);            // continues output i-1
+        fma_row(acc[(j + 1) % 3], f, 2);            // finishes output i-2
+        if (i >= 2 && i < n_in) emit(acc[(j + 1) % 3]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[(j + 1) % 3][e] = b[e];
       }
-      fma_row(M, f, 0);
-      rp += row_stride;
-    }
-#pragma unroll 4
-    for (int r = 0; r < rows; ++r) {               // row ho0+1+r: finishes output row ho0+r
-      float f[3][4];
-      load_row(h_first + 2 + r, rp, f);
-      fma_row(E, f, 2);
-      emit(yp, E);
-      fma_row(M, f, 1);
-#pragma unroll
-      for (int e = 0; e < 4; ++e) Nn[e] = b[e];
-      fma_row(Nn, f, 0);
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        E[e] = M[e];
-        M[e] = Nn[e];
-      }
-      rp += row_stride;
-      yp += out_stride;
     }
   } else {
-    // output row ho = rows 2ho-1 (dy 0), 2ho (dy 1), 2ho+1 (dy 2); row 2ho+1 is also the top row of output ho+1
     float a[4] = {b[0], b[1], b[2], b[3]};
     {
       float f[3][4];
-      load_row(h_first, rp, f);
+      const DwRow r0 = load_next();                 // row 2*ho0 - 1: the top row of the first output
+      unpack(r0, f);
       fma_row(a, f, 0);
-      rp += row_stride;
     }
-#pragma unroll 2
-    for (int r = 0; r < rows; ++r) {
-      float f1[3][4], f2[3][4];
-      load_row(h_first + 1 + 2 * r, rp, f1);
-      load_row(h_first + 2 + 2 * r, rp + row_stride, f2);
-      fma_row(a, f1, 1);
-      fma_row(a, f2, 2);
-      emit(yp, a);
+    DwRow ring[2 * PF];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) a[e] = b[e];
-      fma_row(a, f2, 0);
-      rp += 2 * row_stride;
-      yp += out_stride;
+    for (int j = 0; j < 2 * PF; ++j) ring[j] = load_next();
+    for (int o0 = 0; o0 < rows; o0 += PF) {
+#pragma unroll
+      for (int j = 0; j < PF; ++j) {
+        float f1[3][4], f2[3][4];
+        unpack(ring[2 * j], f1);
+        unpack(ring[2 * j + 1], f2);
+        ring[2 * j] = load_next();
+        ring[2 * j + 1] = load_next();
+        fma_row(a, f1, 1);
+        fma_row(a, f2, 2);
+        if (o0 + j < rows) emit(a);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) a[e] = b[e];
+        fma_row(a, f2, 0);
+      }
     }
   }
+}
+
+// how the launch cuts Ho output rows into chunks: as few as fill the machine evenly (a thread's 2 halo rows and its
+// 36 weight loads are per chunk; waves of 148 x 512 threads should be close to whole)
+inline void dw_pick_chunks(long long base_threads, int Ho, int sms, int* rows_per, int* chunks) {
+  const double wave = (double)sms * 512.0;
+  double best = -1.0;
+  int best_rp = Ho;
+  const int min_rows = Ho < 4 ? Ho : 4;
+  for (int c = 1; c <= 32; ++c) {
+    const int rp = (Ho + c - 1) / c;
+    if (rp < min_rows) break;
+    if (rp > 48 && c < 32) continue;                        // bound the length of one thread
+    const int cc = (Ho + rp - 1) / rp;
+    const double waves = (double)base_threads * cc / wave;
+    const double full = waves <= 1.0 ? waves : waves / (double)(long long)(waves + 0.999999);
+    // few waves cannot hide their ramp-up / tail: prefer >= 4
+    const double depth = waves >= 4.0 ? 1.0 : 0.85 + 0.15 * waves / 4.0;
+    const double score = full * depth * ((double)rp / (rp + 1.0));
+    if (score > best + 1e-9) {
+      best = score;
+      best_rp = rp;
+    }
+  }
+  *rows_per = best_rp;
+  *chunks = (Ho + best_rp - 1) / best_rp;
 }
 
 }  // namespace
@@ -487,22 +530,43 @@ extern "C" int ssdsb_dwconv3x3_nhwc_bf16(const void* d_x, const void* d_w, const
         reinterpret_cast<const uint4*>(d_x), reinterpret_cast<const uint4*>(d_w), d_bias, N, H, W, C / 8,
         stride, Ho, Wo, relu, reinterpret_cast<uint4*>(d_y));
   } else {
-    // rows per thread: as long as possible (2 halo rows are re-read per chunk) while >= ~2 waves of threads remain
-    const size_t items = (size_t)N * Ho * Wo * (C / 4);
-    int rows_per = 16;
-    while (rows_per > 2 && items / rows_per < (size_t)148 * 2048 * 2) rows_per >>= 1;
-    if (rows_per > Ho) rows_per = Ho;
-    const int chunks = (Ho + rows_per - 1) / rows_per;
-    const size_t total = (size_t)N * chunks * Wo * (C / 4);
+    static int sms = 0;
+    if (!sms) {
+      int dev = 0;
+      SSDSB_CUDA(cudaGetDevice(&dev));
+      SSDSB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    int rows_per = 0, chunks = 0;
+    dw_pick_chunks((long long)N * Wo * (C / 4), Ho, sms, &rows_per, &chunks);
+    if (const char* e = getenv("SSDSB_DW_ROWS")) {          // experiment knob (profiling only)
+      const int v = atoi(e);
+      if (v >= 1) {
+        rows_per = v < Ho ? v : Ho;
+        chunks = (Ho + rows_per - 1) / rows_per;
+      }
+    }
+    const long long total = (long long)N * chunks * Wo * (C / 4);
+    SSDSB_REQUIRE(total < (1ll << 31), "dwconv3x3: tensor too large for 32-bit thread indexing");
     const unsigned blocks = (unsigned)((total + 255) / 256);
-    if (stride == 1)
-      dwconv3x3_rows_kernel<1><<<blocks, 256, 0, st>>>(reinterpret_cast<const uint2*>(d_x),
-          reinterpret_cast<const uint2*>(d_w), d_bias, N, H, W, C / 4, Ho, Wo, relu, rows_per, chunks,
-          reinterpret_cast<uint2*>(d_y));
-    else
-      dwconv3x3_rows_kernel<2><<<blocks, 256, 0, st>>>(reinterpret_cast<const uint2*>(d_x),
-          reinterpret_cast<const uint2*>(d_w), d_bias, N, H, W, C / 4, Ho, Wo, relu, rows_per, chunks,
-          reinterpret_cast<uint2*>(d_y));
+    static const int deep = getenv("SSDSB_DW_SHALLOW") ? 0 : 1;   // A/B: prefetch ring 6 vs 3 rows (s1), 3 vs 2 (s2)
+    const uint2* xx = reinterpret_cast<const uint2*>(d_x);
+    const uint2* ww = reinterpret_cast<const uint2*>(d_w);
+    uint2* yy = reinterpret_cast<uint2*>(d_y);
+    if (stride == 1) {
+      if (deep)
+        dwconv3x3_stream_kernel<1, 6><<<blocks, 256, 0, st>>>(xx, ww, d_bias, N, H, W, C / 4, Ho, Wo, relu, rows_per,
+                                                              chunks, yy);
+      else
+        dwconv3x3_stream_kernel<1, 3><<<blocks, 256, 0, st>>>(xx, ww, d_bias, N, H, W, C / 4, Ho, Wo, relu, rows_per,
+                                                              chunks, yy);
+    } else {
+      if (deep)
+        dwconv3x3_stream_kernel<2, 3><<<blocks, 256, 0, st>>>(xx, ww, d_bias, N, H, W, C / 4, Ho, Wo, relu, rows_per,
+                                                              chunks, yy);
+      else
+        dwconv3x3_stream_kernel<2, 2><<<blocks, 256, 0, st>>>(xx, ww, d_bias, N, H, W, C / 4, Ho, Wo, relu, rows_per,
+                                                              chunks, yy);
+    }
   }
   SSDSB_LAUNCH_CHECK("dwconv3x3_kernel");
   return SSDSB_OK;

@@ -231,14 +231,17 @@ __device__ __forceinline__ void staged_epilogue_item_t(uint32_t t_row, int nchun
                                                        uint32_t staging_addr, int slot_bytes, int R,
                                                        SlotRing& ring, uint64_t* slot_ready,
                                                        uint64_t* slot_full, uint64_t* tmem_empty_bar,
-                                                       int relu, int r, int half, int lane) {
+                                                       int relu, int r, int half, int lane, int ncols) {
+  // `ncols`: how many output channels exist from this warp's first column on (Cout need only be a multiple of 32:
+  // the last 64-column chunk may be half empty — its upper-half warps run on zero accumulators (TMA zero-filled the
+  // missing weight rows) with a zero bias, and the TMA store clips those columns at the tensor edge).
   // ReLU / ReLU6 as one clamp: no branches inside the element loops
   const float hi = (relu == 2) ? 6.0f : __int_as_float(0x7f800000);
   uint32_t v[32];
   float4 bv[8];
   tmem_ld32(t_row + (uint32_t)(half * 32), v);
 #pragma unroll
-  for (int e = 0; e < 8; ++e) bv[e] = ldg_nc_f4(bias_half + e * 4);
+  for (int e = 0; e < 8; ++e) bv[e] = ncols > 0 ? ldg_nc_f4(bias_half + e * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
   for (int c = 0; c < nchunks; ++c) {
     tmem_ld_wait_dep(v);
     float f[32];
@@ -252,7 +255,8 @@ __device__ __forceinline__ void staged_epilogue_item_t(uint32_t t_row, int nchun
     if (c + 1 < nchunks) {               // next chunk's accumulator columns and bias: in flight from here on
       tmem_ld32(t_row + (uint32_t)((c + 1) * 64 + half * 32), v);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) bv[e] = ldg_nc_f4(bias_half + (c + 1) * 64 + e * 4);
+      for (int e = 0; e < 8; ++e)
+        bv[e] = (c + 1) * 64 < ncols ? ldg_nc_f4(bias_half + (c + 1) * 64 + e * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
     } else if (tmem_empty_bar) {         // (null: more tiles of this accumulator group follow)
       tcgen05_fence_before();            // accumulator fully read: the MMA warp may overwrite it
       __syncwarp();
@@ -301,13 +305,13 @@ __device__ __forceinline__ void staged_epilogue_item(uint32_t t_row, int nchunks
                                                      uint32_t staging_addr, int slot_bytes, int R,
                                                      SlotRing& ring, uint64_t* slot_ready, uint64_t* slot_full,
                                                      uint64_t* tmem_empty_bar, bool has_res, int relu, int r,
-                                                     int half, int lane) {
+                                                     int half, int lane, int ncols = 1 << 30) {
   if (has_res)
     staged_epilogue_item_t<true>(t_row, nchunks, bias_half, staging_addr, slot_bytes, R, ring, slot_ready,
-                                 slot_full, tmem_empty_bar, relu, r, half, lane);
+                                 slot_full, tmem_empty_bar, relu, r, half, lane, ncols);
   else
     staged_epilogue_item_t<false>(t_row, nchunks, bias_half, staging_addr, slot_bytes, R, ring, slot_ready,
-                                  slot_full, tmem_empty_bar, relu, r, half, lane);
+                                  slot_full, tmem_empty_bar, relu, r, half, lane, ncols);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -160,6 +160,77 @@ def test_dwconv3x3(K, case):
     assert y.shape == ref.shape and err.max().item() <= 1e-2, err.max().item()
 
 
+RAGGED = [
+    # N, H, W, Cin, Cout, k, stride, relu, residual — Cout % 64 == 32: the last 64-column chunk of the staged
+    # TMA-store epilogue is half full (clipped by the store's tensor map)
+    (2, 75, 75, 32, 160, 1, 1, 2, False),     # MobileNetV2 expand 24(32) -> 144(160), 1 n-tile of 256, 3 chunks
+    (2, 75, 75, 160, 32, 1, 1, 0, True),      # project + residual, 4-way BLOCK_N = 64 with half a chunk per tile
+    (3, 38, 38, 192, 32, 1, 1, 0, False),
+    (2, 19, 19, 384, 96, 1, 1, 0, True),      # BLOCK_N = 128, 2 chunks, residual TMA load clipped too
+    (2, 20, 20, 96, 288, 3, 1, 1, False),     # two n-tiles: 256 + 32
+    (1, 40, 24, 64, 480, 1, 2, 1, True),      # RegNet width 432 padded to 480, stride 2 + residual
+    (5, 3, 3, 64, 96, 3, 1, 2, False),        # tiny map, several images per tile
+]
+
+
+@pytest.mark.parametrize("case", RAGGED)
+def test_conv_ragged_cout_staged_equals_direct(K, case, monkeypatch):
+    """[r2] Cout % 64 != 0 layers now take the staged epilogue (full-line TMA stores) instead of per-lane 16-byte
+    stores: same arithmetic, so the two paths must agree bit for bit — and with the torch reference within the
+    file's tolerance.  The output is a channel slice of a wider buffer (concat-style stride): the clipped TMA store
+    must not touch the neighbouring channels."""
+    N, H, W, Cin, Cout, k, stride, relu, use_res = case
+    pad = k // 2
+    g = torch.Generator().manual_seed(Cout * 7 + Cin)
+    x = torch.randn((N, H, W, Cin), generator=g).to(torch.bfloat16).cuda()
+    w = torch.randn((Cout, Cin, k, k), generator=g) * (1.0 / np.sqrt(Cin * k * k))
+    b = (torch.randn((Cout,), generator=g) * 0.2).cuda()
+    ho, wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    res = torch.randn((N, ho, wo, Cout), generator=g).to(torch.bfloat16).cuda() if use_res else None
+    wp = K.pack_weight(w).cuda()
+    outs = []
+    for direct in (False, True):
+        if direct:
+            monkeypatch.setenv("SSDSB_DIRECT_RAGGED", "1")
+        else:
+            monkeypatch.delenv("SSDSB_DIRECT_RAGGED", raising=False)
+        wide = torch.full((N, ho, wo, Cout + 32), 7.0, dtype=torch.bfloat16, device="cuda")
+        y = K.conv2d(x, wp, b, k, k, stride, pad, relu, residual=res, out=wide[..., :Cout])
+        torch.cuda.synchronize()
+        assert torch.all(wide[..., Cout:] == 7.0), "store touched the neighbouring channels"
+        outs.append(y.clone())
+    monkeypatch.delenv("SSDSB_DIRECT_RAGGED", raising=False)
+    assert torch.equal(outs[0], outs[1])
+    ref = ref_conv(x, w.cuda(), b, stride, pad, relu, res)
+    err = (outs[0].float() - ref).abs() / ref.abs().clamp(min=1.0)
+    assert err.max().item() <= 2e-2, err.max().item()
+
+
+@pytest.mark.parametrize("case", [(2, 75, 75, 160, 1, 2), (1, 150, 150, 96, 2, 2), (2, 19, 19, 384, 1, 2),
+                                  (3, 10, 10, 960, 1, 2), (2, 21, 13, 64, 2, 1), (1, 7, 9, 32, 1, 0)])
+def test_dwconv3x3_stream_any_chunking(K, case, monkeypatch):
+    """[r2] the software-pipelined row-streaming depthwise kernel is bit-identical to the per-output kernel
+    (same fp32 tap order) however the launch cuts the rows into chunks: the heuristic's own choice, 1-row chunks,
+    chunks shorter / longer than the prefetch ring, one chunk for the whole map."""
+    N, H, W, Cc, stride, relu = case
+    g = torch.Generator().manual_seed(sum(case) + 1)
+    x = torch.randn((N, H, W, Cc), generator=g).to(torch.bfloat16).cuda()
+    w = K.pack_dw_weight(torch.randn((Cc, 1, 3, 3), generator=g) * 0.3).cuda()
+    b = (torch.randn((Cc,), generator=g) * 0.2).cuda()
+    monkeypatch.setenv("SSDSB_DW_SIMPLE", "1")
+    want = K.dwconv3x3(x, w, b, stride, relu).clone()
+    monkeypatch.delenv("SSDSB_DW_SIMPLE")
+    for rows in (None, 1, 2, 3, 5, 7, 11, 1000):
+        if rows is None:
+            monkeypatch.delenv("SSDSB_DW_ROWS", raising=False)
+        else:
+            monkeypatch.setenv("SSDSB_DW_ROWS", str(rows))
+        got = K.dwconv3x3(x, w, b, stride, relu)
+        torch.cuda.synchronize()
+        assert torch.equal(got, want), (case, rows)
+    monkeypatch.delenv("SSDSB_DW_ROWS", raising=False)
+
+
 @pytest.mark.parametrize("case", [(2, 20, 20, 432, 1), (2, 20, 20, 192, 2), (1, 40, 24, 96, 1), (3, 10, 10, 1008, 1)])
 def test_grouped_conv_regnet(K, case):
     """RegNet 3x3 grouped conv (group width 48; regnet.py:69) as a block-diagonal chunked igemm:

@@ -110,12 +110,33 @@ def run_nms(dec_small=None, dec_large=None):
 
 def run_dw():
     g = torch.Generator(device="cuda").manual_seed(4)
-    for (h, c, stride) in [(150, 96, 2), (75, 160, 1), (75, 160, 2), (38, 192, 1), (38, 192, 2), (19, 384, 1), (19, 576, 1),
-                           (19, 576, 2), (10, 960, 1)]:
+    for (h, c, stride) in [(150, 32, 1), (150, 96, 2), (75, 160, 1), (75, 160, 2), (38, 192, 1), (38, 192, 2),
+                           (19, 384, 1), (19, 576, 1), (19, 576, 2), (10, 960, 1)]:
         x = torch.randn((64, h, h, c), generator=g, device="cuda").to(torch.bfloat16)
         w = K.pack_dw_weight(torch.randn((c, 1, 3, 3)) * 0.3).cuda()
         b = torch.zeros(c, device="cuda")
-        timed(f"dwconv3x3 s{stride} {c} @{h}", lambda: K.dwconv3x3(x, w, b, stride, 2))
+        ho = (h - 1) // stride + 1
+        mb = 64 * (h * h + ho * ho) * c * 2 / 1e6
+        timed(f"dwconv3x3 s{stride} {c} @{h} ({mb:.0f} MB)", lambda: K.dwconv3x3(x, w, b, stride, 2))
+
+
+def run_pw():
+    """the 1x1 convs of MobileNetV2-SSD 300x300, B=64 (channels padded to 32 as the plan stores them)"""
+    g = torch.Generator(device="cuda").manual_seed(6)
+    for (h, cin, cout, relu, res) in [(150, 32, 32, 0, False), (150, 32, 96, 2, False), (75, 96, 32, 0, False),
+                                      (75, 32, 160, 2, False), (75, 160, 32, 0, True), (38, 160, 32, 0, False),
+                                      (38, 32, 192, 2, False), (38, 192, 32, 0, True), (19, 192, 64, 0, False),
+                                      (19, 64, 384, 2, False), (19, 384, 64, 0, True), (19, 384, 96, 0, False),
+                                      (19, 96, 576, 2, False), (19, 576, 96, 0, True), (10, 576, 160, 0, False),
+                                      (10, 160, 960, 2, False), (10, 960, 160, 0, True), (10, 960, 320, 0, False)]:
+        x = torch.randn((64, h, h, cin), generator=g, device="cuda").to(torch.bfloat16)
+        w = K.pack_weight(torch.randn((cout, cin, 1, 1)) * (1.0 / np.sqrt(cin))).cuda()
+        b = torch.zeros(cout, device="cuda")
+        r = torch.randn((64, h, h, cout), generator=g, device="cuda").to(torch.bfloat16) if res else None
+        out = torch.empty((64, h, h, cout), dtype=torch.bfloat16, device="cuda")
+        mb = 64 * h * h * (cin + cout * (2 if res else 1)) * 2 / 1e6
+        timed(f"conv1x1 {cin}->{cout} @{h}{' +res' if res else ''} ({mb:.0f} MB)",
+              lambda: K.conv2d(x, w, b, 1, 1, 1, 0, relu, residual=r, out=out))
 
 
 def run_layout():
@@ -134,7 +155,7 @@ def run_layout():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["loss", "match", "decode", "decode_large", "nms", "dw", "layout"]
+    which = sys.argv[1:] or ["loss", "match", "decode", "decode_large", "nms", "dw", "pw", "layout"]
     small = large = None
     for w in which:
         if w == "loss":
@@ -149,5 +170,7 @@ if __name__ == "__main__":
             run_nms(small, large)
         elif w == "dw":
             run_dw()
+        elif w == "pw":
+            run_pw()
         elif w == "layout":
             run_layout()
