@@ -280,24 +280,26 @@ def _timed(fn, K, barrier):
 
 
 def _self_check(name, sd, dev_in, plan_outputs, make_model):
-    """Bit-exact comparison of the timed plan's outputs with the 1-way, unpaired, eagerly replayed plan."""
+    """Bit-exact comparison of the timed plan's outputs with the 1-way, unpaired, un-fused (three launches per
+    inverted residual), eagerly replayed plan."""
     import torch
-    os.environ["SSDSB_WAYS"], os.environ["SSDSB_NO_PAIR"] = "1", "1"
+    os.environ["SSDSB_WAYS"], os.environ["SSDSB_NO_PAIR"], os.environ["SSDSB_NO_MBFUSE"] = "1", "1", "1"
     try:
         plain = make_model()
         loc, conf = plain(dev_in, use_graph=False)
         torch.cuda.synchronize()
-        n_pair = sum(v["kind"].startswith("pair1x1") for v in plain.plan_for(dev_in)["info"].values())
+        n_pair = sum(v["kind"].startswith(("pair1x1", "mbconv")) for v in plain.plan_for(dev_in)["info"].values())
         assert n_pair == 0
         for a, b in zip(plan_outputs, list(loc) + list(conf)):
             if not torch.equal(a, b):
                 raise SystemExit(f"bench self-check FAILED ({name}): timed plan output differs from the 1-way "
                                  f"unpaired eager plan (max |diff| {(a - b).abs().max().item()})")
     finally:
-        del os.environ["SSDSB_WAYS"], os.environ["SSDSB_NO_PAIR"]
+        del os.environ["SSDSB_WAYS"], os.environ["SSDSB_NO_PAIR"], os.environ["SSDSB_NO_MBFUSE"]
     del plain
     torch.cuda.empty_cache()
-    return "timed plan (multi-way/resident/paired launches, CUDA-graph replay) == 1-way unpaired eager plan, bit for bit"
+    return ("timed plan (multi-way/resident/paired/fused-block launches, CUDA-graph replay) == 1-way unpaired "
+            "un-fused eager plan, bit for bit")
 
 
 def run_b200(args):

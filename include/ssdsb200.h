@@ -45,7 +45,7 @@ typedef enum {
 
 #define SSDSB_MAX_LEVELS 8
 
-#define SSDSB_ABI_VERSION 200
+#define SSDSB_ABI_VERSION 201
 
 SSDSB_API int ssdsb_version(void);          /* == SSDSB_ABI_VERSION of the header the library was built from */
 
@@ -290,6 +290,35 @@ SSDSB_API int ssdsb_conv1x1_pair_bf16(int N, int H, int W, int Cin, int Cmid, in
                                       const void* d_x, const void* d_w1, const float* d_bias1,
                                       const void* d_residual, void* d_y1, const void* d_w2,
                                       const float* d_bias2, void* d_y2, void* stream);
+
+/* Fused MobileNetV2 inverted residual (conv_mbconv.cu; reference ssds/modeling/nets/mobilenet.py:40-76, the
+ * torchvision InvertedResidual it builds its backbone from):
+ *   h = act_e(conv1x1(x, w_exp) + b_exp)            [skipped when d_w_exp == NULL: h = x, hid == Cin]
+ *   g = act_d(depthwise3x3(h, w_dw, stride, pad 1) + b_dw)
+ *   y = act_p(conv1x1(g, w_proj) + b_proj) [+ x]
+ * in ONE launch: the hid-channel tensors h and g only ever exist tile by tile in shared memory / TMEM.
+ * x [N,H,W,Cin], y [N,Ho,Wo,Cout] NHWC bf16 (Ho = (H-1)/stride + 1); w_exp [w_exp_rows >= hid, Cin],
+ * w_proj [w_proj_rows >= Cout, hid] bf16 K-major (BN folded), w_dw [9, hid] bf16 (ssdsb_dwconv3x3 layout),
+ * biases fp32.  Channel counts are multiples of 32, Cout <= 256 (SSDSB_ERR_UNSUPPORTED otherwise: use the three
+ * separate launches).  Results are bit-identical to ssdsb_conv2d_bf16 -> ssdsb_dwconv3x3_nhwc_bf16 ->
+ * ssdsb_conv2d_bf16 (same bf16 rounding points, same fp32 accumulation order). */
+typedef struct {
+  int N, H, W;
+  int Cin, hid, Cout;
+  int stride;       /* of the depthwise conv: 1 | 2 */
+  int residual;     /* 1: y += x (needs stride 1 and Cin == Cout) */
+  int relu_expand, relu_dw, relu_project; /* 0 none, 1 ReLU, 2 ReLU6 */
+  int w_exp_rows, w_proj_rows;
+  int out_cstride;  /* channel stride of y in elements; 0 => Cout */
+} ssdsb_mbconv_desc;
+
+SSDSB_API int ssdsb_mbconv_bf16(const ssdsb_mbconv_desc* desc, const void* d_x, const void* d_w_exp,
+                                const float* d_b_exp, const void* d_w_dw, const float* d_b_dw,
+                                const void* d_w_proj, const float* d_b_proj, void* d_y, void* stream);
+/* Introspection for tests / tools: what the calling thread's last ssdsb_mbconv_bf16 launched:
+ * {hidden chunk, tile W, tile H, expand M tiles per chunk, chunks per tile, x buffers, staging slots,
+ *  depthwise row segments, rows per segment, grid, dynamic shared memory bytes, project accumulator columns}. */
+SSDSB_API int ssdsb_mbconv_last_launch(int* out12);
 
 /* Image pre-processing fused with the layout change the stem needs (SSDDetector.__call__,
  * ssds/ssds.py:48-57: HWC->CHW, (x - mean)/std): packs an image batch into the 2x2

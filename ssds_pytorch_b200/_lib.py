@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libssdsb200.so")
 
 SSDSB_MAX_LEVELS = 8
-ABI_VERSION = 200        # == ssdsb_version(); bumped whenever include/ssdsb200.h changes incompatibly
+ABI_VERSION = 201        # == ssdsb_version(); bumped whenever include/ssdsb200.h changes incompatibly
 
 
 class Level(C.Structure):
@@ -36,6 +36,13 @@ class ConvDesc(C.Structure):
         "N", "H", "W", "Cin", "Cout", "KH", "KW", "stride", "pad", "Ho", "Wo",
         "x_cstride", "out_cstride", "res_cstride", "x_row_pixels", "chunk", "x_kind", "w_rows", "relu", "out_mode", "n_loc",
         "sigmoid")]
+
+
+class MbconvDesc(C.Structure):
+    """mirror of `ssdsb_mbconv_desc` (include/ssdsb200.h)."""
+    _fields_ = [(n, C.c_int) for n in (
+        "N", "H", "W", "Cin", "hid", "Cout", "stride", "residual", "relu_expand", "relu_dw", "relu_project",
+        "w_exp_rows", "w_proj_rows", "out_cstride")]
 
 
 def _load():
@@ -92,6 +99,8 @@ def _load():
         "ssdsb_detection_loss": (i, [llp, i, i, vp, i, f, f, i, i, f, f, i, f, vp, vp, vp, vp, vp, sz, vp]),
         "ssdsb_conv1x1_pair_bf16": (i, [i, i, i, i, i, i, i, i, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
         "ssdsb_conv_last_launch": (i, [C.POINTER(C.c_int)]),
+        "ssdsb_mbconv_bf16": (i, [C.POINTER(MbconvDesc), vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+        "ssdsb_mbconv_last_launch": (i, [C.POINTER(C.c_int)]),
         "ssdsb_conv2d_bf16": (i, [C.POINTER(ConvDesc), vp, vp, vp, vp, vp, vp, vp]),
         "ssdsb_pack_image_s2d": (i, [vp, i, i, i, i, f, f, i, i, vp, vp]),
         "ssdsb_maxpool3x3s2_nhwc_bf16": (i, [vp, i, i, i, i, vp, vp]),

@@ -217,6 +217,37 @@ def dwconv3x3(x, w, bias, stride=1, relu=2, out=None):
     return out
 
 
+def mbconv(x, w_exp, b_exp, w_dw, b_dw, w_proj, b_proj, stride=1, residual=False, relu=(2, 2, 0), out=None):
+    """Fused MobileNetV2 inverted residual in one launch (ssdsb_mbconv_bf16):
+    [1x1 expand + act] -> depthwise 3x3 (stride) + act -> 1x1 project [+ x].  x NHWC bf16 [N,H,W,Cin];
+    w_exp bf16 [hid, 1, Cin] (pack_weight) or None (no expand layer: hid == Cin), w_dw bf16 [9, hid]
+    (pack_dw_weight), w_proj bf16 [Cout, 1, hid].  Bit-identical to conv2d -> dwconv3x3 -> conv2d.
+    Raises NotImplementedError where the kernel has no configuration (Cout > 256): use the separate launches."""
+    N, H, W, Cin = x.shape
+    hid = w_dw.shape[1]
+    Cout = w_proj.shape[0]
+    ho, wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    if out is None:
+        out = torch.empty((N, ho, wo, Cout), dtype=torch.bfloat16, device=x.device)
+    d = _lib.MbconvDesc(N=N, H=H, W=W, Cin=Cin, hid=hid, Cout=Cout, stride=stride, residual=int(bool(residual)),
+                        relu_expand=int(relu[0]), relu_dw=int(relu[1]), relu_project=int(relu[2]),
+                        w_exp_rows=w_exp.shape[0] if w_exp is not None else 0, w_proj_rows=w_proj.shape[0],
+                        out_cstride=out.stride(2))
+    with torch.cuda.device(x.device):
+        rc = lib.ssdsb_mbconv_bf16(C.byref(d), ptr(x), ptr(w_exp), ptr(b_exp), ptr(w_dw), ptr(b_dw), ptr(w_proj),
+                                   ptr(b_proj), ptr(out), stream_ptr())
+    check(rc, "mbconv")          # SSDSB_ERR_UNSUPPORTED -> NotImplementedError
+    return out
+
+
+def mbconv_last_launch():
+    """{hc, tile_w, tile_h, pm, chunks, x_buffers, staging, dw_segments, dw_rows, grid, smem, block_n}"""
+    out = (C.c_int * 12)()
+    check(lib.ssdsb_mbconv_last_launch(out), "mbconv_last_launch")
+    return dict(zip(("hc", "tile_w", "tile_h", "pm", "chunks", "x_buffers", "staging", "dw_segments", "dw_rows",
+                     "grid", "smem", "block_n"), list(out)))
+
+
 def pack_grouped_weight(w_folded, chunk, c_pad):
     """Grouped conv [C, gw, KH, KW] (groups = C / gw) -> block-diagonal chunk slabs for the chunked
     igemm: bf16 [(c_pad/chunk)*128, KH*KW, chunk]; slab s covers channels [s*chunk, (s+1)*chunk), its

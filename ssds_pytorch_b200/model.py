@@ -411,11 +411,34 @@ class _MobileNetV2Backbone:
     def _plan_backbone(self, packed, H, W, steps, buf, add_conv, add_dw):
         x = add_conv(self.stem, packed, Ho=H // 2, Wo=W // 2, x_kind=1, x_width=W // 2)
         feats = []
+        # [r2] one launch per inverted residual (conv_mbconv.cu): the expanded tensor stays on the SM.
+        # SSDSB_NO_MBFUSE=1 keeps the three launches (A/B runs, and the bit-exact reference of the self-check).
+        fuse = os.environ.get("SSDSB_NO_MBFUSE", "0") != "1" and os.environ.get("SSDSB_MBFUSE", "0") == "1"
+
+        def add_mb(blk, x):
+            n, h, w, cin = x.shape
+            dw, pr, ex = blk["dw"], blk["project"], blk.get("expand")
+            ho, wo = (h - 1) // dw.stride + 1, (w - 1) // dw.stride + 1
+            y = buf(n, ho, wo, pr.cout)
+            res = blk["res"]
+            ew, eb = (ex.w, ex.bias) if ex is not None else (None, None)
+            relu = (ex.relu if ex is not None else 0, dw.relu, pr.relu)
+            nfl = ((ex.flops_per_pixel * n * h * w) if ex is not None else 0) + \
+                (dw.flops_per_pixel + pr.flops_per_pixel) * n * ho * wo
+            nby = 2 * (x.numel() * (2 if res else 1) + y.numel() + dw.w.numel() + pr.w.numel() +
+                       (ex.w.numel() if ex is not None else 0))
+            self._add_raw(lambda: K.mbconv(x, ew, eb, dw.w, dw.bias, pr.w, pr.bias, dw.stride, res, relu, out=y),
+                          nfl, kind=f"mbconv s{dw.stride} {cin}->{dw.c}->{pr.cout} @{ho}x{wo}", nbytes=nby)
+            return y
+
         for j, blocks in enumerate(self.layers, start=1):
             for blk in blocks:
-                y = add_conv(blk["expand"], x) if "expand" in blk else x
-                y = add_dw(blk["dw"], y)
-                x = add_conv(blk["project"], y, residual=x if blk["res"] else None)
+                if fuse and blk["project"].cout <= 256:
+                    x = add_mb(blk, x)
+                else:
+                    y = add_conv(blk["expand"], x) if "expand" in blk else x
+                    y = add_dw(blk["dw"], y)
+                    x = add_conv(blk["project"], y, residual=x if blk["res"] else None)
             if j in self.outputs:
                 feats.append(x)
         return feats

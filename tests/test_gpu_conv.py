@@ -231,6 +231,69 @@ def test_dwconv3x3_stream_any_chunking(K, case, monkeypatch):
     monkeypatch.delenv("SSDSB_DW_ROWS", raising=False)
 
 
+MBCONV = [
+    # N, H, W, Cin, hid, Cout, stride, residual — the MobileNetV2-SSD 300x300 block shapes (channels padded to 32
+    # as the plan stores them; hid == Cin and no expand layer for the first block) + ragged odd cases
+    (2, 150, 150, 32, 32, 32, 1, False),
+    (2, 150, 150, 32, 96, 32, 2, False),
+    (2, 75, 75, 32, 160, 32, 1, True),
+    (2, 75, 75, 32, 160, 32, 2, False),
+    (3, 38, 38, 32, 192, 32, 1, True),
+    (2, 38, 38, 32, 192, 64, 2, False),
+    (2, 19, 19, 64, 384, 64, 1, True),
+    (2, 19, 19, 64, 384, 96, 1, False),
+    (2, 19, 19, 96, 576, 96, 1, True),
+    (2, 19, 19, 96, 576, 160, 2, False),
+    (3, 10, 10, 160, 960, 160, 1, True),
+    (1, 21, 13, 32, 64, 32, 1, True),
+    (1, 7, 9, 64, 128, 96, 2, False),
+    (70, 5, 5, 64, 128, 64, 1, True),        # more tiles than SMs would hold at once is not needed: many images
+]
+
+
+@pytest.mark.parametrize("case", MBCONV)
+def test_mbconv_fused_equals_three_launches(K, case):
+    """[r2] ssdsb_mbconv_bf16 (expand -> depthwise -> project [+x] in one launch, the expanded tensor never
+    leaves the SM) is bit-identical to conv2d -> dwconv3x3 -> conv2d: same bf16 rounding points, same fp32
+    accumulation order.  Activations are scaled so that ReLU6 clips on both sides."""
+    N, H, W, Cin, hid, Cout, stride, res = case
+    g = torch.Generator().manual_seed(sum(case))
+    x = torch.randn((N, H, W, Cin), generator=g).to(torch.bfloat16).cuda()
+    has_expand = hid != Cin or Cin != 32 or stride != 1 or res
+    if has_expand:
+        we = K.pack_weight(torch.randn((hid, Cin, 1, 1), generator=g) * (2.0 / np.sqrt(Cin))).cuda()
+        be = (torch.randn((hid,), generator=g) * 0.5).cuda()
+    else:
+        we = be = None
+    wd = K.pack_dw_weight(torch.randn((hid, 1, 3, 3), generator=g) * 0.4).cuda()
+    bd = (torch.randn((hid,), generator=g) * 0.3).cuda()
+    wp = K.pack_weight(torch.randn((Cout, hid, 1, 1), generator=g) * (1.0 / np.sqrt(hid))).cuda()
+    bp = (torch.randn((Cout,), generator=g) * 0.2).cuda()
+    h = K.conv2d(x, we, be, 1, 1, 1, 0, 2) if has_expand else x
+    d = K.dwconv3x3(h, wd, bd, stride, 2)
+    want = K.conv2d(d, wp, bp, 1, 1, 1, 0, 0, residual=x if res else None)
+    got = K.mbconv(x, we, be, wd, bd, wp, bp, stride, res, (2, 2, 0))
+    torch.cuda.synchronize()
+    info = K.mbconv_last_launch()
+    assert got.shape == want.shape
+    if not torch.equal(got, want):
+        diff = (got.float() - want.float()).abs()
+        bad = (diff > 0).nonzero()
+        raise AssertionError(f"{case} {info}: {bad.shape[0]} of {diff.numel()} differ, max {diff.max().item():.4g}, "
+                             f"first at {bad[0].tolist()}, last at {bad[-1].tolist()}")
+    assert (d.float() == 0.0).any() and d.float().max().item() >= 3.0
+
+
+def test_mbconv_unsupported_is_loud(K):
+    x = torch.zeros((1, 10, 10, 160), dtype=torch.bfloat16, device="cuda")
+    we = torch.zeros((960, 1, 160), dtype=torch.bfloat16, device="cuda")
+    wd = torch.zeros((9, 960), dtype=torch.bfloat16, device="cuda")
+    wp = torch.zeros((320, 1, 960), dtype=torch.bfloat16, device="cuda")
+    z = lambda n: torch.zeros(n, device="cuda")
+    with pytest.raises(NotImplementedError):
+        K.mbconv(x, we, z(960), wd, z(960), wp, z(320))
+
+
 @pytest.mark.parametrize("case", [(2, 20, 20, 432, 1), (2, 20, 20, 192, 2), (1, 40, 24, 96, 1), (3, 10, 10, 1008, 1)])
 def test_grouped_conv_regnet(K, case):
     """RegNet 3x3 grouped conv (group width 48; regnet.py:69) as a block-diagonal chunked igemm:

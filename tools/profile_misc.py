@@ -37,6 +37,32 @@ def timed(name, fn, iters=5):
     print(f"{name}: {e0.elapsed_time(e1) / iters * 1e3:.1f} us")
 
 
+def timed_graph(name, fn, iters=10):
+    """like timed(), but the `iters` launches are replayed from one CUDA graph: no per-launch host time in the
+    number (eager ctypes launches cost ~15 us each, more than the small kernels themselves)"""
+    fn()
+    torch.cuda.synchronize()
+    st = torch.cuda.Stream()
+    st.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(st):
+        fn()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr, stream=st):
+            for _ in range(iters):
+                fn()
+    torch.cuda.synchronize()
+    gr.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    gr.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    t = e0.elapsed_time(e1) / iters * 1e3
+    print(f"{name}: {t:.1f} us")
+    return t
+
+
 def levels_cfg4(B):
     g = torch.Generator(device="cuda").manual_seed(1)
     lv = [(8, 80), (16, 40), (32, 20), (64, 10), (128, 5)]
@@ -139,6 +165,42 @@ def run_pw():
               lambda: K.conv2d(x, w, b, 1, 1, 1, 0, relu, residual=r, out=out))
 
 
+def run_mb():
+    """every inverted residual of MobileNetV2-SSD 300x300, B=64: one fused launch vs expand + depthwise + project"""
+    g = torch.Generator(device="cuda").manual_seed(8)
+    blocks = [(150, 32, 32, 32, 1, False), (150, 32, 96, 32, 2, False), (75, 32, 160, 32, 1, True),
+              (75, 32, 160, 32, 2, False), (38, 32, 192, 32, 1, True), (38, 32, 192, 64, 2, False),
+              (19, 64, 384, 64, 1, True), (19, 64, 384, 96, 1, False), (19, 96, 576, 96, 1, True),
+              (19, 96, 576, 160, 2, False), (10, 160, 960, 160, 1, True)]
+    tot_f = tot_s = 0.0
+    for (h, cin, hid, cout, stride, res) in blocks:
+        x = torch.randn((64, h, h, cin), generator=g, device="cuda").to(torch.bfloat16)
+        has_e = not (hid == cin and stride == 1 and not res)
+        we = K.pack_weight(torch.randn((hid, cin, 1, 1)) * (1.0 / np.sqrt(cin))).cuda() if has_e else None
+        be = torch.zeros(hid, device="cuda") if has_e else None
+        wd = K.pack_dw_weight(torch.randn((hid, 1, 3, 3)) * 0.3).cuda()
+        bd = torch.zeros(hid, device="cuda")
+        wp = K.pack_weight(torch.randn((cout, hid, 1, 1)) * (1.0 / np.sqrt(hid))).cuda()
+        bp = torch.zeros(cout, device="cuda")
+        ho = (h - 1) // stride + 1
+        hb = torch.empty((64, h, h, hid), dtype=torch.bfloat16, device="cuda")
+        db = torch.empty((64, ho, ho, hid), dtype=torch.bfloat16, device="cuda")
+        y = torch.empty((64, ho, ho, cout), dtype=torch.bfloat16, device="cuda")
+
+        def separate():
+            hh = K.conv2d(x, we, be, 1, 1, 1, 0, 2, out=hb) if has_e else x
+            K.dwconv3x3(hh, wd, bd, stride, 2, out=db)
+            K.conv2d(db, wp, bp, 1, 1, 1, 0, 0, residual=x if res else None, out=y)
+
+        tag = f"{cin}->{hid}->{cout} s{stride} @{h}{' +x' if res else ''}"
+        tf = timed_graph(f"mbconv fused    {tag}", lambda: K.mbconv(x, we, be, wd, bd, wp, bp, stride, res, (2, 2, 0), out=y))
+        print("      ", K.mbconv_last_launch())
+        ts = timed_graph(f"three launches  {tag}", separate)
+        tot_f += tf
+        tot_s += ts
+    print(f"sum over the 11 distinct blocks: fused {tot_f:.0f} us, separate {tot_s:.0f} us")
+
+
 def run_layout():
     g = torch.Generator(device="cuda").manual_seed(5)
     img = torch.randint(0, 256, (64, 512, 512, 3), dtype=torch.uint8, device="cuda")
@@ -172,5 +234,7 @@ if __name__ == "__main__":
             run_dw()
         elif w == "pw":
             run_pw()
+        elif w == "mb":
+            run_mb()
         elif w == "layout":
             run_layout()
