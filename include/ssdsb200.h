@@ -319,6 +319,12 @@ SSDSB_API int ssdsb_mbconv_bf16(const ssdsb_mbconv_desc* desc, const void* d_x, 
  * {hidden chunk, tile W, tile H, expand M tiles per chunk, chunks per tile, x buffers, staging slots,
  *  depthwise row segments, rows per segment, grid, dynamic shared memory bytes, project accumulator columns}. */
 SSDSB_API int ssdsb_mbconv_last_launch(int* out12);
+/* Diagnostic (host-synchronising, not for the hot path): with SSDSB_MB_PROF set in the environment, CTA 0 of every
+ * ssdsb_mbconv_bf16 launch records how many cycles each of its 16 warps spent blocked on each barrier id
+ * (out[warp * 16 + id], ids listed in conv_mbconv.cu), out[256] = cycles CTA 0 ran, out[257] = chunks it processed,
+ * out[258 + (g - 8) * 8 + k] = cycle stamp of event k of chunk g = 8..15 (dw start / dw done / project wait / project
+ * issue / expand committed / convert start / convert done).  The buffer holds 322 entries. */
+SSDSB_API int ssdsb_mbconv_profile(unsigned long long* out322);
 
 /* Image pre-processing fused with the layout change the stem needs (SSDDetector.__call__,
  * ssds/ssds.py:48-57: HWC->CHW, (x - mean)/std): packs an image batch into the 2x2

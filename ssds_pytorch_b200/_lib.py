@@ -101,6 +101,7 @@ def _load():
         "ssdsb_conv_last_launch": (i, [C.POINTER(C.c_int)]),
         "ssdsb_mbconv_bf16": (i, [C.POINTER(MbconvDesc), vp, vp, vp, vp, vp, vp, vp, vp, vp]),
         "ssdsb_mbconv_last_launch": (i, [C.POINTER(C.c_int)]),
+        "ssdsb_mbconv_profile": (i, [C.POINTER(C.c_ulonglong)]),
         "ssdsb_conv2d_bf16": (i, [C.POINTER(ConvDesc), vp, vp, vp, vp, vp, vp, vp]),
         "ssdsb_pack_image_s2d": (i, [vp, i, i, i, i, f, f, i, i, vp, vp]),
         "ssdsb_maxpool3x3s2_nhwc_bf16": (i, [vp, i, i, i, i, vp, vp]),

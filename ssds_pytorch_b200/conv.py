@@ -248,6 +248,25 @@ def mbconv_last_launch():
                      "grid", "smem", "block_n"), list(out)))
 
 
+MB_BARRIERS = ("WORK", "we_empty", "hp_empty", "wp_empty", "a_full", "wp_full", "we_full", "eacc_empty", "slot_full",
+               "pacc_full", "eacc_full", "hp_full", "a_empty", "x_empty", "pacc_empty", "x_full")
+MB_WARPS = ("tma", "mma", "alloc", "store", "cvt0", "cvt1", "cvt2", "cvt3") + tuple(f"dw{i}" for i in range(8))
+
+
+def mbconv_profile():
+    """wait profile of CTA 0 of the last mbconv launch (needs SSDSB_MB_PROF=1 in the environment at launch):
+    {"cycles", "chunks", "waits": {warp: {barrier: cycles}}}"""
+    out = (C.c_ulonglong * 322)()
+    check(lib.ssdsb_mbconv_profile(out), "mbconv_profile")
+    waits = {}
+    for w, wn in enumerate(MB_WARPS):
+        row = {MB_BARRIERS[i]: int(out[w * 16 + i]) for i in range(0, 16) if out[w * 16 + i]}
+        if row:
+            waits[wn] = row
+    events = [[int(out[258 + g * 8 + k]) for k in range(8)] for g in range(8)]
+    return {"cycles": int(out[256]), "chunks": int(out[257]), "waits": waits, "events": events}
+
+
 def pack_grouped_weight(w_folded, chunk, c_pad):
     """Grouped conv [C, gw, KH, KW] (groups = C / gw) -> block-diagonal chunk slabs for the chunked
     igemm: bf16 [(c_pad/chunk)*128, KH*KW, chunk]; slab s covers channels [s*chunk, (s+1)*chunk), its

@@ -19,9 +19,11 @@
 // Without an expand layer (t = 1, the first block) the x patch IS the depthwise input: TMA writes it straight
 // into hpatch.
 //
-// Warp roles (512 threads): w0 TMA producer, w1 MMA issuer, w2 TMEM allocator, w3 store / residual engine,
+// Warp roles (512 threads): w0 TMA producer, w1 expand-MMA issuer, w2 TMEM allocator + project-MMA issuer,
+// w3 store / residual engine,
 // w4-7 convert + epilogue (TMEM lane quarter = warp % 4), w8-15 depthwise.
-// The MMA thread runs expand(g) one chunk ahead of project(g-1), so convert(g+1) overlaps dw(g).
+// The two GEMMs are issued by two threads on two warp schedulers: a single issuing thread (~15 dependent
+// instructions per tcgen05 op among busy warps) was the bottleneck of the pipeline.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <stdlib.h>
@@ -35,7 +37,7 @@ namespace {
 constexpr int MB_NT = 512;
 constexpr int MB_DW_THREADS = 256;
 constexpr int MB_STAGING_BYTES = BLOCK_M * 128;
-constexpr int MB_MAX_BYTES = 232448;
+constexpr int MB_MAX_BYTES = 232448 - 3072;   // minus the static wait-profile counters / event log
 
 struct MbParams {
   int H, W, Ho, Wo;
@@ -52,11 +54,13 @@ struct MbParams {
   int nseg, rs;            // depthwise: row segments per tile, output rows per segment
   int relu_e, relu_d, relu_p;
   int we_bytes, wp_bytes, hp_bytes, a_bytes;
+  int hp_pitch;            // bytes per pixel row of hpatch: HC*2 + 16 (convert writes conflict-free), dense under TMA
   int off_x, off_we, off_wp, off_hp, off_a, off_stage, off_bar;
   const float* b_exp;
   const float* b_dw;
   const float* b_proj;
   const uint2* w_dw;       // [9][hid / 4] bf16 quads
+  int prof;                // 1: CTA 0 records its per-warp barrier wait cycles (ssdsb_mbconv_profile)
 };
 
 __device__ __forceinline__ uint64_t make_smem_desc_rt(uint32_t smem_addr, int row_bytes) {
@@ -67,13 +71,53 @@ __device__ __forceinline__ uint64_t make_smem_desc_rt(uint32_t smem_addr, int ro
   d |= (uint64_t)(row_bytes == 128 ? 2 : (row_bytes == 64 ? 4 : 6)) << 61;
   return d;
 }
+// tcgen05.mma with the two shared-memory descriptors given as (low word = address >> 4 [+ k offset], constant high
+// word): the single issuing thread only does 32-bit adds per MMA
+__device__ __forceinline__ void umma_bf16_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                               uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// shared-memory accesses of the depthwise stage: volatile (ordered after the barrier waits and among themselves,
+// exactly as written) but without a memory clobber, so the FMAs in between schedule freely
 __device__ __forceinline__ uint2 lds_u2(uint32_t addr) {
   uint2 o;
-  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(o.x), "=r"(o.y) : "r"(addr) : "memory");
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(o.x), "=r"(o.y) : "r"(addr));
   return o;
 }
-__device__ __forceinline__ void sts_u2(uint32_t addr, uint32_t a, uint32_t b) {
-  asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+__device__ __forceinline__ void sts_u2_pred(uint32_t addr, uint32_t a, uint32_t b, bool pred) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %3, 0;\n\t@q st.shared.v2.u32 [%0], {%1, %2};\n\t}" ::"r"(addr),
+               "r"(a), "r"(b), "r"((int)pred));
+}
+// two fp32 lanes in one 64-bit register pair: fma.rn.f32x2 issues two IEEE FMAs as one instruction (same results
+// as two fmaf, half the issue slots — the depthwise stage is issue-bound)
+typedef unsigned long long f2_t;
+__device__ __forceinline__ f2_t pk2(float a, float b) {
+  f2_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void upk2(f2_t v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ f2_t ffma2(f2_t a, f2_t b, f2_t c) {
+  f2_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+// 4 bf16 (8 bytes) -> two packed pairs
+__device__ __forceinline__ void bf4_to_f2(const uint2 v, f2_t (&f)[2]) {
+  f[0] = pk2(__uint_as_float(v.x << 16), __uint_as_float(v.x & 0xffff0000u));
+  f[1] = pk2(__uint_as_float(v.y << 16), __uint_as_float(v.y & 0xffff0000u));
 }
 __device__ __forceinline__ void mb_bf4_to_f(const uint2 v, float (&f)[4]) {
   f[0] = __uint_as_float(v.x << 16);
@@ -98,9 +142,34 @@ __device__ __noinline__ void mb_wait_fail(int id, uint32_t parity) {
          (int)threadIdx.x, id, parity);
   __trap();
 }
+// optional wait profile (ssdsb_mbconv_profile): cycles each warp spent blocked per barrier id, CTA 0 only
+__device__ unsigned long long g_mb_prof[16 * 16 + 2 + 64];   // + event log: chunks 8..15 x 8 events
+__shared__ unsigned long long s_mb_ev[64];
+__shared__ unsigned long long s_mb_prof[16 * 16];
+__shared__ int s_mb_prof_on;
+// PROF is a template parameter of the kernel (0: production, none of this; 1: event stamps only — a clock read
+// and a shared store per event, light enough not to change the schedule; 2: also per-barrier wait cycles)
+template <int PROF>
 __device__ __forceinline__ void mbw(uint64_t* bar, uint32_t parity, int id) {
+  // (try_wait itself may suspend the thread up to a hardware time limit: the whole call is timed)
+  long long t0 = 0;
+  if (PROF == 2) t0 = clock64();
   for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins)
     if (spins > (1u << 24)) mb_wait_fail(id, parity);
+  if (PROF == 2 && s_mb_prof_on && (threadIdx.x & 31) == 0)
+    atomicAdd(&s_mb_prof[(threadIdx.x >> 5) * 16 + id], (unsigned long long)(clock64() - t0));
+}
+// slot 0 of a warp's row: cycles of its own work section (lane 0 only)
+template <int PROF>
+__device__ __forceinline__ void mb_prof_work(long long t0) {
+  if (PROF == 2 && s_mb_prof_on && (threadIdx.x & 31) == 0)
+    atomicAdd(&s_mb_prof[(threadIdx.x >> 5) * 16], (unsigned long long)(clock64() - t0));
+}
+
+// event log (profiling): cycle stamp, relative to the CTA's start, of event k of chunk g (8 <= g < 16)
+template <int PROF>
+__device__ __forceinline__ void mb_event(int g, int k, long long t0) {
+  if (PROF && s_mb_prof_on && g >= 8 && g < 16) s_mb_ev[(g - 8) * 8 + k] = (unsigned long long)(clock64() - t0);
 }
 
 struct MbTile {
@@ -114,7 +183,7 @@ __device__ __forceinline__ MbTile mb_tile(const MbParams& p, int tile) {
   return t;
 }
 
-template <int HC>
+template <int HC, int PROF>
 __global__ void __launch_bounds__(MB_NT, 1)
 mbconv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWe,
               const __grid_constant__ CUtensorMap tmWp, const __grid_constant__ CUtensorMap tmY,
@@ -151,6 +220,12 @@ mbconv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const long long t_start = PROF ? clock64() : 0ll;
+  if (PROF) {
+    if (threadIdx.x < 256) s_mb_prof[threadIdx.x] = 0ull;
+    if (threadIdx.x < 64) s_mb_ev[threadIdx.x] = 0ull;
+    if (threadIdx.x == 0) s_mb_prof_on = (blockIdx.x == 0) ? 1 : 0;
+  }
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmX);
@@ -198,95 +273,144 @@ mbconv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
   const int nchunks_out = (p.Cout + 63) >> 6;
   const int rowb_x = p.blk_x * 2;
 
+  const int my_tiles = ((int)p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int G = my_tiles * nch;           // chunks this CTA processes; chunk g: tile g / nch, hidden chunk g % nch
+
   if (warp == 0) {
     // =============================== TMA producer ===============================
+    // expand weights run two chunks ahead of the project weights (the MMA thread issues expand(g+2) before
+    // project(g)); with two x buffers the next tile's patch is requested a whole tile ahead
     if (lane == 0) {
-      int g = 0, tcount = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcount) {
-        const MbTile t = mb_tile(p, tile);
-        const int iw0 = t.w0 * p.S - 1, ih0 = t.h0 * p.S - 1;
+      auto load_x = [&](int tc) {
+        const MbTile t = mb_tile(p, (int)blockIdx.x + tc * (int)gridDim.x);
+        const int xb = tc % p.n_xbuf;
+        mbw<PROF>(&x_empty[xb], (uint32_t)(((tc / p.n_xbuf) & 1) ^ 1), 13);
+        mbar_expect_tx(&x_full[xb], (uint32_t)(p.xkb * p.PP * rowb_x));
+        for (int kb = 0; kb < p.xkb; ++kb)
+          tma_load_4d(xbuf + xb * p.x_bytes + kb * p.xkb_bytes, &tmX, &x_full[xb], kb * p.blk_x, t.w0 * p.S - 1,
+                      t.h0 * p.S - 1, t.n);
+      };
+      auto load_we = [&](int ge) {
+        const int s = ge & 1;
+        // (the expand of chunk ge - 2 signals ONE barrier, eacc_full: its accumulator is ready and its weight
+        // stage is free — a tcgen05.commit costs the single MMA thread ~100 cycles)
+        mbw<PROF>(&eacc_full[s], (uint32_t)(((ge >> 1) & 1) ^ 1), 1);
+        mbar_expect_tx(&we_full[s], (uint32_t)(p.xkb * HC * rowb_x));
+        for (int kb = 0; kb < p.xkb; ++kb)
+          tma_load_2d(webuf + s * p.we_bytes + kb * HC * rowb_x, &tmWe, &we_full[s], kb * p.blk_x, (ge % nch) * HC);
+      };
+      if (p.has_expand) {
+        load_x(0);
+        if (G > 0) load_we(0);
+        if (G > 1) load_we(1);
+      }
+      for (int g = 0; g < G; ++g) {
+        const int s = g & 1;
+        const uint32_t ph = (uint32_t)((g >> 1) & 1);
+        const int hh = g % nch, tc = g / nch;
         if (p.has_expand) {
-          const int xb = tcount % p.n_xbuf;
-          mbw(&x_empty[xb], (uint32_t)(((tcount / p.n_xbuf) & 1) ^ 1), 13);
-          mbar_expect_tx(&x_full[xb], (uint32_t)(p.xkb * p.PP * rowb_x));
-          for (int kb = 0; kb < p.xkb; ++kb)
-            tma_load_4d(xbuf + xb * p.x_bytes + kb * p.xkb_bytes, &tmX, &x_full[xb], kb * p.blk_x, iw0, ih0, t.n);
+          // next tile's x patch: a tile ahead with two buffers, else as soon as this tile's last expand is issued
+          if (tc + 1 < my_tiles && hh == (p.n_xbuf == 2 ? 0 : nch - 1)) load_x(tc + 1);
+          if (g + 2 < G) load_we(g + 2);
+        } else {
+          const MbTile t = mb_tile(p, (int)blockIdx.x + tc * (int)gridDim.x);
+          mbw<PROF>(&hp_empty[s], ph ^ 1, 2);
+          mbar_expect_tx(&hp_full[s], (uint32_t)(p.PP * RB));
+          tma_load_4d(hpbuf + s * p.hp_bytes, &tmX, &hp_full[s], hh * HC, t.w0 * p.S - 1, t.h0 * p.S - 1, t.n);
         }
-        for (int h = 0; h < nch; ++h, ++g) {
-          const int s = g & 1;
-          const uint32_t ph = (uint32_t)((g >> 1) & 1);
-          if (p.has_expand) {
-            mbw(&we_empty[s], ph ^ 1, 1);
-            mbar_expect_tx(&we_full[s], (uint32_t)(p.xkb * HC * rowb_x));
-            for (int kb = 0; kb < p.xkb; ++kb)
-              tma_load_2d(webuf + s * p.we_bytes + kb * HC * rowb_x, &tmWe, &we_full[s], kb * p.blk_x, h * HC);
-          } else {
-            mbw(&hp_empty[s], ph ^ 1, 2);
-            mbar_expect_tx(&hp_full[s], (uint32_t)(p.PP * RB));
-            tma_load_4d(hpbuf + s * p.hp_bytes, &tmX, &hp_full[s], h * HC, iw0, ih0, t.n);
-          }
-          mbw(&wp_empty[s], ph ^ 1, 3);
-          mbar_expect_tx(&wp_full[s], (uint32_t)(p.block_n * RB));
-          tma_load_2d(wpbuf + s * p.wp_bytes, &tmWp, &wp_full[s], h * HC, 0);
-        }
+        mbw<PROF>(&a_empty[s], ph ^ 1, 3);      // project(g - 2) done: A stage and project-weight stage are free
+        mbar_expect_tx(&wp_full[s], (uint32_t)(p.block_n * RB));
+        tma_load_2d(wpbuf + s * p.wp_bytes, &tmWp, &wp_full[s], hh * HC, 0);
       }
     }
   } else if (warp == 1) {
-    // =============================== MMA issuer ===============================
+    // =============================== expand MMA issuer ===============================
+    // runs ahead as far as the two accumulator / weight stages allow: expand(g+2) only needs convert(g) to have
+    // drained its accumulator, which happens BEFORE the depthwise warps start on chunk g — its result is waiting in
+    // TMEM when they are done.  Within an expand the MMAs of the PM accumulators are interleaved (back-to-back
+    // MMAs on one accumulator retire only every ~146 cycles).
     if (lane == 0) {
+      // A single thread runs this: every instruction costs its full latency, so the loop carries chunk / tile
+      // counters incrementally (no divisions) and descriptors as 32-bit (address >> 4) values; the upper
+      // descriptor word is constant per operand kind.
       const uint32_t idesc_e = make_idesc(BLOCK_M, HC);
+      const int ksteps = p.blk_x / UMMA_K;
+      const uint32_t hi_x = (uint32_t)(make_smem_desc_rt(0u, rowb_x) >> 32);
+      auto lo = [](uint32_t addr) { return (addr & 0x3ffffu) >> 4; };
+      const uint32_t x_lo = lo(smem_u32(xbuf)), we_lo = lo(smem_u32(webuf));
+      const uint32_t x_buf_step = (uint32_t)p.x_bytes >> 4, x_kb_step = (uint32_t)p.xkb_bytes >> 4;
+      const uint32_t x_m_step = (uint32_t)(BLOCK_M * rowb_x) >> 4;
+      const uint32_t we_s_step = (uint32_t)p.we_bytes >> 4, we_kb_step = (uint32_t)(HC * rowb_x) >> 4;
+      // expand sequence state (chunk ge): stage, phase, hidden chunk, x buffer / its phase
+      int e_g = 0, e_hh = 0, e_xb = 0;
+      uint32_t e_xph = 0;
+      auto expand = [&]() {
+        const int s = e_g & 1;
+        const uint32_t ph = (uint32_t)((e_g >> 1) & 1);
+        if (e_hh == 0) mbw<PROF>(&x_full[e_xb], e_xph, 15);
+        mbw<PROF>(&we_full[s], ph, 6);
+        mbw<PROF>(&eacc_empty[s], ph ^ 1, 7);
+        mb_event<PROF>(e_g, 7, t_start);
+        tcgen05_fence_after();
+        const uint32_t xa = x_lo + (uint32_t)e_xb * x_buf_step;
+        const uint32_t wa = we_lo + (uint32_t)s * we_s_step;
+        const uint32_t d0 = tmem_base + eacc_col0 + (uint32_t)(s * p.PM * HC);
+        for (int kb = 0; kb < p.xkb; ++kb) {
+          const uint32_t xk = xa + (uint32_t)kb * x_kb_step, wk = wa + (uint32_t)kb * we_kb_step;
+          for (int k = 0; k < ksteps; ++k) {
+            const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
+            uint32_t am = xk + (uint32_t)(2 * k), dm = d0;
+            for (int m = 0; m < p.PM; ++m, am += x_m_step, dm += (uint32_t)HC)      // accumulators interleaved
+              umma_bf16_lohi(dm, am, hi_x, wk + (uint32_t)(2 * k), hi_x, idesc_e, acc);
+          }
+        }
+        tcgen05_commit(&eacc_full[s]);
+        mb_event<PROF>(e_g, 4, t_start);
+        ++e_g;
+        if (++e_hh == nch) {
+          e_hh = 0;
+          tcgen05_commit(&x_empty[e_xb]);
+          if (++e_xb == p.n_xbuf) {
+            e_xb = 0;
+            e_xph ^= 1u;
+          }
+        }
+      };
+      if (p.has_expand)
+        for (int g = 0; g < G; ++g) expand();
+    }
+  } else if (warp == 2) {
+    // =============================== project MMA issuer ===============================
+    // (a second issuing thread on another scheduler: one thread running both GEMMs was the bottleneck of the
+    // whole pipeline — ~15 dependent instructions per tcgen05.mma / commit at ~10 cycles each among busy warps)
+    if (lane == 0) {
       const uint32_t idesc_p = make_idesc(BLOCK_M, p.block_n);
-      auto project = [&](int gp) {
+      const uint32_t hi_h = (uint32_t)(make_smem_desc_rt(0u, RB) >> 32);
+      const uint32_t a_lo = (smem_u32(abuf) & 0x3ffffu) >> 4, wp_lo = (smem_u32(wpbuf) & 0x3ffffu) >> 4;
+      const uint32_t a_s_step = (uint32_t)p.a_bytes >> 4, wp_s_step = (uint32_t)p.wp_bytes >> 4;
+      int p_hh = 0;
+      uint32_t p_tph = 0;           // parity of the tile count: pacc barriers
+      for (int gp = 0; gp < G; ++gp) {
         const int s = gp & 1;
         const uint32_t ph = (uint32_t)((gp >> 1) & 1);
-        const int hh = gp % nch, tc = gp / nch;
-        mbw(&a_full[s], ph, 4);
-        mbw(&wp_full[s], ph, 5);
-        if (hh == 0) mbw(pacc_empty, (uint32_t)((tc & 1) ^ 1), 14);
+        mb_event<PROF>(gp, 2, t_start);
+        mbw<PROF>(&a_full[s], ph, 4);
+        mbw<PROF>(&wp_full[s], ph, 5);
+        if (p_hh == 0) mbw<PROF>(pacc_empty, p_tph ^ 1u, 14);
+        mb_event<PROF>(gp, 3, t_start);
         tcgen05_fence_after();
-        const uint64_t a_desc = make_smem_desc_rt(smem_u32(abuf + s * p.a_bytes), RB);
-        const uint64_t b_desc = make_smem_desc_rt(smem_u32(wpbuf + s * p.wp_bytes), RB);
+        const uint32_t aa = a_lo + (uint32_t)s * a_s_step, wb = wp_lo + (uint32_t)s * wp_s_step;
 #pragma unroll
         for (int k = 0; k < HC / UMMA_K; ++k)
-          umma_bf16(tmem_base, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc_p,
-                    (hh > 0 || k > 0) ? 1u : 0u);
+          umma_bf16_lohi(tmem_base, aa + (uint32_t)(2 * k), hi_h, wb + (uint32_t)(2 * k), hi_h, idesc_p,
+                         (p_hh > 0 || k > 0) ? 1u : 0u);
         tcgen05_commit(&a_empty[s]);
-        tcgen05_commit(&wp_empty[s]);
-        if (hh == nch - 1) tcgen05_commit(pacc_full);
-      };
-      int g = 0, tcount = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcount) {
-        const int xb = tcount % p.n_xbuf;
-        for (int h = 0; h < nch; ++h, ++g) {
-          if (p.has_expand) {
-            const int s = g & 1;
-            const uint32_t ph = (uint32_t)((g >> 1) & 1);
-            if (h == 0) mbw(&x_full[xb], (uint32_t)((tcount / p.n_xbuf) & 1), 15);
-            mbw(&we_full[s], ph, 6);
-            mbw(&eacc_empty[s], ph ^ 1, 7);
-            tcgen05_fence_after();
-            const uint32_t xa = smem_u32(xbuf + xb * p.x_bytes);
-            const uint32_t wa = smem_u32(webuf + s * p.we_bytes);
-            for (int m = 0; m < p.PM; ++m) {
-              const uint32_t d_tmem = tmem_base + eacc_col0 + (uint32_t)((s * p.PM + m) * HC);
-              for (int kb = 0; kb < p.xkb; ++kb) {
-                const uint64_t a_desc =
-                    make_smem_desc_rt(xa + (uint32_t)(kb * p.xkb_bytes + m * BLOCK_M * rowb_x), rowb_x);
-                const uint64_t b_desc = make_smem_desc_rt(wa + (uint32_t)(kb * HC * rowb_x), rowb_x);
-                const int ksteps = p.blk_x / UMMA_K;
-                for (int k = 0; k < ksteps; ++k)
-                  umma_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc_e,
-                            (kb > 0 || k > 0) ? 1u : 0u);
-              }
-            }
-            tcgen05_commit(&we_empty[s]);
-            tcgen05_commit(&eacc_full[s]);
-            if (h == nch - 1) tcgen05_commit(&x_empty[xb]);
-          }
-          if (g > 0) project(g - 1);
+        if (++p_hh == nch) {
+          p_hh = 0;
+          p_tph ^= 1u;
+          tcgen05_commit(pacc_full);
         }
       }
-      if (g > 0) project(g - 1);
     }
   } else if (warp == 3) {
     // ================= store / residual engine =================
@@ -316,7 +440,7 @@ mbconv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const MbTile t = mb_tile(p, tile);
         for (int c = 0; c < nchunks_out; ++c, ++gs) {
-          mbw(&slot_full[sring.slot], sring.phase, 8);
+          mbw<PROF>(&slot_full[sring.slot], sring.phase, 8);
           tma_store_4d(&tmY, staging + sring.slot * MB_STAGING_BYTES, c * 64, t.w0, t.h0, t.n);
           tma_store_commit();
           sring.advance(R);
@@ -338,7 +462,7 @@ mbconv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     const float lo_e = p.relu_e ? 0.0f : -__int_as_float(0x7f800000);
     SlotRing ring = {0, 0u};
     auto epilogue = [&](int tc) {
-      mbw(pacc_full, (uint32_t)(tc & 1), 9);
+      mbw<PROF>(pacc_full, (uint32_t)(tc & 1), 9);
       tcgen05_fence_after();
       for (int c = 0; c < nchunks_out; ++c) {
 #pragma unroll 1
@@ -376,16 +500,19 @@ mbconv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
       for (int h = 0; h < nch; ++h, ++g) {
         const int s = g & 1;
         const uint32_t ph = (uint32_t)((g >> 1) & 1);
-        mbw(&eacc_full[s], ph, 10);
-        mbw(&hp_empty[s], ph ^ 1, 2);
+        mbw<PROF>(&eacc_full[s], ph, 10);
+        if (lane == 0 && q == 0) mb_event<PROF>(g, 5, t_start);
+        mbw<PROF>(&hp_empty[s], ph ^ 1, 2);
         tcgen05_fence_after();
         const uint32_t hp_addr = smem_u32(hpbuf + s * p.hp_bytes);
         const float* bias = p.b_exp + h * HC;
+        const long long t_work = PROF == 2 ? clock64() : 0ll;
 #pragma unroll
         for (int m = 0; m < 3; ++m) {
           if (m >= p.PM || m * BLOCK_M + q * 32 >= p.PP) break;        // warp-uniform
           const int r = m * BLOCK_M + r_tile;
-          const bool keep = inimg[m];
+          // pixels outside the image: clamp to [0, 0] (the depthwise conv zero-pads the expanded tensor)
+          const float lo_k = inimg[m] ? lo_e : 0.0f, hi_k = inimg[m] ? hi_e : 0.0f;
 #pragma unroll
           for (int half = 0; half < HC / 32; ++half) {
             uint32_t v[32];
@@ -407,27 +534,31 @@ mbconv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
                   f[e * 4 + 3] = __uint_as_float(v[gq * 8 + e * 4 + 3]) + b4.w;
                 }
 #pragma unroll
-                for (int e = 0; e < 8; ++e) f[e] = keep ? fminf(fmaxf(f[e], lo_e), hi_e) : 0.0f;
+                for (int e = 0; e < 8; ++e) f[e] = fminf(fmaxf(f[e], lo_k), hi_k);
                 uint4 o;
                 o.x = pack_bf16(f[0], f[1]);
                 o.y = pack_bf16(f[2], f[3]);
                 o.z = pack_bf16(f[4], f[5]);
                 o.w = pack_bf16(f[6], f[7]);
-                // 16-byte chunk (half * 4 + gq) of row r = channel quads 2*(half*4+gq), +1
-                sts_u4(hp_addr + swz_off<HC>(r, 2 * (half * 4 + gq)), o);
+                // 16-byte chunk (half * 4 + gq) of pixel r; the padded pitch spreads the 8 lanes of a store phase
+                // over all banks
+                sts_u4(hp_addr + (uint32_t)(r * p.hp_pitch + (half * 4 + gq) * 16), o);
               }
             }
           }
         }
+        mb_prof_work<PROF>(t_work);
+        if (lane == 0 && q == 0) mb_event<PROF>(g, 6, t_start);
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) {
           mbar_arrive(&eacc_empty[s]);
           mbar_arrive(&hp_full[s]);
         }
-        // the previous tile's epilogue runs after this tile's first chunk has been handed to the depthwise
-        // warps: its project MMAs only complete after dw of the previous tile's last chunk
-        if (pending && h == 0) {
+        // the previous tile's epilogue runs after this tile's SECOND chunk has been handed to the depthwise warps
+        // (convert of that chunk had to wait for dw of the previous tile's last chunk anyway, so the project MMAs
+        // it needs are complete or about to be, and the depthwise warps have two chunks of work queued meanwhile)
+        if (pending && h == (nch > 1 ? 1 : 0)) {
           epilogue(tcount - 1);
           pending = false;
         }
@@ -442,93 +573,160 @@ mbconv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     const float lo_d = p.relu_d ? 0.0f : -__int_as_float(0x7f800000);
     const int n_items = p.nseg * p.BW * QD;
     const int hq = p.hid >> 2;
+    const bool one_item = n_items <= MB_DW_THREADS;
+    const int it_qd = tid & (QD - 1);
+    const int it_seg = (tid / QD) / p.BW;
+    const int it_bw = (tid / QD) - it_seg * p.BW;
+    const int it_r0 = it_seg * p.rs;
+    const int it_rows = min(p.rs, p.BH - it_r0);
+    const bool it_active = tid < n_items && it_rows > 0;
+    uint2 wraw[9];
+    float4 braw;
+    auto fetch_weights = [&](int hh) {
+      const uint2* wp = p.w_dw + hh * QD + it_qd;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) wraw[k] = __ldg(wp + (size_t)k * hq);
+      braw = __ldg(reinterpret_cast<const float4*>(p.b_dw + hh * HC) + it_qd);
+    };
+    if (one_item && it_active && G > 0) fetch_weights(0);
     int g = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       for (int h = 0; h < nch; ++h, ++g) {
         const int s = g & 1;
         const uint32_t ph = (uint32_t)((g >> 1) & 1);
-        mbw(&hp_full[s], ph, 11);
-        mbw(&a_empty[s], ph ^ 1, 12);
+        mbw<PROF>(&hp_full[s], ph, 11);
+        mbw<PROF>(&a_empty[s], ph ^ 1, 12);
         const uint32_t hp_addr = smem_u32(hpbuf + s * p.hp_bytes);
         const uint32_t a_addr = smem_u32(abuf + s * p.a_bytes);
-        for (int item = tid; item < n_items; item += MB_DW_THREADS) {
-          const int qd = item & (QD - 1);
-          const int tt = item / QD;
-          const int seg = tt / p.BW;
-          const int bw = tt - seg * p.BW;
-          const int r0 = seg * p.rs;
-          const int rows = min(p.rs, p.BH - r0);
-          if (rows <= 0) continue;
-          float wf[9][4], b[4];
-          {
-            const uint2* wp = p.w_dw + h * QD + qd;
+        const long long t_work = PROF == 2 ? clock64() : 0ll;
+        if (tid == 0) mb_event<PROF>(g, 0, t_start);
+        // one item = (row segment, output column, channel quad): its 9 x 4 folded weights and bias come from global
+        // memory (L1 / L2).  With at most one item per thread (the geometry search aims for exactly that) the
+        // decomposition is done once per kernel and the NEXT chunk's weights are requested right after this chunk's
+        // arithmetic, so their latency hides behind the fence / arrive / wait of the hand-over.
+        auto process = [&](const int qd, const int bw, const int r0, const int rows, const f2_t (&wf)[9][2],
+                           const f2_t (&b2)[2]) {
+            const uint32_t pitch = (uint32_t)p.hp_pitch;
+            const uint32_t rsb = (uint32_t)p.PW * pitch;                 // one patch row down
+            struct Raw {
+              uint2 l, m, r;
+            };
+            auto load3 = [&](uint32_t ptr) -> Raw {
+              Raw v;
+              v.l = lds_u2(ptr);
+              v.m = lds_u2(ptr + pitch);
+              v.r = lds_u2(ptr + 2 * pitch);
+              return v;
+            };
+            auto fma_row = [&](f2_t (&a)[2], const Raw& v, int dy) {
+              f2_t f[2];
+              bf4_to_f2(v.l, f);
+              a[0] = ffma2(f[0], wf[dy * 3][0], a[0]);
+              a[1] = ffma2(f[1], wf[dy * 3][1], a[1]);
+              bf4_to_f2(v.m, f);
+              a[0] = ffma2(f[0], wf[dy * 3 + 1][0], a[0]);
+              a[1] = ffma2(f[1], wf[dy * 3 + 1][1], a[1]);
+              bf4_to_f2(v.r, f);
+              a[0] = ffma2(f[0], wf[dy * 3 + 2][0], a[0]);
+              a[1] = ffma2(f[1], wf[dy * 3 + 2][1], a[1]);
+            };
+            auto emit = [&](int oh, const f2_t (&a)[2], bool pred) {
+              float o[4];
+              upk2(a[0], o[0], o[1]);
+              upk2(a[1], o[2], o[3]);
 #pragma unroll
-            for (int k = 0; k < 9; ++k) mb_bf4_to_f(__ldg(wp + (size_t)k * hq), wf[k]);
-            const float4 bv = __ldg(reinterpret_cast<const float4*>(p.b_dw + h * HC) + qd);
-            b[0] = bv.x; b[1] = bv.y; b[2] = bv.z; b[3] = bv.w;
-          }
-          auto load_row = [&](int prow, int pcol, float (&f)[3][4]) {
-            const int pix = prow * p.PW + pcol;
-            mb_bf4_to_f(lds_u2(hp_addr + swz_off<HC>(pix, qd)), f[0]);
-            mb_bf4_to_f(lds_u2(hp_addr + swz_off<HC>(pix + 1, qd)), f[1]);
-            mb_bf4_to_f(lds_u2(hp_addr + swz_off<HC>(pix + 2, qd)), f[2]);
-          };
-          auto fma_row = [&](float (&a)[4], const float (&f)[3][4], int dy) {
+              for (int e = 0; e < 4; ++e) o[e] = fminf(fmaxf(o[e], lo_d), hi_d);
+              sts_u2_pred(a_addr + swz_off<HC>(oh * p.BW + bw, qd), pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pred);
+            };
+            if (p.S == 1) {
+              // patch row r0 + i feeds outputs r0 + i (dy 0), r0 + i - 1 (dy 1), r0 + i - 2 (dy 2): three accumulators
+              // whose roles rotate with period 3 (static under the unroll).  Branch-free: the next row's loads are
+              // issued before this row's FMAs, rows past the last one re-read the last (their outputs are never
+              // stored), stores are predicated.
+              uint32_t ptr = hp_addr + (uint32_t)(r0 * p.PW + bw) * pitch + (uint32_t)(qd * 8);
+              const uint32_t last = ptr + (uint32_t)(rows + 1) * rsb;
+              const int n_in = rows + 2;
+              f2_t acc[3][2];
 #pragma unroll
-            for (int dx = 0; dx < 3; ++dx)
+              for (int a = 0; a < 3; ++a) {
+                acc[a][0] = b2[0];
+                acc[a][1] = b2[1];
+              }
+              Raw nxt = load3(ptr);
+              for (int i0 = 0; i0 < n_in; i0 += 3) {
 #pragma unroll
-              for (int e = 0; e < 4; ++e) a[e] = fmaf(f[dx][e], wf[dy * 3 + dx][e], a[e]);
-          };
-          auto emit = [&](int oh, const float (&a)[4]) {
-            float o[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) o[e] = fminf(fmaxf(a[e], lo_d), hi_d);
-            sts_u2(a_addr + swz_off<HC>(oh * p.BW + bw, qd), pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]));
-          };
-          if (p.S == 1) {
-            // patch row r0 + i feeds outputs r0 + i (dy 0), r0 + i - 1 (dy 1), r0 + i - 2 (dy 2)
-            float acc[3][4];
-#pragma unroll
-            for (int a = 0; a < 3; ++a)
-#pragma unroll
-              for (int e = 0; e < 4; ++e) acc[a][e] = b[e];
-            const int n_in = rows + 2;
-            for (int i0 = 0; i0 < n_in; i0 += 3) {
-#pragma unroll
-              for (int j = 0; j < 3; ++j) {
-                const int i = i0 + j;
-                if (i < n_in) {
-                  float f[3][4];
-                  load_row(r0 + i, bw, f);
-                  fma_row(acc[j], f, 0);
-                  fma_row(acc[(j + 2) % 3], f, 1);
-                  fma_row(acc[(j + 1) % 3], f, 2);
-                  if (i >= 2) emit(r0 + i - 2, acc[(j + 1) % 3]);
+                for (int j = 0; j < 3; ++j) {
+                  const int i = i0 + j;
+                  const Raw cur = nxt;
+                  ptr = min(ptr + rsb, last);
+                  nxt = load3(ptr);
+                  fma_row(acc[j], cur, 0);
+                  fma_row(acc[(j + 2) % 3], cur, 1);
+                  fma_row(acc[(j + 1) % 3], cur, 2);
+                  emit(r0 + i - 2, acc[(j + 1) % 3], i >= 2 && i < n_in);
+                  acc[(j + 1) % 3][0] = b2[0];
+                  acc[(j + 1) % 3][1] = b2[1];
                 }
-#pragma unroll
-                for (int e = 0; e < 4; ++e) acc[(j + 1) % 3][e] = b[e];
+              }
+            } else {
+              // output o = patch rows 2o (dy 0), 2o+1, 2o+2; row 2o+2 is also the top row of output o+1
+              uint32_t ptr = hp_addr + (uint32_t)(2 * r0 * p.PW + 2 * bw) * pitch + (uint32_t)(qd * 8);
+              const uint32_t last = ptr + (uint32_t)(2 * rows) * rsb;
+              f2_t a[2] = {b2[0], b2[1]};
+              {
+                const Raw top = load3(ptr);
+                fma_row(a, top, 0);
+              }
+              ptr = min(ptr + rsb, last);
+              Raw n1 = load3(ptr);
+              ptr = min(ptr + rsb, last);
+              Raw n2 = load3(ptr);
+              for (int o = 0; o < rows; ++o) {
+                const Raw c1 = n1, c2 = n2;
+                ptr = min(ptr + rsb, last);
+                n1 = load3(ptr);
+                ptr = min(ptr + rsb, last);
+                n2 = load3(ptr);
+                fma_row(a, c1, 1);
+                fma_row(a, c2, 2);
+                emit(r0 + o, a, true);
+                a[0] = b2[0];
+                a[1] = b2[1];
+                fma_row(a, c2, 0);
               }
             }
-          } else {
-            float a[4] = {b[0], b[1], b[2], b[3]};
-            {
-              float f[3][4];
-              load_row(2 * r0, 2 * bw, f);
-              fma_row(a, f, 0);
-            }
-            for (int o = 0; o < rows; ++o) {
-              float f1[3][4], f2[3][4];
-              load_row(2 * (r0 + o) + 1, 2 * bw, f1);
-              load_row(2 * (r0 + o) + 2, 2 * bw, f2);
-              fma_row(a, f1, 1);
-              fma_row(a, f2, 2);
-              emit(r0 + o, a);
+        };
+        if (one_item) {
+          if (it_active) {
+            f2_t wf[9][2], b2[2];
 #pragma unroll
-              for (int e = 0; e < 4; ++e) a[e] = b[e];
-              fma_row(a, f2, 0);
-            }
+            for (int k = 0; k < 9; ++k) bf4_to_f2(wraw[k], wf[k]);
+            b2[0] = pk2(braw.x, braw.y);
+            b2[1] = pk2(braw.z, braw.w);
+            process(it_qd, it_bw, it_r0, it_rows, wf, b2);
+            if (g + 1 < G) fetch_weights(h + 1 == nch ? 0 : h + 1);
+          }
+        } else {
+          for (int item = tid; item < n_items; item += MB_DW_THREADS) {
+            const int qd = item & (QD - 1);
+            const int tt = item / QD;
+            const int seg = tt / p.BW;
+            const int bw = tt - seg * p.BW;
+            const int r0 = seg * p.rs;
+            const int rows = min(p.rs, p.BH - r0);
+            if (rows <= 0) continue;
+            f2_t wf[9][2], b2[2];
+            const uint2* wp = p.w_dw + h * QD + qd;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) bf4_to_f2(__ldg(wp + (size_t)k * hq), wf[k]);
+            const float4 bv = __ldg(reinterpret_cast<const float4*>(p.b_dw + h * HC) + qd);
+            b2[0] = pk2(bv.x, bv.y);
+            b2[1] = pk2(bv.z, bv.w);
+            process(qd, bw, r0, rows, wf, b2);
           }
         }
+        mb_prof_work<PROF>(t_work);
+        if (tid == 0) mb_event<PROF>(g, 1, t_start);
         fence_proxy_async();              // generic-proxy smem writes -> visible to the tensor core (async proxy)
         __syncwarp();
         if (lane == 0) {
@@ -544,6 +742,16 @@ mbconv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
   if (warp == 2) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+  if (PROF && s_mb_prof_on) {
+    if (threadIdx.x < 256) g_mb_prof[threadIdx.x] = s_mb_prof[threadIdx.x];
+    if (threadIdx.x < 64) g_mb_prof[258 + threadIdx.x] = s_mb_ev[threadIdx.x];
+    if (threadIdx.x == 0) {
+      g_mb_prof[256] = (unsigned long long)(clock64() - t_start);
+      int my_tiles = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) ++my_tiles;
+      g_mb_prof[257] = (unsigned long long)my_tiles * (unsigned long long)p.nch;
+    }
   }
 }
 
@@ -573,7 +781,9 @@ MbGeom pick_geometry(int Ho, int Wo, int S, int HC, int nch, bool has_expand, in
       for (int nseg = 1; nseg <= 4 && nseg <= BH; ++nseg) {
         const int rs = (BH + nseg - 1) / nseg;
         const int rounds = (nseg * BW * qd + MB_DW_THREADS - 1) / MB_DW_THREADS;
-        const double c = rounds * (rs * (S == 1 ? 44.0 : 56.0) + 70.0);
+        // stride 1 runs its rows in groups of 3 (rs + 2 input rows); ~50 issue slots per row step per warp
+        const double steps = S == 1 ? 3.0 * ((rs + 2 + 2) / 3) : 2.0 * rs + 1.0;
+        const double c = rounds * (steps * 50.0 + 120.0);
         if (c < dw_best) {
           dw_best = c;
           nseg_best = nseg;
@@ -596,9 +806,10 @@ MbGeom pick_geometry(int Ho, int Wo, int S, int HC, int nch, bool has_expand, in
 }
 
 CUresult encode_tm(EncodeTiledFn encode, CUtensorMap* tm, int rank, const void* base, const cuuint64_t* dims,
-                   const cuuint64_t* strides, const cuuint32_t* box, int inner_bytes) {
+                   const cuuint64_t* strides, const cuuint32_t* box, int inner_bytes, bool swizzled = true) {
   cuuint32_t estr[4] = {1, 1, 1, 1};
-  const CUtensorMapSwizzle swz = inner_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+  const CUtensorMapSwizzle swz = !swizzled ? CU_TENSOR_MAP_SWIZZLE_NONE
+                                 : inner_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                                  : (inner_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   return encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box,
                 estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -613,6 +824,13 @@ int pick_block_n_mb(int cout) { return cout <= 64 ? 64 : (cout <= 128 ? 128 : 25
 }  // namespace ssdsb
 
 using namespace ssdsb;
+
+extern "C" int ssdsb_mbconv_profile(unsigned long long* out258 /* 322 entries */) {
+  SSDSB_REQUIRE(out258, "mbconv_profile: NULL argument");
+  SSDSB_CUDA(cudaDeviceSynchronize());
+  SSDSB_CUDA(cudaMemcpyFromSymbol(out258, g_mb_prof, sizeof(unsigned long long) * 322));
+  return SSDSB_OK;
+}
 
 extern "C" int ssdsb_mbconv_last_launch(int* out12) {
   SSDSB_REQUIRE(out12, "mbconv_last_launch: NULL argument");
@@ -666,6 +884,7 @@ extern "C" int ssdsb_mbconv_bf16(const ssdsb_mbconv_desc* d, const void* x, cons
   p.relu_e = d->relu_expand; p.relu_d = d->relu_dw; p.relu_p = d->relu_project;
   p.b_exp = b_exp; p.b_dw = b_dw; p.b_proj = b_proj;
   p.w_dw = reinterpret_cast<const uint2*>(w_dw);
+  p.prof = getenv("SSDSB_MB_PROF") ? atoi(getenv("SSDSB_MB_PROF")) : 0;      // 1: event stamps, 2: + wait cycles
   p.blk_x = has_expand ? (d->Cin % 64 == 0 ? 64 : 32) : 0;
   p.xkb = has_expand ? d->Cin / p.blk_x : 0;
 
@@ -696,7 +915,8 @@ extern "C" int ssdsb_mbconv_bf16(const ssdsb_mbconv_desc* d, const void* x, cons
     const int x_bytes = p.xkb * xkb_bytes;
     const int we_bytes = has_expand ? p.xkb * hc_try * rowb_x : 0;
     const int wp_bytes = block_n * hc_try * 2;
-    const int hp_bytes = pp_pad * hc_try * 2;
+    const int hp_pitch = has_expand ? hc_try * 2 + 16 : hc_try * 2;
+    const int hp_bytes = (pp_pad * hp_pitch + 1023) / 1024 * 1024;
     const int a_bytes = BLOCK_M * hc_try * 2;
     bool done = false;
     for (int n_xbuf = has_expand ? 2 : 0; n_xbuf >= (has_expand ? 1 : 0) && !done; --n_xbuf) {
@@ -712,6 +932,7 @@ extern "C" int ssdsb_mbconv_bf16(const ssdsb_mbconv_desc* d, const void* x, cons
         p.nseg = gm.nseg; p.rs = gm.rs;
         p.xkb_bytes = xkb_bytes; p.x_bytes = x_bytes; p.n_xbuf = n_xbuf ? n_xbuf : 1;
         p.we_bytes = we_bytes; p.wp_bytes = wp_bytes; p.hp_bytes = hp_bytes; p.a_bytes = a_bytes;
+        p.hp_pitch = hp_pitch;
         p.R = R; p.lag = lag;
         p.off_x = 0;
         p.off_we = p.off_x + n_xbuf * x_bytes;
@@ -741,7 +962,8 @@ extern "C" int ssdsb_mbconv_bf16(const ssdsb_mbconv_desc* d, const void* x, cons
     cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
     cuuint64_t strides[3] = {(cuuint64_t)d->Cin * 2, (cuuint64_t)d->W * d->Cin * 2, (cuuint64_t)d->H * d->W * d->Cin * 2};
     cuuint32_t box[4] = {(cuuint32_t)inner, (cuuint32_t)p.PW, (cuuint32_t)p.PH, 1};
-    CUresult r = encode_tm(encode, &tmX, 4, x, dims, strides, box, inner * 2);
+    // (without an expand layer the patch lands in hpatch, which the depthwise warps read as dense linear rows)
+    CUresult r = encode_tm(encode, &tmX, 4, x, dims, strides, box, inner * 2, has_expand);
     if (r != CUDA_SUCCESS) return fail(SSDSB_ERR_CUDA, "mbconv: x tensor map failed (CUresult %d)", (int)r);
   }
   if (has_expand) {
@@ -781,21 +1003,18 @@ extern "C" int ssdsb_mbconv_bf16(const ssdsb_mbconv_desc* d, const void* x, cons
   const int info[12] = {HC, p.BW, p.BH, p.PM, p.nch, p.n_xbuf, p.R, p.nseg, p.rs, grid, smem_total, block_n};
   for (int i = 0; i < 12; ++i) g_mb_last[i] = info[i];
   cudaStream_t st = (cudaStream_t)stream;
-  if (HC == 64) {
-    static bool configured = false;
-    if (!configured) {
-      SSDSB_CUDA(cudaFuncSetAttribute(mbconv_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, MB_MAX_BYTES));
-      configured = true;
-    }
-    mbconv_kernel<64><<<grid, MB_NT, smem_total, st>>>(tmX, tmWe, tmWp, tmY, tmR, p);
-  } else {
-    static bool configured = false;
-    if (!configured) {
-      SSDSB_CUDA(cudaFuncSetAttribute(mbconv_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, MB_MAX_BYTES));
-      configured = true;
-    }
-    mbconv_kernel<32><<<grid, MB_NT, smem_total, st>>>(tmX, tmWe, tmWp, tmY, tmR, p);
-  }
+  auto launch = [&](auto kernel) -> cudaError_t {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MB_MAX_BYTES);
+    if (e != cudaSuccess) return e;
+    kernel<<<grid, MB_NT, smem_total, st>>>(tmX, tmWe, tmWp, tmY, tmR, p);
+    return cudaSuccess;
+  };
+  if (p.prof == 2)
+    SSDSB_CUDA(HC == 64 ? launch(mbconv_kernel<64, 2>) : launch(mbconv_kernel<32, 2>));
+  else if (p.prof == 1)
+    SSDSB_CUDA(HC == 64 ? launch(mbconv_kernel<64, 1>) : launch(mbconv_kernel<32, 1>));
+  else
+    SSDSB_CUDA(HC == 64 ? launch(mbconv_kernel<64, 0>) : launch(mbconv_kernel<32, 0>));
   SSDSB_LAUNCH_CHECK("mbconv_kernel");
   return SSDSB_OK;
 }
