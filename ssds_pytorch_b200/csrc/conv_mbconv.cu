@@ -60,6 +60,7 @@ struct MbParams {
   const float* b_dw;
   const float* b_proj;
   const uint2* w_dw;       // [9][hid / 4] bf16 quads
+  int dbg;                 // SSDSB_MB_DEBUG bits (bisecting aid): 1 no dead-half skip, 2 always refetch dw weights
   int prof;                // 1: CTA 0 records its per-warp barrier wait cycles (ssdsb_mbconv_profile)
 };
 
@@ -114,16 +115,19 @@ __device__ __forceinline__ f2_t ffma2(f2_t a, f2_t b, f2_t c) {
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
   return d;
 }
+// clamp of two packed bf16 values: rounding to bf16 is monotone and both bounds (0, 6, +-inf) are bf16 numbers, so
+// clamp(round(x)) == round(clamp(x)) — one max + one min per PAIR instead of two each per element
+__device__ __forceinline__ uint32_t clamp_bf16x2(uint32_t v, uint32_t lo2, uint32_t hi2) {
+  uint32_t r;
+  asm("{\n\t.reg .b32 t;\n\tmax.bf16x2 t, %1, %2;\n\tmin.bf16x2 %0, t, %3;\n\t}" : "=r"(r) : "r"(v), "r"(lo2), "r"(hi2));
+  return r;
+}
+__device__ __forceinline__ uint32_t relu_lo2(int relu) { return relu ? 0x00000000u : 0xff80ff80u; }        // 0 | -inf
+__device__ __forceinline__ uint32_t relu_hi2(int relu) { return relu == 2 ? 0x40c040c0u : 0x7f807f80u; }   // 6 | +inf
 // 4 bf16 (8 bytes) -> two packed pairs
 __device__ __forceinline__ void bf4_to_f2(const uint2 v, f2_t (&f)[2]) {
   f[0] = pk2(__uint_as_float(v.x << 16), __uint_as_float(v.x & 0xffff0000u));
   f[1] = pk2(__uint_as_float(v.y << 16), __uint_as_float(v.y & 0xffff0000u));
-}
-__device__ __forceinline__ void mb_bf4_to_f(const uint2 v, float (&f)[4]) {
-  f[0] = __uint_as_float(v.x << 16);
-  f[1] = __uint_as_float(v.x & 0xffff0000u);
-  f[2] = __uint_as_float(v.y << 16);
-  f[3] = __uint_as_float(v.y & 0xffff0000u);
 }
 
 // byte offset of channel quad `qd` (4 bf16 = 8 bytes) of row `p` in a K-major tile with HC*2-byte rows,
@@ -458,8 +462,7 @@ mbconv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     const int r_tile = q * 32 + lane;              // row of an M tile == TMEM lane
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
     const uint32_t staging_addr = smem_u32(staging);
-    const float hi_e = (p.relu_e == 2) ? 6.0f : __int_as_float(0x7f800000);
-    const float lo_e = p.relu_e ? 0.0f : -__int_as_float(0x7f800000);
+    const uint32_t hi_e = relu_hi2(p.relu_e), lo_e = relu_lo2(p.relu_e);
     SlotRing ring = {0, 0u};
     auto epilogue = [&](int tc) {
       mbw<PROF>(pacc_full, (uint32_t)(tc & 1), 9);
@@ -468,10 +471,25 @@ mbconv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
 #pragma unroll 1
         for (int half = 0; half < 2; ++half) {
           SlotRing rr = ring;
-          staged_epilogue_item(t_lane + (uint32_t)(c * 64), 1, p.b_proj + c * 64 + half * 32, staging_addr,
-                               MB_STAGING_BYTES, p.R, rr, slot_ready, slot_full,
-                               c == nchunks_out - 1 ? pacc_empty : nullptr, p.has_res != 0, p.relu_p, r_tile, half,
-                               lane, p.Cout - c * 64 - half * 32);
+          if (p.Cout - c * 64 - half * 32 <= 0 && !(p.dbg & 1)) {
+            // this warp's 32 columns lie beyond Cout (Cout % 64 == 32, e.g. every 32-channel block output): no
+            // arithmetic, only the barriers' arrival counts (slot_ready first: an early slot_full arrival would
+            // count towards the slot's previous use)
+            if (c == nchunks_out - 1) {
+              tcgen05_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(pacc_empty);
+            }
+            mbar_wait(&slot_ready[rr.slot], rr.phase);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&slot_full[rr.slot]);
+            rr.advance(p.R);
+          } else {
+            staged_epilogue_item(t_lane + (uint32_t)(c * 64), 1, p.b_proj + c * 64 + half * 32, staging_addr,
+                                 MB_STAGING_BYTES, p.R, rr, slot_ready, slot_full,
+                                 c == nchunks_out - 1 ? pacc_empty : nullptr, p.has_res != 0, p.relu_p, r_tile, half,
+                                 lane, p.Cout - c * 64 - half * 32);
+          }
           if (half == 1) ring = rr;
         }
       }
@@ -512,7 +530,7 @@ mbconv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
           if (m >= p.PM || m * BLOCK_M + q * 32 >= p.PP) break;        // warp-uniform
           const int r = m * BLOCK_M + r_tile;
           // pixels outside the image: clamp to [0, 0] (the depthwise conv zero-pads the expanded tensor)
-          const float lo_k = inimg[m] ? lo_e : 0.0f, hi_k = inimg[m] ? hi_e : 0.0f;
+          const uint32_t lo_k = inimg[m] ? lo_e : 0u, hi_k = inimg[m] ? hi_e : 0u;
 #pragma unroll
           for (int half = 0; half < HC / 32; ++half) {
             uint32_t v[32];
@@ -533,13 +551,11 @@ mbconv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
                   f[e * 4 + 2] = __uint_as_float(v[gq * 8 + e * 4 + 2]) + b4.z;
                   f[e * 4 + 3] = __uint_as_float(v[gq * 8 + e * 4 + 3]) + b4.w;
                 }
-#pragma unroll
-                for (int e = 0; e < 8; ++e) f[e] = fminf(fmaxf(f[e], lo_k), hi_k);
                 uint4 o;
-                o.x = pack_bf16(f[0], f[1]);
-                o.y = pack_bf16(f[2], f[3]);
-                o.z = pack_bf16(f[4], f[5]);
-                o.w = pack_bf16(f[6], f[7]);
+                o.x = clamp_bf16x2(pack_bf16(f[0], f[1]), lo_k, hi_k);
+                o.y = clamp_bf16x2(pack_bf16(f[2], f[3]), lo_k, hi_k);
+                o.z = clamp_bf16x2(pack_bf16(f[4], f[5]), lo_k, hi_k);
+                o.w = clamp_bf16x2(pack_bf16(f[6], f[7]), lo_k, hi_k);
                 // 16-byte chunk (half * 4 + gq) of pixel r; the padded pitch spreads the 8 lanes of a store phase
                 // over all banks
                 sts_u4(hp_addr + (uint32_t)(r * p.hp_pitch + (half * 4 + gq) * 16), o);
@@ -569,8 +585,7 @@ mbconv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
   } else if (warp >= 8) {
     // =============================== depthwise ===============================
     const int tid = threadIdx.x - 256;
-    const float hi_d = (p.relu_d == 2) ? 6.0f : __int_as_float(0x7f800000);
-    const float lo_d = p.relu_d ? 0.0f : -__int_as_float(0x7f800000);
+    const uint32_t hi_d = relu_hi2(p.relu_d), lo_d = relu_lo2(p.relu_d);
     const int n_items = p.nseg * p.BW * QD;
     const int hq = p.hid >> 2;
     const bool one_item = n_items <= MB_DW_THREADS;
@@ -634,9 +649,8 @@ mbconv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
               float o[4];
               upk2(a[0], o[0], o[1]);
               upk2(a[1], o[2], o[3]);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) o[e] = fminf(fmaxf(o[e], lo_d), hi_d);
-              sts_u2_pred(a_addr + swz_off<HC>(oh * p.BW + bw, qd), pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pred);
+              sts_u2_pred(a_addr + swz_off<HC>(oh * p.BW + bw, qd), clamp_bf16x2(pack_bf16(o[0], o[1]), lo_d, hi_d),
+                          clamp_bf16x2(pack_bf16(o[2], o[3]), lo_d, hi_d), pred);
             };
             if (p.S == 1) {
               // patch row r0 + i feeds outputs r0 + i (dy 0), r0 + i - 1 (dy 1), r0 + i - 2 (dy 2): three accumulators
@@ -704,7 +718,7 @@ mbconv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
             b2[0] = pk2(braw.x, braw.y);
             b2[1] = pk2(braw.z, braw.w);
             process(it_qd, it_bw, it_r0, it_rows, wf, b2);
-            if (g + 1 < G) fetch_weights(h + 1 == nch ? 0 : h + 1);
+            if ((nch > 1 || (p.dbg & 2)) && g + 1 < G) fetch_weights(h + 1 == nch ? 0 : h + 1);   // (one chunk: same weights again)
           }
         } else {
           for (int item = tid; item < n_items; item += MB_DW_THREADS) {
@@ -884,6 +898,7 @@ extern "C" int ssdsb_mbconv_bf16(const ssdsb_mbconv_desc* d, const void* x, cons
   p.relu_e = d->relu_expand; p.relu_d = d->relu_dw; p.relu_p = d->relu_project;
   p.b_exp = b_exp; p.b_dw = b_dw; p.b_proj = b_proj;
   p.w_dw = reinterpret_cast<const uint2*>(w_dw);
+  p.dbg = getenv("SSDSB_MB_DEBUG") ? atoi(getenv("SSDSB_MB_DEBUG")) : 0;
   p.prof = getenv("SSDSB_MB_PROF") ? atoi(getenv("SSDSB_MB_PROF")) : 0;      // 1: event stamps, 2: + wait cycles
   p.blk_x = has_expand ? (d->Cin % 64 == 0 ? 64 : 32) : 0;
   p.xkb = has_expand ? d->Cin / p.blk_x : 0;

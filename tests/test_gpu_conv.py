@@ -282,6 +282,8 @@ def test_mbconv_fused_equals_three_launches(K, case):
         raise AssertionError(f"{case} {info}: {bad.shape[0]} of {diff.numel()} differ, max {diff.max().item():.4g}, "
                              f"first at {bad[0].tolist()}, last at {bad[-1].tolist()}")
     assert (d.float() == 0.0).any() and d.float().max().item() >= 3.0
+    if has_expand:                      # both clamp bounds of both ReLU6 stages are exercised
+        assert (h.float() == 6.0).any() and (h.float() == 0.0).any() and (d.float() == 6.0).any()
 
 
 def test_mbconv_unsupported_is_loud(K):

@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout -s KILL 600 python -m pytest tests/test_gpu_conv.py tests/test_gpu_model.py -q -m gpu --tb=short -x 2>&1 | tail -8 > gpurun_out/r2p_tests.log
+timeout -s KILL 600 python -m pytest tests/test_gpu_conv.py tests/test_gpu_model.py -q -m gpu --tb=short 2>&1 | tail -8 > gpurun_out/r2p_tests.log
 cat gpurun_out/r2p_tests.log
 timeout -s KILL 300 python tools/profile_misc.py mb > gpurun_out/r2p_mb_timings.txt 2>&1
 grep -v "^ " gpurun_out/r2p_mb_timings.txt
