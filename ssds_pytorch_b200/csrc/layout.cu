@@ -338,6 +338,33 @@ __device__ __forceinline__ uint2 ldg_pred_u2(const uint2* p, bool pred) {
   return v;
 }
 
+// two fp32 lanes per 64-bit register pair: fma.rn.f32x2 = two IEEE FMAs in one issue slot (bit-identical to two
+// fmaf; the kernel is issue / latency bound); ReLU / ReLU6 as max + min on the packed bf16 pair AFTER rounding
+// (rounding is monotone, 0 and 6 are bf16 numbers: clamp(round(x)) == round(clamp(x)))
+typedef unsigned long long dwf2_t;
+__device__ __forceinline__ dwf2_t dw_pk2(float a, float b) {
+  dwf2_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void dw_upk2(dwf2_t v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ dwf2_t dw_ffma2(dwf2_t a, dwf2_t b, dwf2_t c) {
+  dwf2_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ void bf4_to_f2(const uint2 v, dwf2_t (&f)[2]) {
+  f[0] = dw_pk2(__uint_as_float(v.x << 16), __uint_as_float(v.x & 0xffff0000u));
+  f[1] = dw_pk2(__uint_as_float(v.y << 16), __uint_as_float(v.y & 0xffff0000u));
+}
+__device__ __forceinline__ uint32_t dw_clamp_bf16x2(uint32_t v, uint32_t lo2, uint32_t hi2) {
+  uint32_t r;
+  asm("{\n\t.reg .b32 t;\n\tmax.bf16x2 t, %1, %2;\n\tmin.bf16x2 %0, t, %3;\n\t}" : "=r"(r) : "r"(v), "r"(lo2), "r"(hi2));
+  return r;
+}
+
 struct DwRow {
   uint2 l, m, r;
 };
@@ -359,14 +386,16 @@ dwconv3x3_stream_kernel(const uint2* __restrict__ x, const uint2* __restrict__ w
   const int n = (int)(t / (unsigned)chunks);
   const int ho0 = ch * rows_per;
   const int rows = min(Ho, ho0 + rows_per) - ho0;
-  float wf[9][4], b[4];
+  dwf2_t wf[9][2], b[2];
 #pragma unroll
-  for (int k = 0; k < 9; ++k) bf4_to_f(__ldg(w + (size_t)k * C4 + c), wf[k]);
+  for (int k = 0; k < 9; ++k) bf4_to_f2(__ldg(w + (size_t)k * C4 + c), wf[k]);
   {
     const float4 bv = __ldg(reinterpret_cast<const float4*>(bias) + c);
-    b[0] = bv.x; b[1] = bv.y; b[2] = bv.z; b[3] = bv.w;
+    b[0] = dw_pk2(bv.x, bv.y);
+    b[1] = dw_pk2(bv.z, bv.w);
   }
-  const float lo = relu ? 0.0f : -INFINITY, hi = (relu == 2) ? 6.0f : INFINITY;
+  const uint32_t lo2 = relu ? 0x00000000u : 0xff80ff80u;          // bf16x2 (0 | -inf), (6 | +inf)
+  const uint32_t hi2 = (relu == 2) ? 0x40c040c0u : 0x7f807f80u;
   const int w0 = wo * S - 1;                       // leftmost input column of this output column
   const bool has_l = w0 >= 0, has_r = w0 + 2 < W;  // the centre column wo*S is always inside
   const int h_first = ho0 * S - 1;                 // first input row this thread streams (may be -1)
@@ -385,22 +414,23 @@ dwconv3x3_stream_kernel(const uint2* __restrict__ x, const uint2* __restrict__ w
     ++li;
     return r;
   };
-  auto fma_row = [&](float (&a)[4], const float (&f)[3][4], int dy) {
+  auto fma_row = [&](dwf2_t (&a)[2], const dwf2_t (&f)[3][2], int dy) {
 #pragma unroll
-    for (int dx = 0; dx < 3; ++dx)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) a[e] = fmaf(f[dx][e], wf[dy * 3 + dx][e], a[e]);
+    for (int dx = 0; dx < 3; ++dx) {
+      a[0] = dw_ffma2(f[dx][0], wf[dy * 3 + dx][0], a[0]);
+      a[1] = dw_ffma2(f[dx][1], wf[dy * 3 + dx][1], a[1]);
+    }
   };
-  auto unpack = [&](const DwRow& r, float (&f)[3][4]) {
-    bf4_to_f(r.l, f[0]); bf4_to_f(r.m, f[1]); bf4_to_f(r.r, f[2]);
+  auto unpack = [&](const DwRow& r, dwf2_t (&f)[3][2]) {
+    bf4_to_f2(r.l, f[0]); bf4_to_f2(r.m, f[1]); bf4_to_f2(r.r, f[2]);
   };
   uint2* yp = y + ((long long)n * Ho + ho0) * ((long long)Wo * C4) + (long long)wo * C4 + c;
   const long long out_stride = (long long)Wo * C4;
-  auto emit = [&](const float (&a)[4]) {
+  auto emit = [&](const dwf2_t (&a)[2]) {
     float o[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) o[e] = fminf(fmaxf(a[e], lo), hi);
-    *yp = make_uint2(pack2(o[0], o[1]), pack2(o[2], o[3]));
+    dw_upk2(a[0], o[0], o[1]);
+    dw_upk2(a[1], o[2], o[3]);
+    *yp = make_uint2(dw_clamp_bf16x2(pack2(o[0], o[1]), lo2, hi2), dw_clamp_bf16x2(pack2(o[2], o[3]), lo2, hi2));
     yp += out_stride;
   };
 
@@ -408,16 +438,17 @@ dwconv3x3_stream_kernel(const uint2* __restrict__ x, const uint2* __restrict__ w
     DwRow ring[PF];
 #pragma unroll
     for (int j = 0; j < PF; ++j) ring[j] = load_next();
-    float acc[3][4];
+    dwf2_t acc[3][2];
 #pragma unroll
-    for (int a = 0; a < 3; ++a)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) acc[a][e] = b[e];
+    for (int a = 0; a < 3; ++a) {
+      acc[a][0] = b[0];
+      acc[a][1] = b[1];
+    }
     for (int i0 = 0; i0 < n_in; i0 += PF) {
 #pragma unroll
       for (int j = 0; j < PF; ++j) {
         const int i = i0 + j;                       // input row h_first + i
-        float f[3][4];
+        dwf2_t f[3][2];
         unpack(ring[j], f);
         ring[j] = load_next();                      // row i + PF
         // rows outside [0, n_in) were loaded as zeros; outputs outside [0, rows) are accumulated but never emitted
@@ -425,14 +456,14 @@ dwconv3x3_stream_kernel(const uint2* __restrict__ x, const uint2* __restrict__ w
         fma_row(acc[(j + 2) % 3], f, 1);            // continues output i-1
         fma_row(acc[(j + 1) % 3], f, 2);            // finishes output i-2
         if (i >= 2 && i < n_in) emit(acc[(j + 1) % 3]);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) acc[(j + 1) % 3][e] = b[e];
+        acc[(j + 1) % 3][0] = b[0];
+        acc[(j + 1) % 3][1] = b[1];
       }
     }
   } else {
-    float a[4] = {b[0], b[1], b[2], b[3]};
+    dwf2_t a[2] = {b[0], b[1]};
     {
-      float f[3][4];
+      dwf2_t f[3][2];
       const DwRow r0 = load_next();                 // row 2*ho0 - 1: the top row of the first output
       unpack(r0, f);
       fma_row(a, f, 0);
@@ -443,7 +474,7 @@ dwconv3x3_stream_kernel(const uint2* __restrict__ x, const uint2* __restrict__ w
     for (int o0 = 0; o0 < rows; o0 += PF) {
 #pragma unroll
       for (int j = 0; j < PF; ++j) {
-        float f1[3][4], f2[3][4];
+        dwf2_t f1[3][2], f2[3][2];
         unpack(ring[2 * j], f1);
         unpack(ring[2 * j + 1], f2);
         ring[2 * j] = load_next();
@@ -451,8 +482,8 @@ dwconv3x3_stream_kernel(const uint2* __restrict__ x, const uint2* __restrict__ w
         fma_row(a, f1, 1);
         fma_row(a, f2, 2);
         if (o0 + j < rows) emit(a);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) a[e] = b[e];
+        a[0] = b[0];
+        a[1] = b[1];
         fma_row(a, f2, 0);
       }
     }
