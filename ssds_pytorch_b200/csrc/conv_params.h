@@ -17,6 +17,7 @@ struct ConvKernelParams {
   int ntile_cout;    // output channels covered by one n-tile (BLOCK_N, or the chunk width)
   int ways;          // M tiles processed together with interleaved MMAs (1, 2 or 4 accumulators)
   int b_resident;    // weights of this CTA's n-tile stay in shared memory for the whole kernel
+  int mma_converged; // MMA warp issues from converged code through elect.sync (default) or from lane 0 only (A/B)
   int BW, BH, BN;    // output-pixel patch of one M tile (product <= 128)
   int tiles_w, tiles_h, tiles_n, n_tiles;
   int Ho, Wo, N;

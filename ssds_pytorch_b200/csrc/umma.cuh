@@ -126,6 +126,33 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// The same two instructions for a CONVERGED warp: all 32 lanes execute the statement, elect.sync picks the one that
+// issues.  From a `if (lane == 0)` branch ptxas wraps every tcgen05.mma / commit in an elect - vote - branch loop
+// ("once per active thread": ~9 SASS instructions per MMA, mostly that wrapper); in this form it emits the bare
+// UTCHMMA / UTCBAR on the uniform datapath (~3 per MMA).  The issuing thread's instruction stream is what bounds the
+// N = 64 layers (an N = 64 MMA is ~50 cycles of tensor-pipe work): tools/umma_bench.cu measured 64-78 cycles per
+// MMA with the lane-0 form whatever the number of interleaved accumulators.
+__device__ __forceinline__ void umma_bf16_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pe, pa;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "setp.ne.b32 pa, %4, 0;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, pa;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit_elect(uint64_t* bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+      "}" ::"r"(smem_u32(bar))
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "

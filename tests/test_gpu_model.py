@@ -156,6 +156,37 @@ def test_pair_launch_plan_is_bit_identical_to_separate_launches(env, tag, monkey
         assert torch.equal(a, b)
 
 
+@pytest.mark.parametrize("mode", ["always", "auto"])
+def test_mobilenet_plan_with_fused_inverted_residuals_is_bit_identical(env, mode, monkeypatch):
+    """[r2] SSD-MobileNetV2 300x300 with every inverted residual the fused kernel supports in ONE launch
+    (SSDSB_MBFUSE=1: 16 of 17 blocks, the 320-channel one has no configuration), and with the plan's own per-block
+    choice, vs three launches per block (SSDSB_NO_MBFUSE=1): exactly the same loc / conf tensors."""
+    from ssds_pytorch_b200 import model as MD
+    sd, fl, x, _, image, ncls = build("mbv2", env)
+    L = len(fl[0])
+    outs = []
+    for fused in (False, True):
+        monkeypatch.delenv("SSDSB_MBFUSE", raising=False)
+        monkeypatch.delenv("SSDSB_NO_MBFUSE", raising=False)
+        if not fused:
+            monkeypatch.setenv("SSDSB_NO_MBFUSE", "1")
+        elif mode == "always":
+            monkeypatch.setenv("SSDSB_MBFUSE", "1")
+        m = MD.engine_for("SSD", "MobileNetV2")(sd, fl, ncls, [6] * L, device="cuda").eval()
+        plan = m.plan_for(x.cuda())
+        loc, conf = m(x.cuda())
+        torch.cuda.synchronize()
+        n_mb = sum(v["kind"].startswith("mbconv") for v in plan["info"].values())
+        outs.append((n_mb, plan["launches"], [t.clone() for t in loc], [t.clone() for t in conf]))
+    monkeypatch.delenv("SSDSB_MBFUSE", raising=False)
+    monkeypatch.delenv("SSDSB_NO_MBFUSE", raising=False)
+    assert outs[0][0] == 0
+    if mode == "always":
+        assert outs[1][0] == 16 and outs[1][1] == outs[0][1] - (15 * 2 + 1)     # block 0 has no expand launch
+    for a, b in zip(outs[0][2] + outs[0][3], outs[1][2] + outs[1][3]):
+        assert torch.equal(a, b)
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # BASELINE.json configs[1] at its real shape: SSD-ResNet50 512x512, the plan bench.py times
 # ---------------------------------------------------------------------------------------------------------------
