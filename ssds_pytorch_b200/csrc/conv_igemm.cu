@@ -89,6 +89,59 @@ __device__ __forceinline__ TileCoord tile_coord(const ConvKernelParams& p, int m
   return t;
 }
 
+// The MMA-issuing loop of conv_igemm_kernel for a converged warp (see the call site).
+template <int BLOCK_N, int BLOCK_K, int WAYS>
+__device__ __noinline__ void mma_issue_converged(const ConvKernelParams& p, uint32_t smem_addr, uint32_t bres_addr,
+                                                 uint64_t* full_bar, uint64_t* empty_bar, uint64_t* tmem_full,
+                                                 uint64_t* tmem_empty, uint64_t* b_full, uint32_t tmem_base,
+                                                 int num_groups, int stage_bytes) {
+  using S = ConvSmem<BLOCK_N, BLOCK_K>;
+  constexpr int A_STAGE_BYTES = S::A_STAGE_BYTES;
+  constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N);
+  const int STAGES = p.stages;
+  const uint32_t tmem_base_u = __reduce_max_sync(0xffffffffu, tmem_base);      // REDUX writes a uniform register
+  int stage = 0;
+  uint32_t phase = 0;
+  int acc = 0;
+  uint32_t acc_phase = 0;
+  if (p.b_resident && (int)blockIdx.x < num_groups) mbar_wait(b_full, 0);
+  for (int group = blockIdx.x; group < num_groups; group += gridDim.x) {
+    mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+    tcgen05_fence_after();
+    const uint32_t d_tmem = tmem_base_u + (uint32_t)(acc * WAYS * BLOCK_N);
+    for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+      mbar_wait(&full_bar[stage], phase);
+      tcgen05_fence_after();
+      const uint32_t sa = smem_addr + (uint32_t)(stage * stage_bytes);
+      uint64_t a_desc[WAYS];
+#pragma unroll
+      for (int w = 0; w < WAYS; ++w) a_desc[w] = make_smem_desc<S::ROW_BYTES>(sa + (uint32_t)(w * A_STAGE_BYTES));
+      const uint64_t b_desc = p.b_resident
+          ? make_smem_desc<S::ROW_BYTES>(bres_addr + (uint32_t)(kb * S::B_STAGE_BYTES))
+          : make_smem_desc<S::ROW_BYTES>(sa + (uint32_t)(WAYS * A_STAGE_BYTES));
+#pragma unroll
+      for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+        // advance 16 bf16 = 32 bytes inside the swizzle row: +2 in the (>>4) address field;
+        // consecutive MMAs go to different accumulators
+#pragma unroll
+        for (int w = 0; w < WAYS; ++w)
+          umma_bf16_elect(d_tmem + (uint32_t)(w * BLOCK_N), a_desc[w] + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k),
+                          idesc, (kb > 0 || k > 0) ? 1u : 0u);
+      }
+      tcgen05_commit_elect(&empty_bar[stage]);    // frees the stage when these MMAs retire
+      if (++stage == STAGES) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+    tcgen05_commit_elect(&tmem_full[acc]);      // accumulators ready for the epilogue
+    if (++acc == 2) {
+      acc = 0;
+      acc_phase ^= 1;
+    }
+  }
+}
+
 template <int BLOCK_N, int BLOCK_K, int WAYS>
 __global__ void __launch_bounds__(CONV_NT, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -220,52 +273,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
     if (p.mma_converged) {
-      // the whole warp runs the loop (waits, descriptor arithmetic: all uniform); elect.sync inside the two helpers
-      // picks the issuing lane — see umma_bf16_elect.  Everything the MMAs take must be PROVABLY warp-uniform for
-      // ptxas to keep it on the uniform datapath: the TMEM base is a per-thread shared-memory load -> broadcast it.
-      const uint32_t tmem_base_u = __shfl_sync(0xffffffffu, tmem_base, 0);
-      constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      if (p.b_resident && (int)blockIdx.x < num_groups) mbar_wait(b_full, 0);
-      const uint32_t bres_addr = smem_u32(bres);
-      for (int group = blockIdx.x; group < num_groups; group += gridDim.x) {
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-        tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base_u + (uint32_t)(acc * WAYS * BLOCK_N);
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tcgen05_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * stage_bytes);
-          uint64_t a_desc[WAYS];
-#pragma unroll
-          for (int w = 0; w < WAYS; ++w) a_desc[w] = make_smem_desc<S::ROW_BYTES>(sa + (uint32_t)(w * A_STAGE_BYTES));
-          const uint64_t b_desc = p.b_resident
-              ? make_smem_desc<S::ROW_BYTES>(bres_addr + (uint32_t)(kb * S::B_STAGE_BYTES))
-              : make_smem_desc<S::ROW_BYTES>(sa + (uint32_t)(WAYS * A_STAGE_BYTES));
-#pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            // advance 16 bf16 = 32 bytes inside the swizzle row: +2 in the (>>4) address field;
-            // consecutive MMAs go to different accumulators
-#pragma unroll
-            for (int w = 0; w < WAYS; ++w)
-              umma_bf16_elect(d_tmem + (uint32_t)(w * BLOCK_N), a_desc[w] + (uint64_t)(2 * k),
-                        b_desc + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
-          }
-          tcgen05_commit_elect(&empty_bar[stage]);    // frees the stage when these MMAs retire
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
-        }
-        tcgen05_commit_elect(&tmem_full[acc]);      // accumulators ready for the epilogue
-        if (++acc == 2) {
-          acc = 0;
-          acc_phase ^= 1;
-        }
-      }
+      // the whole warp runs the loop (waits, descriptor arithmetic: all uniform); elect.sync inside the helpers picks
+      // the issuing lane.  A separate NON-INLINED function: inside this 12-role kernel ptxas keeps the descriptors in
+      // vector registers and moves them through R2UR for every MMA; compiled on its own the loop stays on the
+      // uniform datapath (bare UTCHMMA / UTCBAR, ~3 instructions per MMA).
+      mma_issue_converged<BLOCK_N, BLOCK_K, WAYS>(p, smem_u32(smem), smem_u32(bres), full_bar, empty_bar, tmem_full,
+                                                  tmem_empty, b_full, tmem_base, num_groups, stage_bytes);
     } else if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N);
       int stage = 0;
