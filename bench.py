@@ -391,6 +391,9 @@ def run_b200(args):
     plan = model.plan_for(dev_in)
     flops_step = plan["flops"]
     conv_bytes = sum(v.get("bytes", 0) for v in plan["info"].values())
+    # what the plan as launched has to move at least (fused inverted residuals: block input + output only)
+    conv_bytes_as_launched = sum(v.get("bytes_fused", v.get("bytes", 0)) for v in plan["info"].values())
+    n_fused = sum(v["kind"].startswith("mbconv") for v in plan["info"].values())
 
     # ---- self-check (before anything is timed) ----
     self_check = None
@@ -507,7 +510,12 @@ def run_b200(args):
                               "normalisation of ALL levels in ONE launch (loss_step_kernel); logits read once")
         traffic, tfile = measured_conv_traffic(name)
         main_rl = dict(rl[c["dominant"]])
-        main_rl.update({"kernel": "conv_igemm_kernel + conv_pair_kernel (+ dwconv3x3 etc.): all conv-stack launches of a step",
+        if n_fused:
+            main_rl["fused_blocks"] = n_fused
+            main_rl["floor_bytes_as_launched"] = conv_bytes_as_launched
+            main_rl["floor_note"] = ("with the fused inverted residuals the expanded tensors never reach DRAM: the HBM floor "
+                                     "of the plan as launched is floor_bytes_as_launched, not work_per_step")
+        main_rl.update({"kernel": "conv_igemm_kernel + conv_pair_kernel + mbconv_kernel (+ dwconv3x3 etc.): all conv-stack launches of a step",
                         "traffic": traffic,
                         "traffic_unit": f"DRAM bytes per step over the conv launches (ncu, profiles/{tfile})" if tfile else None,
                         "flops_per_step": flops_step, "conv_ms_per_step": sec["conv"]})

@@ -226,6 +226,7 @@ class _Engine(torch.nn.Module):
             info[len(steps) - 1] = {"kind": kind, "flops": nflops, "bytes": nbytes}
 
         self._add_raw = add_raw
+        self._last_info = lambda: info[len(steps) - 1]
         feats = self._plan_backbone(packed, H, W, steps, buf, add_conv, add_dw)
         # everything after the backbone may write the loc/conf outputs: the graph is split here, and the second
         # part waits for the consumer of the previous step's outputs (decode/NMS on another stream)
@@ -485,10 +486,17 @@ class _MobileNetV2Backbone:
             args = mb_args(blk, x)
             nfl = ((ex.flops_per_pixel * n * h * w) if ex is not None else 0) + \
                 (dw.flops_per_pixel + pr.flops_per_pixel) * n * ho * wo
-            nby = 2 * (x.numel() * (2 if blk["res"] else 1) + y.numel() + dw.w.numel() + pr.w.numel() +
-                       (ex.w.numel() if ex is not None else 0))
+            # "bytes" stays the UN-FUSED algorithmic figure of SURVEY 8d (what expand / depthwise / project move as
+            # three launches), so the reported roofline fraction is comparable across plans; the fused launch's own
+            # floor (block input + output) is kept next to it
+            wts = dw.w.numel() + pr.w.numel() + (ex.w.numel() if ex is not None else 0)
+            hid_in, hid_out = n * h * w * dw.c, n * ho * wo * dw.c
+            nby = 2 * (x.numel() * (2 if blk["res"] else 1) + (2 * hid_in if ex is not None else 0) + 2 * hid_out +
+                       y.numel() + wts)
             self._add_raw(lambda: K.mbconv(*args, out=y), nfl,
                           kind=f"mbconv s{dw.stride} {cin}->{dw.c}->{pr.cout} @{ho}x{wo}", nbytes=nby)
+            steps_info = self._last_info()
+            steps_info["bytes_fused"] = 2 * (x.numel() * (2 if blk["res"] else 1) + y.numel() + wts)
             return y
 
         fuse = mode != "never"

@@ -171,18 +171,38 @@ class LossStep(object):
         return scalars
 
     def loss_host(self, images, targets):
+        """Asynchronous: returns a pinned [3] tensor that is valid after `sync()`.  Two device staging sets and a copy
+        stream: the host->device copy of this call's batch runs while the previous call's step is still computing
+        (the copy of a 16 x 640 x 640 batch is ~0.45 ms of a 3.9 ms step when serialised behind it)."""
         images, targets = torch.as_tensor(images), torch.as_tensor(targets)
         key = (tuple(images.shape), images.dtype, tuple(targets.shape))
         st = self._stage.get(key)
         if st is None:
-            st = {"img": torch.empty(images.shape, dtype=images.dtype, device=self.device),
-                  "tg": torch.empty(targets.shape, dtype=torch.float32, device=self.device),
-                  "out": torch.empty(3, dtype=torch.float32).pin_memory()}
+            st = {"img": [torch.empty(images.shape, dtype=images.dtype, device=self.device) for _ in range(2)],
+                  "tg": [torch.empty(targets.shape, dtype=torch.float32, device=self.device) for _ in range(2)],
+                  "out": [torch.empty(3, dtype=torch.float32).pin_memory() for _ in range(2)],
+                  "copied": [torch.cuda.Event() for _ in range(2)], "done": [None, None],
+                  "stream": torch.cuda.Stream(device=self.device), "n": 0}
             self._stage[key] = st
-        st["img"].copy_(images, non_blocking=True)
-        st["tg"].copy_(targets, non_blocking=True)
-        st["out"].copy_(self.loss_device(st["img"], st["tg"]), non_blocking=True)
-        return st["out"]
+        i = st["n"] & 1
+        st["n"] += 1
+        main = torch.cuda.current_stream(self.device)
+        pinned = images.is_pinned() and targets.is_pinned()
+        with torch.cuda.stream(st["stream"]):
+            if st["done"][i] is not None:
+                st["stream"].wait_event(st["done"][i])       # the step that last read this staging set has finished
+            st["img"][i].copy_(images, non_blocking=True)
+            st["tg"][i].copy_(targets, non_blocking=True)
+            st["copied"][i].record(st["stream"])
+        if not pinned:
+            # a pageable source is staged by the driver: the caller may reuse its buffer as soon as we return only if
+            # the copy has completed (same guard as SSDDetector.detect_host)
+            st["copied"][i].synchronize()
+        main.wait_event(st["copied"][i])
+        st["out"][i].copy_(self.loss_device(st["img"][i], st["tg"][i]), non_blocking=True)
+        st["done"][i] = torch.cuda.Event()
+        st["done"][i].record(main)
+        return st["out"][i]
 
     def sync(self):
         torch.cuda.current_stream(self.device).synchronize()

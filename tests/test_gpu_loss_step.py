@@ -194,3 +194,47 @@ def test_loss_step_host_api_matches_device_path(P):
     loc, conf = step.model(x.cuda())
     sc, _ = P.fused_loss_step(loc, conf, tg.cuda(), step.anchors, 20, "FocalLoss", "SmoothL1Loss")
     assert torch.equal(got, sc.cpu()) and got[2] >= 4 and torch.isfinite(got).all()
+
+
+@pytest.mark.parametrize("pinned", [True, False])
+def test_loss_step_host_api_pipelined_batches(P, pinned):
+    """[r2] loss_host overlaps the H2D copy of call i with the step of call i-1 (copy stream, two staging sets):
+    five different batches issued back to back without a sync give exactly the per-batch results of the synchronous
+    device path, from pinned and from pageable host buffers (the caller reuses ONE pageable buffer: the call must not
+    return before that source has been consumed)."""
+    from ssds_pytorch_b200 import synth
+    fl = [[3, 4, 5, "Conv:S"], [128, 256, 512, 256]]
+    cfg = {"MODEL": {"SSDS": "SSD", "NETS": "ResNet18", "IMAGE_SIZE": [160, 160], "NUM_CLASSES": 20,
+                     "FEATURE_LAYER": fl, "SIZES": [[2.0, 2.828]] * 4, "ASPECT_RATIOS": [[1, 2, 0.5]] * 4},
+           "DATASET": {"PREPROC": {"MEAN": 0, "STD": 255}}}
+    sd = synth.synthetic_state_dict("ResNet18", fl, [6] * 4, 20, seed=3, style="test")
+    step = P.LossStep(cfg, sd, use_graph=True)
+    g = torch.Generator().manual_seed(10)
+    xs = [torch.randint(0, 256, (3, 160, 160, 3), generator=g, dtype=torch.uint8) for _ in range(5)]
+    tgs = []
+    for i in range(5):
+        t = synth.synthetic_targets(3, T=8, seed=20 + i)
+        t[..., :4] *= 0.25
+        tgs.append(t)
+    want = []
+    for x, t in zip(xs, tgs):
+        want.append(step.loss_device(x.cuda(), t.cuda()).cpu().clone())
+    outs = []
+    if pinned:
+        for x, t in zip(xs, tgs):
+            outs.append(step.loss_host(x.pin_memory(), t.pin_memory()))
+            if len(outs) >= 2:                      # the result tensors alternate between two pinned buffers
+                step.sync()
+                outs[-2] = outs[-2].clone()
+    else:
+        hx, ht = torch.empty_like(xs[0]), torch.empty_like(tgs[0])
+        for x, t in zip(xs, tgs):
+            hx.copy_(x)
+            ht.copy_(t)
+            outs.append(step.loss_host(hx, ht))
+            step.sync()
+            outs[-1] = outs[-1].clone()
+    step.sync()
+    for o, w in zip(outs, want):
+        assert torch.equal(o.clone(), w)
+    assert len({tuple(w.tolist()) for w in want}) == 5

@@ -21,7 +21,7 @@ for r in rows[1:]:
 items = list(by.values())
 idx = [i for i, d in enumerate(items) if "pack_image" in d["name"]]
 step = items[idx[-2]:idx[-1]]                      # one complete step between two image-packing launches
-conv = [d for d in step if any(k in d["name"] for k in ("conv_igemm", "conv_pair", "dwconv", "maxpool", "upsample",
+conv = [d for d in step if any(k in d["name"] for k in ("conv_igemm", "conv_pair", "dwconv", "mbconv", "maxpool", "upsample",
                                                          "bifpn_fuse"))]
 tot_t = sum(d["gpu__time_duration.sum"] for d in step) / 1e3
 res = {"config": name,
