@@ -45,7 +45,7 @@ typedef enum {
 
 #define SSDSB_MAX_LEVELS 8
 
-#define SSDSB_ABI_VERSION 201
+#define SSDSB_ABI_VERSION 202
 
 SSDSB_API int ssdsb_version(void);          /* == SSDSB_ABI_VERSION of the header the library was built from */
 
@@ -340,6 +340,11 @@ SSDSB_API int ssdsb_pack_image_s2d(const void* d_src, int src_format, int N, int
 /* 3x3 / stride 2 / pad 1 max pooling on NHWC bf16 (resnet.py:45 `self.maxpool`). C % 8 == 0. */
 SSDSB_API int ssdsb_maxpool3x3s2_nhwc_bf16(const void* d_x, int N, int H, int W, int C, void* d_y,
                                            void* stream);
+/* 5x5 / stride 1 / pad 2 max-pool, NHWC bf16, with channel strides (elements) for input and output so that it can
+ * read one channel slice of a concatenated buffer and write another: YOLOv4's SPP block (reference
+ * ssds/modeling/ssds/yolo.py:161-184, pools of 5 / 9 / 13 concatenated after x) is three cascaded calls. */
+SSDSB_API int ssdsb_maxpool5x5s1_nhwc_bf16(const void* d_x, int N, int H, int W, int C, int x_cstride, void* d_y,
+                                           int y_cstride, void* stream);
 
 /* Depthwise 3x3 / pad 1 / stride 1|2 conv + folded BN + activation (relu: 0 none, 1 ReLU, 2 ReLU6) on
  * NHWC bf16 — torchvision InvertedResidual's depthwise stage (reference nets/mobilenet.py:78) and

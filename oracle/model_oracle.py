@@ -203,6 +203,59 @@ def yolov3_resnet_forward(sd, x, feature_layer, training=False, policy="fp32"):
     return tuple(loc), tuple(conf)
 
 
+def yolov4_resnet_forward(sd, x, feature_layer, training=False, policy="fp32"):
+    """reference yolo.py:249-323 (YOLOV4.forward): transforms (the last one with the SPP block, yolo.py:161-184:
+    max-pools of 5 / 9 / 13, stride 1, concatenated after x), PANModule.forward (yolo.py:222-246: top-down with
+    nearest-2x upsample + concat + ConvBNReLUx2, then bottom-up with stride-2 conv + concat + ConvBNReLUx2),
+    'Conv:S' extras chained from the last PAN level, per-level heads.  bf16 policy: every conv output is stored
+    (max-pooling and concatenation of stored values are exact)."""
+    layers = feature_layer[0]
+    stacks = 1 if len(feature_layer) == 2 else feature_layer[2]
+    outputs = [l for l in layers if isinstance(l, int)]
+    feats = resnet_features(sd, x, outputs, policy)
+    n = len(feats)
+
+    def cbr(t, conv, bn, stride=1, pad=1):
+        return _r(_conv_bn(t, sd, conv, bn, stride, pad, True, policy), policy)
+
+    def x2(t, p):
+        t = cbr(t, p + ".0.weight", p + ".1", 1, 0)
+        return cbr(t, p + ".3.weight", p + ".4", 1, 1)
+
+    xx = []
+    for i in range(n):
+        if i == n - 1:
+            t = cbr(feats[i], f"transforms.{i}.0.0.weight", f"transforms.{i}.0.1")
+            pools = [t] + [F.max_pool2d(t, kernel_size=k, stride=1, padding=(k - 1) // 2) for k in (5, 9, 13)]
+            t = cbr(torch.cat(pools, dim=1), f"transforms.{i}.2.0.weight", f"transforms.{i}.2.1")
+        else:
+            t = cbr(feats[i], f"transforms.{i}.0.weight", f"transforms.{i}.1")
+        xx.append(t)
+    for st in range(stacks):
+        for i in range(n - 1, 0, -1):
+            t = cbr(xx[i], f"fpn.{st}.top-down-{i}-to-{i - 1}.0.weight", f"fpn.{st}.top-down-{i}-to-{i - 1}.1")
+            xx[i - 1] = x2(torch.cat((xx[i - 1], F.interpolate(t, scale_factor=2, mode="nearest")), dim=1),
+                           f"fpn.{st}.top-down-{i - 1}")
+        for i in range(0, n - 1):
+            t = cbr(xx[i], f"fpn.{st}.bottom-up-{i}-to-{i + 1}.0.weight", f"fpn.{st}.bottom-up-{i}-to-{i + 1}.1", 2, 1)
+            xx[i + 1] = x2(torch.cat((xx[i + 1], t), dim=1), f"fpn.{st}.bottom-up-{i + 1}")
+    t, j = xx[-1], 0
+    while f"extras.{j}.0.weight" in sd:
+        t = cbr(t, f"extras.{j}.0.weight", f"extras.{j}.1", 2, 1)
+        xx.append(t)
+        j += 1
+    loc, conf = [], []
+    for i, f in enumerate(xx):
+        outs = []
+        for tower in ("loc", "conf"):
+            h = cbr(f, f"{tower}.{i}.0.0.weight", f"{tower}.{i}.0.1")
+            outs.append(_conv_bn(h, sd, f"{tower}.{i}.1.weight", None, 1, 1, False, policy,
+                                 bias=sd[f"{tower}.{i}.1.bias"]))
+        loc.append(outs[0])
+        conf.append(outs[1] if training else torch.sigmoid(outs[1]))
+    return tuple(loc), tuple(conf)
+
+
 def ssd_mobilenetv2_forward(sd, x, feature_layer, training=False, policy="fp32"):
     """SSD.forward (ssd.py:42-74) over the MobileNetV2 backbone."""
     return ssd_resnet_forward(sd, x, feature_layer, training, policy, backbone="mobilenetv2")

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libssdsb200.so")
 
 SSDSB_MAX_LEVELS = 8
-ABI_VERSION = 201        # == ssdsb_version(); bumped whenever include/ssdsb200.h changes incompatibly
+ABI_VERSION = 202        # == ssdsb_version(); bumped whenever include/ssdsb200.h changes incompatibly
 
 
 class Level(C.Structure):
@@ -105,6 +105,7 @@ def _load():
         "ssdsb_conv2d_bf16": (i, [C.POINTER(ConvDesc), vp, vp, vp, vp, vp, vp, vp]),
         "ssdsb_pack_image_s2d": (i, [vp, i, i, i, i, f, f, i, i, vp, vp]),
         "ssdsb_maxpool3x3s2_nhwc_bf16": (i, [vp, i, i, i, i, vp, vp]),
+        "ssdsb_maxpool5x5s1_nhwc_bf16": (i, [vp, i, i, i, i, i, vp, i, vp]),
         "ssdsb_upsample2x_add_nhwc_bf16": (i, [vp, vp, i, i, i, i, vp]),
         "ssdsb_upsample2x_concat_nhwc_bf16": (i, [vp, vp, i, i, i, i, i, vp, vp]),
         "ssdsb_dwconv3x3_nhwc_bf16": (i, [vp, vp, vp, i, i, i, i, i, i, vp, vp]),

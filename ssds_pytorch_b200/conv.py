@@ -205,6 +205,16 @@ def pack_dw_weight(w_folded, c_pad=None):
     return out.to(torch.bfloat16).contiguous()
 
 
+def maxpool5x5s1(x, out):
+    """5x5 / stride 1 / pad 2 max-pool, NHWC bf16; x and out may be channel slices of wider buffers (SPP concat)."""
+    N, H, W, Cc = x.shape
+    assert out.shape == x.shape and x.stride(3) == 1 and out.stride(3) == 1
+    with torch.cuda.device(x.device):
+        check(lib.ssdsb_maxpool5x5s1_nhwc_bf16(ptr(x), N, H, W, Cc, x.stride(2), ptr(out), out.stride(2), stream_ptr()),
+              "maxpool5x5s1")
+    return out
+
+
 def dwconv3x3(x, w, bias, stride=1, relu=2, out=None):
     """NHWC bf16 depthwise 3x3/pad 1 + bias + activation (0 none, 1 ReLU, 2 ReLU6)."""
     N, H, W, Cc = x.shape

@@ -516,10 +516,64 @@ inline void dw_pick_chunks(long long base_threads, int Ho, int sms, int* rows_pe
   *chunks = (Ho + best_rp - 1) / best_rp;
 }
 
+// 5x5 / stride 1 / pad 2 max-pool on NHWC bf16 with independent channel strides for input and output: the SPP
+// block of YOLOv4 (reference ssds/modeling/ssds/yolo.py:161-184: max-pools of 5, 9, 13 concatenated after x) is
+// three cascaded calls (5 o 5 = 9, 5 o 9 = 13 for stride-1 max-pools with -inf padding), each reading one channel
+// slice of the concatenated buffer and writing the next.  One thread = one output pixel x 8 channels; the maps are
+// the smallest backbone level (<= 40 x 40), so 25 16-byte loads per thread from L1/L2 are not worth tiling.
+__global__ void __launch_bounds__(256)
+maxpool5x5s1_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int C8, int x_cs,
+                    __nv_bfloat16* __restrict__ y, int y_cs) {
+  const size_t total = (size_t)N * H * W * C8;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C8);
+    const int w = (int)((i / C8) % W);
+    const int h = (int)((i / ((size_t)C8 * W)) % H);
+    const int n = (int)(i / ((size_t)C8 * W * H));
+    float m[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) m[e] = -INFINITY;
+    for (int dy = -2; dy <= 2; ++dy) {
+      const int hh = h + dy;
+      if (hh < 0 || hh >= H) continue;
+      for (int dx = -2; dx <= 2; ++dx) {
+        const int ww = w + dx;
+        if (ww < 0 || ww >= W) continue;
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + (((size_t)n * H + hh) * W + ww) * x_cs) + c);
+        const uint32_t vs[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          m[e * 2] = fmaxf(m[e * 2], __uint_as_float(vs[e] << 16));
+          m[e * 2 + 1] = fmaxf(m[e * 2 + 1], __uint_as_float(vs[e] & 0xffff0000u));
+        }
+      }
+    }
+    *(reinterpret_cast<uint4*>(y + (((size_t)n * H + h) * W + w) * y_cs) + c) =
+        make_uint4(pack2(m[0], m[1]), pack2(m[2], m[3]), pack2(m[4], m[5]), pack2(m[6], m[7]));
+  }
+}
+
 }  // namespace
 }  // namespace ssdsb
 
 using namespace ssdsb;
+
+extern "C" int ssdsb_maxpool5x5s1_nhwc_bf16(const void* d_x, int N, int H, int W, int C, int x_cstride, void* d_y,
+                                            int y_cstride, void* stream) {
+  SSDSB_REQUIRE(d_x && d_y, "maxpool5x5s1: NULL argument");
+  SSDSB_REQUIRE(N >= 1 && H >= 1 && W >= 1 && C >= 8 && C % 8 == 0, "maxpool5x5s1: bad shape");
+  SSDSB_REQUIRE(x_cstride >= C && y_cstride >= C && x_cstride % 8 == 0 && y_cstride % 8 == 0,
+                "maxpool5x5s1: channel strides must be >= C and multiples of 8");
+  SSDSB_REQUIRE((((uintptr_t)d_x | (uintptr_t)d_y) & 15) == 0, "maxpool5x5s1: pointers must be 16-byte aligned");
+  const size_t total = (size_t)N * H * W * (C / 8);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  maxpool5x5s1_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(d_x), N, H, W,
+                                                                C / 8, x_cstride,
+                                                                reinterpret_cast<__nv_bfloat16*>(d_y), y_cstride);
+  SSDSB_LAUNCH_CHECK("maxpool5x5s1_kernel");
+  return SSDSB_OK;
+}
 
 extern "C" int ssdsb_bifpn_fuse_nhwc_bf16(const void* d_a, const void* d_b, const void* d_c, int mode,
                                           float w0, float w1, float w2, int N, int H, int W, int C,

@@ -863,6 +863,138 @@ class _YOLOV3Neck:
         return locs, confs
 
 
+class _YOLOV4Neck(_YOLOV3Neck):
+    """YOLOv4 neck + heads (reference ssds/modeling/ssds/yolo.py:161-392): per backbone level transforms.{i} =
+    ConvBNReLU 3x3 (depth -> depth/2), the last one followed by the SPP block (max-pools of 5 / 9 / 13 concatenated
+    after x: three cascaded 5x5 pools, each reading one channel slice of the 4c buffer and writing the next) and a
+    second 3x3 conv; a stack of PANModules (top-down: 3x3 conv + nearest-2x upsample concatenated AFTER the finer
+    level + ConvBNReLUx2; bottom-up: 3x3 stride-2 conv concatenated AFTER the coarser level + ConvBNReLUx2);
+    'Conv:S' extras chained from the last PAN level; per-level heads as in YOLOv3.  Concatenations cost no launch
+    except the upsampling one: every producer writes straight into its channel slice of the concatenated buffer
+    (conv `out_cstride`), and the convs read channel slices through `x_cstride`."""
+
+    def _build_neck(self, sd, feature_layer):
+        dev = self.device
+        layers = feature_layer[0]
+        self.stacks = 1 if len(feature_layer) == 2 else feature_layer[2]
+        if self.stacks != 1:
+            raise NotImplementedError("YOLOV4 with more than one PAN stack is not on the tcgen05 conv stack yet")
+        n = len(self.outputs)
+        cbr = lambda p, q, stride=1, pad=1: _Conv(sd[p + ".weight"], _bn(sd, q), None, stride, pad, True, dev)
+        self.transforms = []
+        for i in range(n):
+            if i == n - 1:
+                self.transforms.append([cbr(f"transforms.{i}.0.0", f"transforms.{i}.0.1"),
+                                        cbr(f"transforms.{i}.2.0", f"transforms.{i}.2.1")])
+            else:
+                self.transforms.append([cbr(f"transforms.{i}.0", f"transforms.{i}.1")])
+        self.pan = []
+        for st in range(self.stacks):
+            td, bu = {}, {}
+            for i in range(n - 1, 0, -1):
+                p = f"fpn.{st}.top-down-{i - 1}"
+                td[i] = (cbr(f"fpn.{st}.top-down-{i}-to-{i - 1}.0", f"fpn.{st}.top-down-{i}-to-{i - 1}.1"),
+                         cbr(p + ".0", p + ".1", 1, 0), cbr(p + ".3", p + ".4"))
+            for i in range(0, n - 1):
+                p = f"fpn.{st}.bottom-up-{i + 1}"
+                bu[i] = (cbr(f"fpn.{st}.bottom-up-{i}-to-{i + 1}.0", f"fpn.{st}.bottom-up-{i}-to-{i + 1}.1", 2, 1),
+                         cbr(p + ".0", p + ".1", 1, 0), cbr(p + ".3", p + ".4"))
+            self.pan.append((td, bu))
+        self.extras = []
+        j = 0
+        for layer in layers:
+            if isinstance(layer, int):
+                continue
+            if layer != "Conv:S":
+                raise ValueError(layer + " does not support by YOLO")            # yolo.py:360
+            self.extras.append(cbr(f"extras.{j}.0", f"extras.{j}.1", 2, 1))
+            j += 1
+        self.towers, self.head_loc, self.head_conf = [], [], []
+        for l in range(len(layers)):
+            w0 = torch.cat([sd[f"loc.{l}.0.0.weight"], sd[f"conf.{l}.0.0.weight"]], 0)
+            bn0 = tuple(torch.cat([a, b], 0) if isinstance(a, torch.Tensor) else a
+                        for a, b in zip(_bn(sd, f"loc.{l}.0.1"), _bn(sd, f"conf.{l}.0.1")))
+            self.towers.append(_Conv(w0, bn0, None, 1, 1, True, dev))
+            hl = _Conv(sd[f"loc.{l}.1.weight"], None, sd[f"loc.{l}.1.bias"], 1, 1, False, dev)
+            hl.n_loc = hl.cout
+            hc = _Conv(sd[f"conf.{l}.1.weight"], None, sd[f"conf.{l}.1.bias"], 1, 1, False, dev)
+            hc.n_loc = 0
+            self.head_loc.append(hl)
+            self.head_conf.append(hc)
+
+    def _plan_neck(self, feats, steps, buf, add_conv, add_head):
+        n = len(feats)
+        L = n + len(self.extras)
+        locs, confs = [None] * L, [None] * L
+        dev = self.device
+
+        def record_heads(l, f, br):
+            with steps.on(br):
+                t = add_conv(self.towers[l], f)                                   # [.., 2c]: loc half | conf half
+                c = t.shape[3] // 2
+                nb, fh, fw, _ = f.shape
+                loc = torch.empty((nb, self.head_loc[l].cout, fh, fw), dtype=torch.float32, device=dev)
+                conf = torch.empty((nb, self.head_conf[l].cout, fh, fw), dtype=torch.float32, device=dev)
+                dummy = torch.empty((1,), dtype=torch.float32, device=dev)
+                add_head(t[..., :c], self.head_loc[l], loc=loc, conf=dummy)
+                add_head(t[..., c:], self.head_conf[l], loc=dummy, conf=conf)
+            locs[l], confs[l] = loc, conf
+
+        # the concatenated input of every bottom-up ConvBNReLUx2 (level j >= 1): [.., xx[j] | stride-2 conv of xx[j-1]];
+        # whoever produces xx[j] writes it straight into the first half
+        def cat_for(t):
+            nb, h, w, c = t.shape
+            return buf(nb, h, w, 2 * c)
+
+        xx = [None] * n
+        for i in range(n):
+            tr = self.transforms[i]
+            nb, h, w, _ = feats[i].shape
+            c = tr[0].cout
+            if i == n - 1:
+                spp = buf(nb, h, w, 4 * c)                                       # yolo.py:161-184: x | pool5 | pool9 | pool13
+                add_conv(tr[0], feats[i], out=spp[..., :c])
+                for k in range(3):
+                    steps.append(lambda a=spp[..., k * c:(k + 1) * c], o=spp[..., (k + 1) * c:(k + 2) * c]:
+                                 K.maxpool5x5s1(a, o))
+                top_cat = buf(nb, h, w, 2 * c) if n > 1 else None
+                xx[i] = add_conv(tr[1], spp, out=top_cat[..., :c] if top_cat is not None else None)
+                cats = {i: top_cat}
+            else:
+                xx[i] = add_conv(tr[0], feats[i])
+        for st, (td, bu) in enumerate(self.pan):
+            if st > 0:
+                cats = {}
+            for i in range(n - 1, 0, -1):                                         # top-down (yolo.py:225-236)
+                t = add_conv(td[i][0], xx[i])
+                nb, h, w, cf = xx[i - 1].shape
+                cat = buf(nb, h, w, cf + t.shape[3])
+                steps.append(lambda f=xx[i - 1], cc=t, o=cat: K.upsample2x_concat(f, cc, out=o))
+                y = add_conv(td[i][1], cat)
+                if i - 1 >= 1:                                                     # becomes xx[i-1] of a bottom-up concat
+                    cats[i - 1] = buf(nb, h, w, 2 * td[i][2].cout)
+                    xx[i - 1] = add_conv(td[i][2], y, out=cats[i - 1][..., :td[i][2].cout])
+                else:
+                    xx[i - 1] = add_conv(td[i][2], y)
+            for i in range(0, n - 1):                                             # bottom-up (yolo.py:238-246)
+                cat = cats.get(i + 1)
+                c = bu[i][0].cout
+                if cat is None:                                                    # (only after a previous PAN stack)
+                    nb, h, w, _ = xx[i + 1].shape
+                    cat = buf(nb, h, w, 2 * c)
+                    steps.append(lambda s_=xx[i + 1], o=cat[..., :c]: o.copy_(s_))
+                add_conv(bu[i][0], xx[i], out=cat[..., c:])
+                y = add_conv(bu[i][1], cat)
+                xx[i + 1] = add_conv(bu[i][2], y)
+        t = xx[-1]
+        for e in self.extras:                                                      # yolo.py:303-306
+            t = add_conv(e, t)
+            xx.append(t)
+        for l, f in enumerate(xx):
+            record_heads(l, f, steps.fork() if l != len(xx) - 1 else 0)
+        return locs, confs
+
+
 class SSDResNet(_SSDNeck, _ResNetBackbone, _Engine):
     """SSD + ResNet18/34/50/101/152 (reference cfg SSDS='SSD', NETS='ResNet*')."""
 
@@ -891,7 +1023,11 @@ class YOLOV3ResNet(_YOLOV3Neck, _ResNetBackbone, _Engine):
     """YOLOV3 + ResNet18/34/50/... (reference cfg SSDS='YOLOV3'; experiments/cfgs/tests/test.yml is ResNet18 @320)."""
 
 
-ENGINES = {("YOLOV3", "ResNet"): YOLOV3ResNet, ("SSD", "ResNet"): SSDResNet, ("SSDFPN", "ResNet"): SSDFPNResNet,
+class YOLOV4ResNet(_YOLOV4Neck, _ResNetBackbone, _Engine):
+    """YOLOV4 + ResNet (reference cfg SSDS='YOLOV4': SPP + PAN neck, yolo.py:161-392)."""
+
+
+ENGINES = {("YOLOV3", "ResNet"): YOLOV3ResNet, ("YOLOV4", "ResNet"): YOLOV4ResNet, ("SSD", "ResNet"): SSDResNet, ("SSDFPN", "ResNet"): SSDFPNResNet,
            ("SSD", "MobileNetV2"): SSDMobileNetV2, ("SSDBIFPN", "ResNet"): SSDBiFPNResNet,
            ("SSDBIFPN", "RegNetX032"): SSDBiFPNRegNetX, ("SSDFPN", "RegNetX032"): SSDFPNRegNetX}
 

@@ -150,6 +150,8 @@ def model_shapes(ssds, nets, feature_layer, number_box, num_classes):
         return back + ssd_neck_shapes(feature_layer, number_box, num_classes)
     if ssds == "YOLOV3":
         return back + yolov3_neck_shapes(feature_layer, number_box, num_classes)
+    if ssds == "YOLOV4":
+        return back + yolov4_neck_shapes(feature_layer, number_box, num_classes)
     stacks = 0
     if ssds == "SSDBIFPN":
         stacks = 1 if len(feature_layer) == 2 else feature_layer[2]
@@ -191,6 +193,59 @@ def yolov3_neck_shapes(feature_layer, number_box, num_classes):
             out.append((f"extras.{i}.3.weight", (cout, cout // 2, 3, 3))); _bn_keys(out, f"extras.{i}.4", cout)
         else:
             out.append((f"extras.{i}.0.weight", (cout, cin, 3, 3))); _bn_keys(out, f"extras.{i}.1", cout)
+    for tower, per in (("loc", 4), ("conf", num_classes)):
+        for l, (c, nb) in enumerate(zip(heads, number_box)):
+            out.append((f"{tower}.{l}.0.0.weight", (c, c, 3, 3))); _bn_keys(out, f"{tower}.{l}.0.1", c)
+            out.append((f"{tower}.{l}.1.weight", (nb * per, c, 3, 3)))
+            out.append((f"{tower}.{l}.1.bias", (nb * per,)))
+    return out
+
+
+def yolov4_neck_shapes(feature_layer, number_box, num_classes):
+    """YOLOV4.add_extras (yolo.py:325-392): transforms.{i} = ConvBNReLU(depth, depth/2, 3) per backbone level, the
+    last one Sequential(ConvBNReLU(depth, depth/2, 3), SPPModule(3), ConvBNReLU(2*depth, depth/2, 3)); extras.{j} =
+    ConvBNReLU stride 2 per 'Conv:S'; fpn.{s} = PANModule(depths/2) (yolo.py:187-246: top-down-{i}-to-{i-1} 3x3 +
+    ConvBNReLUx2, then bottom-up-{i}-to-{i+1} 3x3 stride 2 + ConvBNReLUx2); heads as in YOLOV3.  Key order =
+    registration order of the reference modules: transforms, extras, fpn, loc, conf."""
+    layers, depths = feature_layer[0], feature_layer[1]
+    stacks = 1 if len(feature_layer) == 2 else feature_layer[2]
+    ints = [l for l in layers if isinstance(l, int)]
+    out, heads, chans = [], [], []
+    in_ch, ei = None, 0
+    extras = []
+    for idx, (layer, depth) in enumerate(zip(layers, depths)):
+        if isinstance(layer, int):
+            i = len(chans)
+            chans.append(depth // 2)
+            if layer == ints[-1]:
+                out.append((f"transforms.{i}.0.0.weight", (depth // 2, depth, 3, 3))); _bn_keys(out, f"transforms.{i}.0.1", depth // 2)
+                out.append((f"transforms.{i}.2.0.weight", (depth // 2, depth * 2, 3, 3))); _bn_keys(out, f"transforms.{i}.2.1", depth // 2)
+            else:
+                out.append((f"transforms.{i}.0.weight", (depth // 2, depth, 3, 3))); _bn_keys(out, f"transforms.{i}.1", depth // 2)
+            in_ch = depth // 2
+        elif layer == "Conv:S":
+            extras.append((in_ch, depth))
+            in_ch = depth
+        else:
+            raise ValueError(layer + " does not support by YOLO")
+        heads.append(in_ch)
+    for j, (cin, cout) in enumerate(extras):
+        out.append((f"extras.{j}.0.weight", (cout, cin, 3, 3))); _bn_keys(out, f"extras.{j}.1", cout)
+    n = len(chans)
+
+    def x2(prefix, cin, cout):
+        out.append((prefix + ".0.weight", (cout // 2, cin, 1, 1))); _bn_keys(out, prefix + ".1", cout // 2)
+        out.append((prefix + ".3.weight", (cout, cout // 2, 3, 3))); _bn_keys(out, prefix + ".4", cout)
+
+    for st in range(stacks):
+        for i in range(n - 1, 0, -1):
+            pre = f"fpn.{st}.top-down-{i}-to-{i - 1}"
+            out.append((pre + ".0.weight", (chans[i - 1], chans[i], 3, 3))); _bn_keys(out, pre + ".1", chans[i - 1])
+            x2(f"fpn.{st}.top-down-{i - 1}", chans[i - 1] * 2, chans[i - 1])
+        for i in range(0, n - 1):
+            pre = f"fpn.{st}.bottom-up-{i}-to-{i + 1}"
+            out.append((pre + ".0.weight", (chans[i + 1], chans[i], 3, 3))); _bn_keys(out, pre + ".1", chans[i + 1])
+            x2(f"fpn.{st}.bottom-up-{i + 1}", chans[i + 1] * 2, chans[i + 1])
     for tower, per in (("loc", 4), ("conf", num_classes)):
         for l, (c, nb) in enumerate(zip(heads, number_box)):
             out.append((f"{tower}.{l}.0.0.weight", (c, c, 3, 3))); _bn_keys(out, f"{tower}.{l}.0.1", c)
@@ -306,7 +361,7 @@ def synthetic_state_dict(nets, feature_layer, number_box, num_classes, seed=0, s
     shapes = model_shapes(ssds, nets, feature_layer, number_box, num_classes)
     bn_prefixes = {k.rsplit(".", 1)[0] for k, _ in shapes if k.endswith("running_mean")}
     fpn_like = ssds.upper() != "SSD"
-    if ssds.upper() == "YOLOV3":
+    if ssds.upper() in ("YOLOV3", "YOLOV4"):
         head_final = {k for k, _ in shapes if k.startswith(("loc.", "conf.")) and k.split(".")[2] == "1"}
     else:
         head_final = {k for k, _ in shapes if k.startswith(("loc.", "conf.")) and

@@ -145,8 +145,49 @@ def main_yolo():
     print("wrote", out, os.path.getsize(out) // 1024, "KiB")
 
 
+def main_yolo4():
+    """YOLOV4 + ResNet18 (SPP + PAN neck, one 'Conv:S' extra level) through the reference's create_model ->
+    model_yolo4.npz."""
+    G = {}
+    fl = [[3, 4, 5, "Conv:S"], [128, 256, 512, 256]]
+    sizes = [[2.0, 2.828]] * 4
+    ratios = [[1, 2, 0.5]] * 4
+    image, ncls, B, nb = [128, 160], 20, 2, [6] * 4
+    cfg, model = build("ResNet18", fl, [list(s_) for s_ in sizes], ratios, image, ncls, "YOLOV4")
+    ref_sd = model.state_dict()
+    shapes = synth.model_shapes("YOLOV4", "ResNet18", fl, nb, ncls)
+    assert [k for k, _ in shapes] == list(ref_sd.keys()), "state_dict key order differs"
+    for k, s_ in shapes:
+        assert tuple(ref_sd[k].shape) == tuple(s_), (k, ref_sd[k].shape, s_)
+    sd = synth.synthetic_state_dict("ResNet18", fl, nb, ncls, seed=11, style="test", ssds="YOLOV4")
+    model.load_state_dict(sd)
+    model.eval()
+    anchors = model_builder.create_anchors(cfg, model, image)
+    x = torch.rand((B, 3, image[0], image[1]), generator=torch.Generator().manual_seed(1234))
+    with torch.no_grad():
+        loc, conf = model(x)
+    rcfg.cfg.POST_PROCESS.MAX_DETECTIONS_PER_LEVEL = 300
+    decoder = model_builder.create_decoder(rcfg.cfg.POST_PROCESS)
+    with torch.no_grad():
+        det = decoder(loc, conf, anchors)
+    tag = "yolo4"
+    G[tag + "_image"] = np.asarray(image)
+    G[tag + "_x"] = x.numpy().astype(np.float16)
+    G[tag + "_strides"] = np.asarray(list(anchors.keys()))
+    for i, (l, c) in enumerate(zip(loc, conf)):
+        G[f"{tag}_loc{i}"] = l.numpy()
+        G[f"{tag}_conf{i}"] = c.numpy()[:, ::CONF_CH_STRIDE]
+    G[tag + "_det_scores"], G[tag + "_det_boxes"], G[tag + "_det_classes"] = [d.numpy() for d in det]
+    out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "model_yolo4.npz")
+    np.savez_compressed(out, **G)
+    print(tag, "levels", [tuple(c.shape) for c in conf], "dets>0:", int((det[0] > 0).sum()))
+    print("wrote", out, os.path.getsize(out) // 1024, "KiB")
+
+
 if __name__ == "__main__":
-    if "--yolo" in sys.argv:
+    if "--yolo4" in sys.argv:
+        main_yolo4()
+    elif "--yolo" in sys.argv:
         main_yolo()
     else:
         main()

@@ -231,6 +231,23 @@ def test_dwconv3x3_stream_any_chunking(K, case, monkeypatch):
     monkeypatch.delenv("SSDSB_DW_ROWS", raising=False)
 
 
+@pytest.mark.parametrize("case", [(2, 10, 12, 64), (1, 4, 5, 256), (3, 20, 20, 32), (1, 1, 1, 8)])
+def test_maxpool5x5s1_spp_cascade(K, case):
+    """[r2] YOLOv4's SPP block (yolo.py:161-184): x | maxpool5 | maxpool9 | maxpool13 concatenated = three cascaded
+    5x5 / stride-1 pools between channel slices of one buffer; exact (max of bf16 values)."""
+    N, H, W, Cc = case
+    g = torch.Generator().manual_seed(sum(case))
+    x = torch.randn((N, H, W, Cc), generator=g).to(torch.bfloat16).cuda()
+    cat = torch.full((N, H, W, 4 * Cc), 9.0, dtype=torch.bfloat16, device="cuda")
+    cat[..., :Cc] = x
+    for k in range(3):
+        K.maxpool5x5s1(cat[..., k * Cc:(k + 1) * Cc], cat[..., (k + 1) * Cc:(k + 2) * Cc])
+    torch.cuda.synchronize()
+    xn = x.float().permute(0, 3, 1, 2)
+    ref = torch.cat([xn] + [F.max_pool2d(xn, kernel_size=kk, stride=1, padding=kk // 2) for kk in (5, 9, 13)], dim=1)
+    assert torch.equal(cat.float(), ref.permute(0, 2, 3, 1))
+
+
 MBCONV = [
     # N, H, W, Cin, hid, Cout, stride, residual — the MobileNetV2-SSD 300x300 block shapes (channels padded to 32
     # as the plan stores them; hid == Cin and no expand layer for the first block) + ragged odd cases

@@ -86,7 +86,7 @@ def _match(s, b, c, rs, rb, rc, px=1.5, rel=0.05):
     return found, total
 
 
-@pytest.mark.parametrize("which", ["test.yml", "cfg1b"])
+@pytest.mark.parametrize("which", ["test.yml", "cfg1b", "yolov4"])
 def test_plumbing_config_end_to_end_vs_reference(R, which):
     """BASELINE configs[0]: the reference's CPU plumbing config.  The reference model is built by its own
     create_model (its own random init, then BN statistics randomised so that folding is exercised), its
@@ -97,6 +97,12 @@ def test_plumbing_config_end_to_end_vs_reference(R, which):
         import yaml
         cfg = yaml.safe_load(open(yml))
         model_cfg = cfg["MODEL"]
+    elif which == "yolov4":
+        # [r2] the SPP + PAN neck (yolo.py:161-392) with one 'Conv:S' extra level
+        model_cfg = dict(SSDS="YOLOV4", NETS="ResNet18", IMAGE_SIZE=[256, 320], NUM_CLASSES=20,
+                         FEATURE_LAYER=[[3, 4, 5, "Conv:S"], [128, 256, 512, 256]],
+                         SIZES=[[2.0, 2.828]] * 4, ASPECT_RATIOS=[[1, 2, 0.5]] * 4)
+        cfg = {"MODEL": model_cfg}
     else:
         model_cfg = dict(SSDS="SSD", NETS="MobileNetV2", IMAGE_SIZE=[300, 300], NUM_CLASSES=80,
                          FEATURE_LAYER=[[5, 7, "Conv:S", "Conv:S", "Conv:S", "Conv:S"], [96, 320, 512, 256, 256, 128]],

@@ -101,3 +101,32 @@ def test_yolov3_oracle_matches_reference_module():
     np.testing.assert_array_equal(c_, gold["yolo_det_classes"])
     np.testing.assert_allclose(s_, gold["yolo_det_scores"], rtol=1e-4, atol=1e-6)
     np.testing.assert_allclose(b_, gold["yolo_det_boxes"], rtol=1e-4, atol=1e-3)
+
+
+YOLO4_FL = [[3, 4, 5, "Conv:S"], [128, 256, 512, 256]]
+
+
+def test_yolov4_oracle_matches_reference_module():
+    """[r2] oracle.yolov4_resnet_forward (yolo.py:161-323 restated: SPP block, PANModule, extras, heads) vs the
+    reference's own YOLOV4 module outputs (tests/golden/model_yolo4.npz, make_golden_model.py --yolo4), and the box
+    oracle's Decoder on them vs the reference's detections."""
+    from collections import OrderedDict
+    gold = np.load(os.path.join(os.path.dirname(GOLD), "model_yolo4.npz"))
+    sd = synth.synthetic_state_dict("ResNet18", YOLO4_FL, [6] * 4, 20, seed=11, style="test", ssds="YOLOV4")
+    image = [int(v) for v in gold["yolo4_image"]]
+    x = torch.rand((2, 3, image[0], image[1]), generator=torch.Generator().manual_seed(1234))
+    np.testing.assert_array_equal(x.numpy().astype(np.float16), gold["yolo4_x"])
+    with torch.no_grad():
+        loc, conf = M.yolov4_resnet_forward(sd, x, YOLO4_FL, training=False, policy="fp32")
+    assert len(loc) == 4
+    for i, (l, c) in enumerate(zip(loc, conf)):
+        np.testing.assert_allclose(l.numpy(), gold[f"yolo4_loc{i}"], rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(c.numpy()[:, ::7], gold[f"yolo4_conf{i}"], rtol=1e-4, atol=1e-6)
+    strides = [image[1] // c.shape[-1] for c in conf]
+    np.testing.assert_array_equal(strides, gold["yolo4_strides"])
+    anchors = OrderedDict((s, O.generate_anchors(s, [1, 2, 0.5], [2.0, 2.828])) for s in strides)
+    s_, b_, c_ = O.decoder_call([l.numpy() for l in loc], [c.numpy() for c in conf], anchors, 0.01, 0.6, 100, 300,
+                                True, True)
+    np.testing.assert_array_equal(c_, gold["yolo4_det_classes"])
+    np.testing.assert_allclose(s_, gold["yolo4_det_scores"], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(b_, gold["yolo4_det_boxes"], rtol=1e-4, atol=1e-3)
