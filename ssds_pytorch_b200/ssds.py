@@ -7,7 +7,8 @@
 NUM_CLASSES,FEATURE_LAYER,SIZES,ASPECT_RATIOS}, POST_PROCESS.{SCORE_THRESHOLD,IOU_THRESHOLD,
 MAX_DETECTIONS,MAX_DETECTIONS_PER_LEVEL,USE_DIOU,RESCORE_CENTER}, DATASET.PREPROC.{MEAN,STD}; a path to
 a yml file is accepted too.  On the tcgen05 conv stack: SSD / SSDFPN / SSDBiFPN over ResNet18-152 and
-RegNetX032, SSD over MobileNetV2 (model.ENGINES); YOLO/FSSD/FCOS are out of scope.
+RegNetX032, SSD over MobileNetV2, YOLOV3 / YOLOV4 over ResNet (model.ENGINES); FSSD/FCOS are out of scope (SURVEY 2
+rows 9-11).
 `ssds_pytorch_b200.checkpoint.detector_from_checkpoint` builds one from a reference `.pth`.
 
 One process per GPU.  Under torch.distributed each rank runs its shard of the batch and
