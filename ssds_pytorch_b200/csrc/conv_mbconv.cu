@@ -920,7 +920,18 @@ extern "C" int ssdsb_mbconv_bf16(const ssdsb_mbconv_desc* d, const void* x, cons
         const int PM = (PW * PH + BLOCK_M - 1) / BLOCK_M;
         if (PM <= 3 && (!has_expand || 2 * PM * hc_try <= 512 - block_n)) {
           gm.BW = bw; gm.BH = bh; gm.PW = PW; gm.PH = PH; gm.PP = PW * PH; gm.PM = PM;
-          gm.nseg = 1; gm.rs = bh;
+          double best = 1e30;                    // row segmentation of the forced tile: same rule as pick_geometry
+          for (int nseg = 1; nseg <= 4 && nseg <= bh; ++nseg) {
+            const int rs = (bh + nseg - 1) / nseg;
+            const int rounds = (nseg * bw * (hc_try / 4) + MB_DW_THREADS - 1) / MB_DW_THREADS;
+            const double steps = S == 1 ? 3.0 * ((rs + 2 + 2) / 3) : 2.0 * rs + 1.0;
+            const double c = rounds * (steps * 50.0 + 120.0);
+            if (c < best) {
+              best = c;
+              gm.nseg = nseg;
+              gm.rs = rs;
+            }
+          }
         }
       }
     }
