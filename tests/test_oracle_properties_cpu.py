@@ -121,3 +121,19 @@ def test_multibox_loss_selection_counts():
         neg_sel = sel & ~pos
         assert not (neg_sel & (depth[b].reshape(-1) != 0)).any()             # ...nor anything with depth != 0
     assert not (out[1] != 0).any()
+
+
+def test_spp_cascade_identity():
+    """The SPP block of YOLOv4 (reference yolo.py:161-184) pools with kernels 5, 9 and 13 (stride 1, -inf padding);
+    the engine runs three cascaded 5x5 pools instead.  max-pooling composes exactly: 5 o 5 = 9 and 5 o 9 = 13 —
+    checked here on ragged map sizes, including maps smaller than the windows."""
+    import torch
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(3)
+    for (h, w) in [(1, 1), (2, 3), (4, 5), (7, 9), (10, 12), (20, 20)]:
+        x = torch.randn((2, 8, h, w), generator=g)
+        p5 = F.max_pool2d(x, 5, 1, 2)
+        p9 = F.max_pool2d(p5, 5, 1, 2)
+        p13 = F.max_pool2d(p9, 5, 1, 2)
+        assert torch.equal(p9, F.max_pool2d(x, 9, 1, 4))
+        assert torch.equal(p13, F.max_pool2d(x, 13, 1, 6))
