@@ -788,9 +788,7 @@ class _YOLOV3Neck:
 
     def _build_neck(self, sd, feature_layer):
         dev = self.device
-        layers, depths = feature_layer
-        if any(isinstance(d, list) for d in depths):
-            raise NotImplementedError("YOLOV3 with [in, out] depth pairs is not on the tcgen05 conv stack yet")
+        layers, depths = feature_layer        # ([in, out] depth pairs only change channel counts: read off the weights)
         n_back = len(self.outputs)
         self.transforms = [_Conv(sd[f"transforms.{i}.0.weight"], _bn(sd, f"transforms.{i}.1"), None, 1, 1, True, dev)
                            for i in range(n_back - 1)]

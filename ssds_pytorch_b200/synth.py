@@ -159,31 +159,33 @@ def model_shapes(ssds, nets, feature_layer, number_box, num_classes):
 
 
 def yolov3_neck_shapes(feature_layer, number_box, num_classes):
-    """YOLOV3.add_extras (yolo.py:88-160) with int depths: transforms.{i} = ConvBNReLU 3x3 on every backbone level
-    but the last, extras.{i} = ConvBNReLUx2 (levels) / ConvBNReLU stride 2 ('Conv:S'), per-level heads
-    loc.{l} / conf.{l} = Sequential(ConvBNReLU(c, c, 3), Conv2d(c, A*4 | A*C, 3))."""
+    """YOLOV3.add_extras (yolo.py:88-160): transforms.{i} = ConvBNReLU 3x3 on every backbone level but the last,
+    extras.{i} = ConvBNReLUx2 (levels) / ConvBNReLU stride 2 ('Conv:S'), per-level heads loc.{l} / conf.{l} =
+    Sequential(ConvBNReLU(c, c, 3), Conv2d(c, A*4 | A*C, 3)).  A depth is an int d (neck width d/2) or an
+    [in, out] pair (backbone channels `in`, neck width `out`; yolo.py:120-131)."""
     layers, depths = feature_layer
-    if any(isinstance(d, list) for d in depths):
-        raise NotImplementedError("YOLOV3 with [in, out] depth pairs is not packed here")
     ints = [l for l in layers if isinstance(l, int)]
+    d_in = lambda d: d[0] if isinstance(d, list) else d            # backbone channels of the level
+    d_out = lambda d: d[1] if isinstance(d, list) else d // 2      # neck channels of the level
     tr, ex, heads = [], [], []
     in_ch = None
     for idx, (layer, depth) in enumerate(zip(layers, depths)):
         if isinstance(layer, int):
             if layer == ints[-1]:
-                ex.append(("x2", depth, depth // 2))
+                ex.append(("x2", d_in(depth), d_out(depth)))
             else:
                 prev = depths[idx + 1]
-                tr.append((prev // 2, depth // 2))
-                ex.append(("x2", int(depth * 1.5), depth // 2))
-            head_c = depth // 2
+                tr.append((d_out(prev), d_in(depth) // 2))
+                ex.append(("x2", int(d_in(depth) * 1.5), d_out(depth)))
+            head_c = d_out(depth)
+            in_ch = d_in(depth)               # yolo.py:157: the 'Conv:S' chain starts from the RAW last backbone map
         elif layer == "Conv:S":
             ex.append(("s2", in_ch, depth))
             head_c = depth
+            in_ch = depth
         else:
             raise ValueError(layer + " does not support by YOLO")
         heads.append(head_c)
-        in_ch = depth
     out = []
     for i, (cin, cout) in enumerate(tr):
         out.append((f"transforms.{i}.0.weight", (cout, cin, 3, 3))); _bn_keys(out, f"transforms.{i}.1", cout)

@@ -26,12 +26,15 @@ CASES = {
     # the model of the reference's shipped experiments/cfgs/tests/test.yml (YOLOV3 + ResNet18, 80 classes)
     "yolo": ("ResNet18", [[3, 4, 5], [128, 256, 512]], 80, 2, [128, 160]),
     "yolo50x": ("ResNet50", [[3, 4, 5, "Conv:S"], [512, 1024, 2048, 512]], 20, 2, [128, 128]),
+    # [r2] YOLOv3 with [in, out] depth pairs (yolo.py:120-131): neck widths chosen independently of the backbone's
+    "yolo_pairs": ("ResNet18", [[3, 4, 5, "Conv:S"], [[128, 128], [256, 128], [512, 256], 256]], 20, 2, [128, 160]),
     # [r2] YOLOv4 neck (SPP + PAN, yolo.py:161-392)
     "yolo4": ("ResNet18", [[3, 4, 5, "Conv:S"], [128, 256, 512, 256]], 20, 2, [128, 160]),
     "yolo4_50": ("ResNet50", [[3, 4, 5], [512, 1024, 2048]], 80, 1, [192, 192]),
 }
 NBOX = {"yolo": [6, 6, 9]}
-SSDS_OF = {"fpn50": "SSDFPN", "bifpn": "SSDBiFPN", "yolo": "YOLOV3", "yolo50x": "YOLOV3", "yolo4": "YOLOV4",
+SSDS_OF = {"fpn50": "SSDFPN", "bifpn": "SSDBiFPN", "yolo": "YOLOV3", "yolo50x": "YOLOV3", "yolo_pairs": "YOLOV3",
+           "yolo4": "YOLOV4",
            "yolo4_50": "YOLOV4"}
 
 
@@ -58,7 +61,8 @@ def build(tag, S):
     return sd, fl, x, model, image, ncls
 
 
-@pytest.mark.parametrize("tag", ["r18", "r50", "fpn50", "mbv2", "bifpn", "yolo", "yolo50x", "yolo4", "yolo4_50"])
+@pytest.mark.parametrize("tag", ["r18", "r50", "fpn50", "mbv2", "bifpn", "yolo", "yolo50x", "yolo_pairs", "yolo4",
+                                 "yolo4_50"])
 def test_conv_stack_vs_oracle_bf16_policy(env, tag):
     from oracle import model_oracle as M
     sd, fl, x, model, image, ncls = build(tag, env)
@@ -68,6 +72,7 @@ def test_conv_stack_vs_oracle_bf16_policy(env, tag):
     with torch.no_grad():
         fwd = {"fpn50": M.ssdfpn_resnet_forward, "mbv2": M.ssd_mobilenetv2_forward, "bifpn": M.ssdbifpn_forward,
                "yolo": M.yolov3_resnet_forward, "yolo50x": M.yolov3_resnet_forward,
+               "yolo_pairs": M.yolov3_resnet_forward,
                "yolo4": M.yolov4_resnet_forward, "yolo4_50": M.yolov4_resnet_forward}.get(tag, M.ssd_resnet_forward)
         rloc, rconf = fwd(sd_gpu, x.cuda(), fl, training=False, policy="bf16")
     worst_l = worst_c = 0.0

@@ -27,6 +27,8 @@ CASES = {
     "SSDFPN-RegNetX032": ("SSDFPN", "RegNetX032", [[2, 3, 4, "Conv:S", "Conv:S"], [192, 432, 1008, 1008, 256]]),
     "YOLOV3-ResNet18": ("YOLOV3", "ResNet18", [[3, 4, 5], [128, 256, 512]]),            # experiments/cfgs/tests/test.yml
     "YOLOV3-ResNet50+extras": ("YOLOV3", "ResNet50", [[3, 4, 5, "Conv:S"], [512, 1024, 2048, 512]]),
+    "YOLOV3-ResNet18 [in,out] depth pairs": ("YOLOV3", "ResNet18", [[3, 4, 5, "Conv:S"],
+                                                                     [[128, 128], [256, 128], [512, 256], 256]]),
     "YOLOV4-ResNet18+extras": ("YOLOV4", "ResNet18", [[3, 4, 5, "Conv:S"], [128, 256, 512, 256]]),
     "YOLOV4-ResNet50": ("YOLOV4", "ResNet50", [[3, 4, 5], [512, 1024, 2048]]),
 }
